@@ -1,0 +1,152 @@
+"""Shared test plumbing: oracle / host-simulator loaders and frame generators.
+
+Only tests may touch oracle/ (it is the checker, never the product)."""
+import ctypes
+import json
+import os
+import random
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+ERR_FLOOR = (-120) & 0xFFFFFFFF
+
+
+def is_err(r):
+    return int(r) > ERR_FLOOR
+
+
+def err(code):
+    return (-code) & 0xFFFFFFFF
+
+
+class Oracle:
+    def __init__(self):
+        path = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+        src = os.path.join(ROOT, "oracle", "zstd_oracle.cpp")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+            subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+        o = ctypes.CDLL(path)
+        o.oracle_decompress.restype = ctypes.c_uint32
+        o.oracle_decompress.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint32]
+        o.oracle_decompress_diag.restype = ctypes.c_uint32
+        o.oracle_decompress_diag.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_int)]
+        o.oracle_get_decompressed_size.restype = ctypes.c_uint64
+        o.oracle_get_decompressed_size.argtypes = [ctypes.c_char_p, ctypes.c_uint32]
+        o.oracle_xxh64.restype = ctypes.c_uint64
+        o.oracle_xxh64.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint64]
+        o.oracle_default_table.restype = ctypes.c_uint32
+        o.oracle_default_table.argtypes = [ctypes.c_int, ctypes.c_void_p]
+        self.lib = o
+
+    def decompress(self, frame, cap):
+        """-> (result code, bytes or None, overread flag)"""
+        frame = bytes(frame)
+        buf = ctypes.create_string_buffer(max(cap, 1))
+        ov = ctypes.c_int(0)
+        r = self.lib.oracle_decompress_diag(buf, cap, frame, len(frame), ctypes.byref(ov))
+        return r, (buf.raw[:r] if not is_err(r) else None), ov.value
+
+    def get_decompressed_size(self, frame):
+        frame = bytes(frame)
+        return self.lib.oracle_get_decompressed_size(frame, len(frame))
+
+    def xxh64(self, data, seed=0):
+        data = bytes(data)
+        return self.lib.oracle_xxh64(data, len(data), seed)
+
+
+class HostSim:
+    """g++ build of the GPU decoder's __host__ __device__ entropy stages (tests/hostsim/hostsim.cpp)."""
+
+    def __init__(self):
+        d = os.path.join(ROOT, "tests", "hostsim")
+        path = os.path.join(d, "_build", "libhostsim.so")
+        deps = [os.path.join(d, "hostsim.cpp")] + [os.path.join(ROOT, "zstandard_b200", "csrc", f)
+                                                  for f in ("zb_common.cuh", "zb_format.cuh", "zb_decode.cuh")]
+        if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(p) for p in deps):
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-static-libstdc++", "-static-libgcc",
+                            "-o", path, deps[0]], check=True)
+        h = ctypes.CDLL(path)
+        h.hostsim_decompress.restype = ctypes.c_uint32
+        h.hostsim_decompress.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint32,
+                                         ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_int)]
+        self.lib = h
+
+    def decompress(self, frame, cap, oracle):
+        frame = bytes(frame)
+        buf = ctypes.create_string_buffer(max(cap, 1))
+        tr = ctypes.c_uint32(0)
+        nx = ctypes.c_int(0)
+        r = self.lib.hostsim_decompress(buf, cap, frame, len(frame), ctypes.byref(tr), ctypes.byref(nx))
+        out = buf.raw[:r] if not is_err(r) else None
+        if out is not None and nx.value:   # the checksum kernel's job; emulate with the oracle's XXH64
+            if (oracle.xxh64(out) & 0xFFFFFFFF) != int.from_bytes(frame[tr.value:tr.value + 4], "little"):
+                return err(22), None
+        return r, out
+
+
+def golden_vectors():
+    """[(name, frame bytes, expected plaintext)] from the reference's own tests (tests/golden/make_golden.py)."""
+    cs = open(os.path.join(GOLDEN, "csharp_alphabet.zst"), "rb").read()
+    cs_raw = open(os.path.join(GOLDEN, "csharp_alphabet.raw"), "rb").read()
+    jv = open(os.path.join(GOLDEN, "java_abc.zst"), "rb").read()
+    spec = json.load(open(os.path.join(GOLDEN, "java_abc.raw.json")))
+    pat = spec["pattern"].encode()
+    jv_raw = (pat * (spec["length"] // len(pat) + 1))[:spec["length"]]
+    return [("csharp_alphabet", cs, cs_raw), ("java_abc", jv, jv_raw)]
+
+
+def sample_payload(rng, kind, n):
+    from tools import corpus
+    if kind == 0:
+        return corpus.log(n, (rng.randrange(1 << 30), 24)).tobytes()
+    if kind == 1:
+        return corpus.tick(n, (rng.randrange(1 << 30), 25)).tobytes()
+    if kind == 2:
+        return corpus.random_(n, (rng.randrange(1 << 30), 26)).tobytes()
+    if kind == 3:
+        return bytes([rng.choice(b"ab")]) * n
+    if kind == 4:
+        return bytes(rng.choice(b"abcdefgh") for _ in range(n))
+    words = [bytes(rng.choice(b"abcdefghijklmnopqrstuvwxyz ") for _ in range(rng.randint(2, 9))) for _ in range(50)]
+    return b" ".join(rng.choice(words) for _ in range(n // 5 + 1))[:n]
+
+
+SIZES = [0, 1, 2, 5, 17, 100, 1000, 4096, 5000, 65536, 70000, 131072, 200000, 300000]
+LEVELS = [1, 2, 3, 3, 3, 5, 9, 19, -1, -5]
+
+
+def make_frames(seed, count, sizes=SIZES, levels=LEVELS):
+    """Deterministic mix of libzstd frames: all literal modes, table modes, raw/RLE blocks, multi-block, +/- checksum."""
+    from tools import zstd_ref
+    rng = random.Random(seed)
+    out = []
+    for t in range(count):
+        n = rng.choice(sizes)
+        data = sample_payload(rng, t % 6, n)
+        frame = zstd_ref.compress(data, rng.choice(levels), checksum=rng.random() < 0.7, content_size=rng.random() < 0.8)
+        out.append((frame, data))
+    return out
+
+
+def mutate(rng, frame):
+    b = bytearray(frame)
+    mode = rng.randrange(4)
+    if mode == 0:
+        i = rng.randrange(len(b)); b[i] ^= 1 << rng.randrange(8)
+    elif mode == 1:
+        b = b[:rng.randrange(len(b))]
+    elif mode == 2:
+        for _ in range(3):
+            i = rng.randrange(len(b)); b[i] = rng.randrange(256)
+    else:
+        i = rng.randrange(min(len(b), 40)); b[i] ^= 1 << rng.randrange(8)
+    return bytes(b)
+
+
+def skippable(payload, nibble=0):
+    return (0x184D2A50 + nibble).to_bytes(4, "little") + len(payload).to_bytes(4, "little") + payload

@@ -1,0 +1,175 @@
+"""Parity tests proper: the CUDA decode path, called through the C ABI, against the oracle.
+
+Bit-exact bar: decoded bytes and result codes equal the oracle's on the same inputs (integer/byte work, no
+tolerance).  The one documented deviation (DESIGN.md "over-read") is asserted explicitly where it can occur."""
+import random
+
+import numpy as np
+import pytest
+
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_decode(ctx, frames_and_caps):
+    srcs = [f for f, _ in frames_and_caps]
+    dsts = [np.zeros(max(c, 1), dtype=np.uint8)[:c] for _, c in frames_and_caps]
+    res = ctx.decompress_batch(srcs, dsts)
+    return res, dsts
+
+
+def test_reference_golden_vectors_through_public_api(gpu_ctx):
+    # same assertions as csharp/test/TestDecompress.cs:91-98, through the mirror of ZStdDecompress
+    import zstandard_b200 as zb
+    for name, frame, raw in helpers.golden_vectors():
+        n = zb.ZStdDecompress.GetDecompressedSize(frame)
+        assert n == len(raw), name
+        out = np.zeros(n, dtype=np.uint8)
+        r = zb.ZStdDecompress.Decompress(out, frame)
+        assert r == n and out.tobytes() == raw, name
+        out2 = np.zeros(n + 100, dtype=np.uint8)
+        assert zb.ZStdDecompress.Decompress(out2, n + 100, frame, len(frame)) == n and out2[:n].tobytes() == raw
+
+
+def test_batch_matches_oracle_on_valid_frames(gpu_ctx, oracle):
+    frames = helpers.make_frames(301, 300)
+    items = []
+    for frame, data in frames:
+        n = len(data)
+        for cap in (n, n + 13, max(0, n - 1)):
+            items.append((frame, cap))
+    res, dsts = _gpu_decode(gpu_ctx, items)
+    for (frame, cap), r, d in zip(items, res, dsts):
+        ro, oo, _ = oracle.decompress(frame, cap)
+        assert int(r) == ro, (len(frame), cap, hex(int(r)), hex(ro))
+        if not helpers.is_err(ro):
+            assert d[:ro].tobytes() == oo
+
+
+def test_edge_cases(gpu_ctx, oracle):
+    (f1, d1), (f2, d2) = helpers.make_frames(9, 2, sizes=[3000, 70000])
+    bad_sum = bytearray(helpers.make_frames(5, 8, sizes=[5000], levels=[3])[1][0])
+    cases = [
+        (b"", 10),                                                    # empty input -> 0
+        (b"\x28\xb5", 10),                                            # shorter than a frame prefix
+        (helpers.skippable(b"hello"), 10),                            # only a skippable frame -> 0
+        (helpers.skippable(b"hello") + f1, len(d1)),                  # skippable then frame
+        (f1 + helpers.skippable(b"tail" * 5), len(d1)),               # frame then skippable
+        (f1 + b"\x00", len(d1)),                                      # 1 trailing byte -> srcSize_wrong
+        (f1 + b"\x00" * 8, len(d1)),                                  # trailing garbage -> prefix_unknown
+        (b"\x00" * 8 + f1, len(d1)),                                  # leading garbage -> prefix_unknown
+        (f1[:len(f1) // 2], len(d1)),                                 # truncated
+        (f2, len(d2) - 1), (f2, 0),                                   # dst too small
+    ]
+    for frame, data in helpers.make_frames(5, 8, sizes=[5000]):
+        f = bytearray(frame); f[4] |= 0x08
+        cases.append((bytes(f), len(data)))                           # reserved bit
+    res, dsts = _gpu_decode(gpu_ctx, cases)
+    for (frame, cap), r, d in zip(cases, res, dsts):
+        ro, oo, _ = oracle.decompress(frame, cap)
+        assert int(r) == ro, (frame[:12].hex(), cap, hex(int(r)), hex(ro))
+        if not helpers.is_err(ro):
+            assert d[:ro].tobytes() == oo
+    del bad_sum
+
+
+def test_checksum_mismatch_is_reported(gpu_ctx, oracle):
+    from tools import zstd_ref
+    rng = random.Random(4)
+    items = []
+    for n in (1, 31, 32, 33, 1000, 65536, 70001):
+        data = helpers.sample_payload(rng, 0, n)
+        f = bytearray(zstd_ref.compress(data, 3, checksum=True))
+        items.append((bytes(f), n))
+        f[-1] ^= 0x5A
+        items.append((bytes(f), n))
+    res, _ = _gpu_decode(gpu_ctx, items)
+    for k, ((frame, cap), r) in enumerate(zip(items, res)):
+        ro, _, _ = oracle.decompress(frame, cap)
+        assert int(r) == ro
+        assert helpers.is_err(ro) == bool(k & 1)
+
+
+def test_fuzzed_frames_same_verdict_and_bytes(gpu_ctx, oracle):
+    rng = random.Random(78)
+    frames = helpers.make_frames(302, 150)
+    items = []
+    for frame, data in frames:
+        if len(frame) < 12:
+            continue
+        for _ in range(8):
+            items.append((helpers.mutate(rng, frame), len(data) + rng.choice([0, 0, 5])))
+    res, dsts = _gpu_decode(gpu_ctx, items)
+    n_dev = 0
+    for (frame, cap), r, d in zip(items, res, dsts):
+        ro, oo, over = oracle.decompress(frame, cap)
+        eo, eg = helpers.is_err(ro), helpers.is_err(int(r))
+        if eo != eg:
+            # documented deviation: reference accepts a last sequence read past the stream start
+            assert over and eg and not eo, (hex(ro), hex(int(r)))
+            n_dev += 1
+        elif not eo:
+            assert int(r) == ro and d[:ro].tobytes() == oo
+    assert n_dev <= len(items) // 50
+
+
+def test_one_bad_item_does_not_poison_the_batch(gpu_ctx, oracle):
+    frames = helpers.make_frames(303, 40, sizes=[4096, 65536])
+    items = [(f, len(d)) for f, d in frames]
+    items[7] = (b"\xff" * 100, 100)
+    items[19] = (items[19][0][:20], items[19][1])
+    res, dsts = _gpu_decode(gpu_ctx, items)
+    for k, ((frame, cap), r, d) in enumerate(zip(items, res, dsts)):
+        ro, oo, _ = oracle.decompress(frame, cap)
+        assert int(r) == ro
+        if k not in (7, 19):
+            assert not helpers.is_err(ro) and d[:ro].tobytes() == oo
+
+
+def test_device_pointer_api(gpu_ctx, oracle):
+    import torch
+    frames = helpers.make_frames(304, 64, sizes=[100, 4096, 65536, 131072])
+    blob = b"".join(f for f, _ in frames)
+    soff = np.cumsum([0] + [len(f) for f, _ in frames])[:-1].astype(np.uint64)
+    ssz = np.array([len(f) for f, _ in frames], dtype=np.uint32)
+    cap = np.array([len(d) for _, d in frames], dtype=np.uint32)
+    doff = np.cumsum([0] + [(int(c) + 15) // 16 * 16 for c in cap])[:-1].astype(np.uint64)
+    dev = torch.device("cuda:0")
+    t_src = torch.frombuffer(bytearray(blob) + bytearray(16), dtype=torch.uint8).to(dev)
+    t_dst = torch.zeros(int(doff[-1]) + int(cap[-1]) + 64, dtype=torch.uint8, device=dev)
+    t_soff = torch.from_numpy(soff.view(np.int64)).to(dev)
+    t_doff = torch.from_numpy(doff.view(np.int64)).to(dev)
+    t_ssz = torch.from_numpy(ssz.view(np.int32)).to(dev)
+    t_cap = torch.from_numpy(cap.view(np.int32)).to(dev)
+    t_res = torch.zeros(len(frames), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    gpu_ctx.decompress_batch_device(t_src.data_ptr(), t_soff.data_ptr(), t_ssz.data_ptr(), t_dst.data_ptr(), t_doff.data_ptr(),
+                                    t_cap.data_ptr(), t_res.data_ptr(), len(frames), stream=stream)
+    torch.cuda.synchronize()
+    res = t_res.cpu().numpy().view(np.uint32)
+    out = t_dst.cpu().numpy()
+    for k, (frame, data) in enumerate(frames):
+        assert int(res[k]) == len(data)
+        assert out[int(doff[k]):int(doff[k]) + len(data)].tobytes() == data
+    ms = gpu_ctx.decompress_batch_device_timed(t_src.data_ptr(), t_soff.data_ptr(), t_ssz.data_ptr(), t_dst.data_ptr(), t_doff.data_ptr(),
+                                               t_cap.data_ptr(), t_res.data_ptr(), len(frames), stream=stream)
+    assert set(ms) == {"k_parse", "k_huf", "k_seq", "k_exec", "k_xxh"} and all(v >= 0 for v in ms.values())
+
+
+@pytest.mark.parametrize("kind,chunk", [("log", 65536), ("tick", 65536), ("mixed", 65536), ("tick", 4096), ("log", 1 << 20)])
+def test_full_size_round_trip_properties(gpu_ctx, kind, chunk):
+    """Size-independent properties at bench-like sizes: every frame decodes to exactly its chunk of the corpus
+    (libzstd frames carry XXH64 checksums, which the GPU path verifies itself) — 32 MiB per case."""
+    from tools import corpus, zstd_ref
+    total = 32 << 20
+    raw = corpus.make(kind, total)
+    blob, off = zstd_ref.compress_chunks(raw, chunk, level=3, checksum=True)
+    n = len(off) - 1
+    srcs = [blob[int(off[i]):int(off[i + 1])] for i in range(n)]
+    out = np.zeros(total, dtype=np.uint8)
+    dsts = [out[i * chunk:min(total, (i + 1) * chunk)] for i in range(n)]
+    res = gpu_ctx.decompress_batch(srcs, dsts)
+    want = np.array([d.size for d in dsts], dtype=np.uint32)
+    assert (res == want).all(), [hex(int(r)) for r in res[res != want][:5]]
+    assert (out == raw).all()

@@ -1,0 +1,426 @@
+// decode_kernels.cu — sm_100a kernels of the batched zstd frame decoder.
+//
+// Pipeline per batch (all on one stream unless the host overlaps sub-batches):
+//   k_parse : thread / item     frame header, skippable frames, early verdicts      (ZStdDecompress.cs:2096-2160, 389-499)
+//   k_huf   : 4 lanes / frame   Huffman literals -> literal scratch                  (HufDecompress.cs:117-358)
+//   k_seq   : thread / frame    FSE tables + sequence bitstream -> 8-byte records    (ZStdDecompress.cs:958-1180, 1443-1608)
+//   k_exec  : warp / frame      literal copy + match copy into dst, raw/RLE blocks   (ZStdDecompress.cs:1212-1352, 1599-1605, 2033-2091)
+//   k_xxh   : 4 lanes / frame   XXH64 content checksum                               (XxHash.cs:896-1161)
+#include "zb_decode.cuh"
+#include "decode_kernels.cuh"
+
+namespace zb {
+
+// -----------------------------------------------------------------------------------------------
+// scratch addressing shared by the stages (see DESIGN.md "HBM layout")
+// -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ u8* lit_region(const DecodeArgs& a, u32 f) { return a.lit_arena + (a.dst_off[f] & ~15ull) + 64ull * f; }
+__device__ __forceinline__ u64 lit_capacity(u32 cap) { return (u64)cap + 40; }
+__device__ __forceinline__ SeqRec* seq_region(const DecodeArgs& a, u32 f) { return a.seq_arena + 2 * (a.dst_off[f] / 3) + 32ull * f; }
+
+// =================================================================================================
+// k_parse
+// =================================================================================================
+__global__ void __launch_bounds__(128) k_parse(DecodeArgs a) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  FrameInfo fi; u32 r = 0;
+  bool go = parse_item(a.src_base + a.src_off[i], a.src_size[i], fi, &r);
+  a.info[i] = fi;
+  if (!go) a.result[i] = r;
+}
+
+// =================================================================================================
+// k_huf : one warp per CTA, 8 frames per warp, lanes 4f..4f+3 own the 4 streams of frame f
+// =================================================================================================
+struct HufSmem {
+  u16 table[8][1 << HUF_LOG_MAX];
+  HufBuildWk wk[8];
+};
+
+__global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  HufSmem& sm = *reinterpret_cast<HufSmem*>(smem_raw);
+  const u32 lane = threadIdx.x, sub = lane & 3, slot = lane >> 2;
+  const u32 f = blockIdx.x * 8 + slot;
+  const unsigned gmask = 0xFu << (slot * 4);
+  bool active = f < a.n;
+  FrameInfo fi;
+  if (active) { fi = a.info[f]; if (fi.flags & FI_DONE) active = false; }
+  if (!active) return;   // whole 4-lane group leaves together; group syncs below use gmask
+  const u8* src = a.src_base + a.src_off[f]; const u32 size = a.src_size[f];
+  u8* lit = lit_region(a, f); const u64 litCap = lit_capacity(a.dst_cap[f]);
+  u16* dt = sm.table[slot]; HufBuildWk& wk = sm.wk[slot];
+  u32 pos = fi.body_off, blk = 0; u64 litRun = 0;
+  u32 tableLog = 0; bool haveTable = false;
+  u32 errBlock = 0xFFFFFFFFu, errCode = 0;
+  while (true) {
+    BlockHdr bh;
+    if (read_block_hdr(src + pos, size - pos, bh)) break;
+    pos += 3;
+    if (bh.type == 2) {
+      const u8* bp = src + pos; u32 bsz = bh.csize;
+      if (bsz >= BLOCKSIZE_MAX) break;
+      LitHdr lh; bool needs;
+      if (read_lit_hdr(bp, bsz, lh, &needs)) break;
+      if (lh.type >= 2) {
+        if (lh.type == 3 && !haveTable) break;                                     // dictionary_corrupted, reported by k_exec
+        bool ok = true; u32 code = ZE_corruption_detected;
+        const u8* body = bp + lh.lhSize; u32 bodySize = lh.litCSize;
+        if (litRun + lh.litSize + 3 > litCap) { ok = false; code = ZE_dstSize_tooSmall; }
+        if (ok && lh.type == 2) {
+          if (!lh.single && (lh.litSize == 0 || bodySize == 0)) ok = false;       // HufDecompress.cs:1211-1212
+          u32 hdr = 0, nbSym = 0, tl = 0;
+          if (ok) {
+            u32 e = 0;
+            if (sub == 0) {
+              e = huf_read_weights(body, bodySize, wk, &hdr, &tl, &nbSym);
+              if (!e && hdr >= bodySize) e = ZE_srcSize_wrong;                     // HufDecompress.cs:1193
+            }
+            __syncwarp(gmask);
+            e = __shfl_sync(gmask, e, slot * 4); hdr = __shfl_sync(gmask, hdr, slot * 4);
+            tl = __shfl_sync(gmask, tl, slot * 4); nbSym = __shfl_sync(gmask, nbSym, slot * 4);
+            if (e) ok = false;
+          }
+          if (ok) {
+            huf_fill_table(dt, wk, tl, nbSym, sub, 4);
+            __syncwarp(gmask);
+            tableLog = tl; haveTable = true;
+            body += hdr; bodySize -= hdr;
+          }
+        }
+        if (ok) {
+          bool good = true;
+          if (lh.single) {
+            if (sub == 0) good = huf_decode_stream(body, bodySize, lit + litRun, lh.litSize, dt, tableLog);   // HufDecompress.cs:247-264
+          } else {
+            HufStream st;
+            good = huf_split4(body, bodySize, lh.litSize, sub, st);
+            if (good) good = huf_decode_stream(st.src, st.len, lit + litRun + st.outOfs, st.count, dt, tableLog);
+          }
+          unsigned okmask = __ballot_sync(gmask, good);
+          if ((okmask & gmask) != gmask) ok = false;
+        }
+        if (!ok) { errBlock = blk; errCode = code; break; }
+        litRun += lh.litSize;
+      }
+    }
+    pos += bh.csize; blk++;
+    if (bh.last) break;
+  }
+  if (sub == 0 && errBlock != 0xFFFFFFFFu) { a.info[f].huf_err_block = errBlock; a.info[f].huf_err_code = errCode; }
+}
+
+// =================================================================================================
+// k_seq : one warp per CTA, one frame per lane, tables bank-interleaved across lanes
+// =================================================================================================
+struct SeqSmem {
+  u32 ll[512][32];
+  u32 ml[512][32];
+  u32 of[256][32];
+  u32 defLL[64], defOF[32], defML[64];
+  u32 llBase[36], mlBase[53];
+};
+
+__global__ void __launch_bounds__(32) k_seq(DecodeArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SeqSmem& sm = *reinterpret_cast<SeqSmem*>(smem_raw);
+  const u32 lane = threadIdx.x;
+  // predefined tables + base LUTs, built once per CTA
+  if (lane < 3) {
+    u16 symbolNext[53]; s16 norm[53];
+    if (lane == 0) { for (int i = 0; i < 36; i++) norm[i] = kLLnorm[i]; build_seq_table(sm.defLL, 1, norm, 35, 6, KIND_LL, symbolNext); }
+    if (lane == 1) { for (int i = 0; i < 29; i++) norm[i] = kOFnorm[i]; build_seq_table(sm.defOF, 1, norm, 28, 5, KIND_OF, symbolNext); }
+    if (lane == 2) { for (int i = 0; i < 53; i++) norm[i] = kMLnorm[i]; build_seq_table(sm.defML, 1, norm, 52, 6, KIND_ML, symbolNext); }
+  }
+  for (u32 i = lane; i < 36; i += 32) sm.llBase[i] = kLLbase[i];
+  for (u32 i = lane; i < 53; i += 32) sm.mlBase[i] = kMLbase[i];
+  __syncwarp();
+  const u32 f = blockIdx.x * 32 + lane;
+  if (f >= a.n) return;
+  FrameInfo fi = a.info[f];
+  if (fi.flags & FI_DONE) return;
+  SeqTableSet T;
+  T.space[KIND_LL] = &sm.ll[0][lane]; T.space[KIND_ML] = &sm.ml[0][lane]; T.space[KIND_OF] = &sm.of[0][lane]; T.stride = 32;
+  T.defs[KIND_LL] = sm.defLL; T.defs[KIND_OF] = sm.defOF; T.defs[KIND_ML] = sm.defML;
+  SeqFrameOut res;
+  seq_decode_frame(a.src_base + a.src_off[f], a.src_size[f], fi.body_off, T, seq_region(a, f), seq_capacity(a.dst_cap[f]), res, sm.llBase, sm.mlBase);
+  if (res.err_block != 0xFFFFFFFFu) {
+    a.info[f].seq_err_block = res.err_block; a.info[f].seq_err_code = res.err_code; a.info[f].seq_err_index = res.err_index;
+  }
+}
+
+// =================================================================================================
+// warp-cooperative byte movers
+// =================================================================================================
+// dst and src must not overlap.  All 32 lanes call with identical arguments.
+__device__ __forceinline__ void warp_copy(u8* dst, const u8* src, u32 n, u32 lane) {
+  if (n < 128) { for (u32 i = lane; i < n; i += 32) dst[i] = src[i]; return; }
+  u32 head = (u32)(-(intptr_t)dst) & 15;
+  if (lane < head) dst[lane] = src[lane];
+  dst += head; src += head; n -= head;
+  u32 body = n & ~15u;
+  if ((((uintptr_t)src) & 15) == 0) {
+    const uint4* s = (const uint4*)src; uint4* d = (uint4*)dst;
+    for (u32 i = lane; i < body / 16; i += 32) d[i] = s[i];
+  } else {
+    // dst is 16-byte aligned, src is not: rebuild each 16-byte vector from five aligned 4-byte words of src
+    const u32 sh = ((u32)(uintptr_t)src & 3) * 8;
+    const u32* s = (const u32*)((uintptr_t)src & ~(uintptr_t)3); uint4* d = (uint4*)dst;
+    for (u32 i = lane; i < body / 16; i += 32) {
+      const u32* p = s + 4 * i;
+      u32 w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3], w4 = sh ? p[4] : 0;
+      d[i] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+    }
+  }
+  for (u32 i = body + lane; i < n; i += 32) dst[i] = src[i];
+}
+__device__ __forceinline__ void warp_fill(u8* dst, u8 v, u32 n, u32 lane) {
+  if (n < 128) { for (u32 i = lane; i < n; i += 32) dst[i] = v; return; }
+  u32 head = (u32)(-(intptr_t)dst) & 15;
+  if (lane < head) dst[lane] = v;
+  dst += head; n -= head;
+  u32 body = n & ~15u, w = v * 0x01010101u;
+  uint4* d = (uint4*)dst; uint4 vv = make_uint4(w, w, w, w);
+  for (u32 i = lane; i < body / 16; i += 32) d[i] = vv;
+  for (u32 i = body + lane; i < n; i += 32) dst[i] = v;
+}
+
+__device__ __forceinline__ u32 warp_incl_scan(u32 v, u32 lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= (u32)d) v += t; }
+  return v;
+}
+
+// =================================================================================================
+// k_exec : one warp per frame
+// =================================================================================================
+__global__ void __launch_bounds__(EXEC_THREADS) k_exec(DecodeArgs a) {
+  const u32 lane = threadIdx.x & 31;
+  const u32 f = (blockIdx.x * EXEC_THREADS + threadIdx.x) >> 5;
+  if (f >= a.n) return;
+  FrameInfo fi = a.info[f];
+  if (fi.flags & FI_DONE) return;
+  const u8* src = a.src_base + a.src_off[f]; const u32 size = a.src_size[f];
+  u8* dst = a.dst_base + a.dst_off[f]; const u64 cap = a.dst_cap[f];
+  const u8* litScratch = lit_region(a, f);
+  const SeqRec* recs = seq_region(a, f);
+  u32 pos = fi.body_off, blk = 0; u64 op = 0, litRun = 0, recRun = 0;
+  bool litEntropy = false; u32 err = 0;
+  while (true) {
+    BlockHdr bh;
+    err = read_block_hdr(src + pos, size - pos, bh);
+    if (err) break;
+    pos += 3;
+    if (bh.type == 0) {                                                            // raw, :662-667
+      if (bh.csize > cap - op) { err = ZE_dstSize_tooSmall; break; }
+      warp_copy(dst + op, src + pos, bh.csize, lane); op += bh.csize;
+    } else if (bh.type == 1) {                                                     // RLE, :1945-1950
+      if (bh.orig > cap - op) { err = ZE_dstSize_tooSmall; break; }
+      warp_fill(dst + op, src[pos], bh.orig, lane); op += bh.orig;
+    } else {
+      const u8* bp = src + pos; const u32 bsz = bh.csize;
+      if (bsz >= BLOCKSIZE_MAX) { err = ZE_srcSize_wrong; break; }                 // :1880
+      LitHdr lh; bool needs;
+      u32 e = read_lit_hdr(bp, bsz, lh, &needs);
+      if (needs && !litEntropy) { err = ZE_dictionary_corrupted; break; }          // :696-697
+      if (e) { err = e; break; }
+      const u8* lit; u32 rleByte = 0; bool isRle = false;
+      if (lh.type >= 2) {
+        if (fi.huf_err_block == blk) { err = fi.huf_err_code; break; }             // :742 (all Huffman failures -> corruption_detected)
+        litEntropy = true; lit = litScratch + litRun; litRun += lh.litSize;
+      } else if (lh.type == 0) lit = bp + lh.lhSize;
+      else { lit = nullptr; isRle = true; rleByte = bp[lh.lhSize]; }
+      const u32 litSize = lh.litSize;
+      const u8* sp = bp + lh.consumed; const u32 ssz = bsz - lh.consumed;
+      u32 nbSeq, modes, hdr;
+      e = read_seq_count(sp, ssz, &nbSeq, &modes, &hdr);
+      if (e) { err = e; break; }
+      if (fi.seq_err_block == blk && fi.seq_err_index == 0xFFFFFFFFu) { err = fi.seq_err_code; break; }
+      u64 litPos = 0;
+      if (nbSeq) {
+        const SeqRec* r = recs + recRun; bool done = false;
+        while (!done) {
+          SeqRec rec = r[lane];
+          unsigned term = __ballot_sync(0xFFFFFFFFu, rec.x == 0);
+          u32 cnt = term ? (u32)__ffs(term) - 1 : 32; done = term != 0;
+          bool valid = lane < cnt;
+          u32 ll = valid ? (rec.y & 0xFFFF) : 0, ml = valid ? (rec.y >> 16) : 0, off = rec.x;
+          u32 tot = ll + ml;
+          u32 incl = warp_incl_scan(tot, lane), lincl = warp_incl_scan(ll, lane);
+          u64 myop = op + (incl - tot);                 // output position of this sequence's literals
+          u64 mpos = myop + ll;                         // ... and of its match
+          // checks in the reference's order (:1278, :1279, :1290-1294)
+          bool e1 = valid && (myop + tot > cap);
+          bool e2 = valid && (litPos + lincl > litSize);
+          bool e3 = valid && ((u64)off > mpos);
+          unsigned bad = __ballot_sync(0xFFFFFFFFu, e1 | e2 | e3);
+          if (bad) {
+            u32 first = (u32)__ffs(bad) - 1;
+            u32 code = e1 ? ZE_dstSize_tooSmall : ZE_corruption_detected;
+            err = __shfl_sync(0xFFFFFFFFu, code, first);
+            break;
+          }
+          // ---- literals of the whole group, flattened over lanes ----
+          u32 Lg = __shfl_sync(0xFFFFFFFFu, lincl, 31);
+          u32 lexcl = lincl - ll; u32 myop32 = (u32)(myop - op);
+          for (u32 t0 = 0; t0 < Lg; t0 += 32) {
+            u32 t = t0 + lane; u32 j = 0;
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) { u32 v = __shfl_sync(0xFFFFFFFFu, lincl, (j + s - 1) & 31); if (v <= t) j += s; }
+            j &= 31;
+            u32 dj = __shfl_sync(0xFFFFFFFFu, myop32, j), lj = __shfl_sync(0xFFFFFFFFu, lexcl, j);
+            if (t < Lg) dst[op + dj + (t - lj)] = isRle ? (u8)rleByte : lit[litPos + t];
+          }
+          __syncwarp();
+          // ---- matches, in order ----
+          for (u32 j = 0; j < cnt; j++) {
+            u32 mj = __shfl_sync(0xFFFFFFFFu, ml, j);
+            if (!mj) continue;
+            u32 oj = __shfl_sync(0xFFFFFFFFu, off, j);
+            u64 dj = __shfl_sync(0xFFFFFFFFu, (unsigned long long)mpos, j);
+            u8* d = dst + dj; const u8* s = d - oj;
+            if (oj >= mj) {
+              for (u32 i = lane; i < mj; i += 32) d[i] = s[i];
+            } else if (oj >= 32) {
+              for (u32 i0 = 0; i0 < mj; i0 += 32) { u32 i = i0 + lane; if (i < mj) d[i] = s[i]; __syncwarp(); }
+            } else {
+              u32 r0 = lane % oj, stepm = 32 % oj;
+              for (u32 i = lane; i < mj; i += 32) { d[i] = s[r0]; r0 += stepm; if (r0 >= oj) r0 -= oj; }
+            }
+            __syncwarp();
+          }
+          op += __shfl_sync(0xFFFFFFFFu, incl, 31); litPos += Lg;
+          r += cnt + (done ? 1 : 0);
+        }
+        if (err) break;
+        recRun = (u64)(r - recs);
+        if (fi.seq_err_block == blk) { err = fi.seq_err_code; break; }             // :1594 after the decodable prefix
+      }
+      // last literals (:1599-1605)
+      u64 lastLL = litSize - litPos;
+      if (lastLL > cap - op) { err = ZE_dstSize_tooSmall; break; }
+      if (isRle) warp_fill(dst + op, (u8)rleByte, (u32)lastLL, lane); else warp_copy(dst + op, lit + litPos, (u32)lastLL, lane);
+      op += lastLL;
+      __syncwarp();
+    }
+    pos += bh.csize; blk++;
+    if (bh.last) break;
+  }
+  // ---- frame epilogue (:2069-2085) and the multi-frame loop tail (:2111-2157) ----
+  bool needXxh = false; u32 trailer = 0;
+  if (!err) {
+    if ((fi.flags & FI_FCS_KNOWN) && op != fi.fcs) err = ZE_corruption_detected;
+    else if (fi.flags & FI_CHECKSUM) {
+      if (size - pos < 4) err = ZE_checksum_wrong; else { trailer = pos; pos += 4; needXxh = true; }
+    }
+  }
+  u32 tailErr = 0;
+  if (!err) {
+    while (true) {
+      u32 rem = size - pos;
+      if (rem < 5) { if (rem) tailErr = ZE_srcSize_wrong; break; }
+      u32 magic = ld32(src + pos);
+      if (magic == MAGIC) { tailErr = ZE_GENERIC; break; }                         // second data frame in one item: see DESIGN.md (host splits)
+      if ((magic & 0xFFFFFFF0u) != MAGIC_SKIP) { tailErr = ZE_prefix_unknown; break; }
+      if (rem < 8) { tailErr = ZE_srcSize_wrong; break; }
+      u32 skip = ld32(src + pos + 4) + 8u;
+      if (rem < skip) { tailErr = ZE_srcSize_wrong; break; }
+      pos += skip;
+    }
+  }
+  if (lane == 0) {
+    u32 res = err ? zerr(err) : (tailErr ? zerr(tailErr) : (u32)op);
+    a.result[f] = res;
+    a.info[f].trailer_off = trailer; a.info[f].decoded = (u32)op;
+    a.info[f].flags = fi.flags | (needXxh ? FI_NEED_XXH : 0);
+  }
+}
+
+// =================================================================================================
+// k_xxh : XXH64(seed 0) of the decoded bytes, 4 lanes per frame (one accumulator each)
+// =================================================================================================
+#define XP1 11400714785074694791ull
+#define XP2 14029467366897019727ull
+#define XP3 1609587929392839161ull
+#define XP4 9650029242287828579ull
+#define XP5 2870177450012600261ull
+__device__ __forceinline__ u64 rotl64(u64 x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ __forceinline__ u64 xxh_round(u64 acc, u64 in) { acc += in * XP2; acc = rotl64(acc, 31); return acc * XP1; }
+__device__ __forceinline__ u64 xxh_merge(u64 acc, u64 v) { v = xxh_round(0, v); acc ^= v; return acc * XP1 + XP4; }
+__device__ __forceinline__ u64 ldg64u(const u8* p) {   // unaligned 8-byte load from aligned words
+  if ((((uintptr_t)p) & 7) == 0) return *(const u64*)p;
+  const u32* w = (const u32*)((uintptr_t)p & ~(uintptr_t)3); u32 sh = ((u32)(uintptr_t)p & 3) * 8;
+  u32 a0 = w[0], a1 = w[1], a2 = sh ? w[2] : 0;
+  return ((u64)__funnelshift_r(a1, a2, sh) << 32) | __funnelshift_r(a0, a1, sh);
+}
+
+__device__ u64 xxh64_group(const u8* p, u64 len, u32 sub, unsigned gmask, u32 lead) {
+  u64 h;
+  const u8* tail = p;
+  if (len >= 32) {
+    u64 v = sub == 0 ? XP1 + XP2 : (sub == 1 ? XP2 : (sub == 2 ? 0 : 0 - XP1));
+    u64 stripes = len / 32;
+    const u8* q = p + 8 * sub;
+    for (u64 i = 0; i < stripes; i++) { v = xxh_round(v, ldg64u(q)); q += 32; }
+    u64 v1 = __shfl_sync(gmask, v, lead), v2 = __shfl_sync(gmask, v, lead + 1), v3 = __shfl_sync(gmask, v, lead + 2), v4 = __shfl_sync(gmask, v, lead + 3);
+    h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
+    h = xxh_merge(h, v1); h = xxh_merge(h, v2); h = xxh_merge(h, v3); h = xxh_merge(h, v4);
+    tail = p + stripes * 32;
+  } else h = XP5;   // seed(0) + P5
+  h += len;
+  const u8* end = p + len;
+  while (tail + 8 <= end) { h ^= xxh_round(0, ldg64u(tail)); h = rotl64(h, 27) * XP1 + XP4; tail += 8; }
+  if (tail + 4 <= end) { h ^= (u64)ld32(tail) * XP1; h = rotl64(h, 23) * XP2 + XP3; tail += 4; }
+  while (tail < end) { h ^= (*tail) * XP5; h = rotl64(h, 11) * XP1; tail++; }
+  h ^= h >> 33; h *= XP2; h ^= h >> 29; h *= XP3; h ^= h >> 32;
+  return h;
+}
+
+__global__ void __launch_bounds__(128) k_xxh(DecodeArgs a) {
+  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 f = t >> 2, sub = t & 3, lane = threadIdx.x & 31;
+  const unsigned gmask = 0xFu << (lane & ~3u);
+  if (f >= a.n) return;
+  FrameInfo fi = a.info[f];
+  if (!(fi.flags & FI_NEED_XXH)) return;
+  const u8* dst = a.dst_base + a.dst_off[f];
+  u64 h = xxh64_group(dst, fi.decoded, sub, gmask, lane & ~3u);
+  if (sub == 0) {
+    const u8* src = a.src_base + a.src_off[f];
+    if ((u32)h != ld32(src + fi.trailer_off)) a.result[f] = zerr(ZE_checksum_wrong);   // :2078-2082
+  }
+}
+
+// =================================================================================================
+// launch
+// =================================================================================================
+size_t decode_lit_arena_bytes(u64 max_dst_bytes, u64 max_items) { return (size_t)(max_dst_bytes + 64 * (max_items + 2) + 256); }
+size_t decode_seq_arena_bytes(u64 max_dst_bytes, u64 max_items) { return (size_t)((2 * (max_dst_bytes / 3) + 32 * (max_items + 2) + 64) * sizeof(SeqRec)); }
+
+cudaError_t decode_configure() {
+  cudaError_t e = cudaFuncSetAttribute(k_huf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HufSmem));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqSmem));
+}
+
+const char* const kDecodeKernelNames[DECODE_KERNELS] = {"k_parse", "k_huf", "k_seq", "k_exec", "k_xxh"};
+
+cudaError_t decode_launch(const DecodeArgs& a, cudaStream_t st, int* launches, cudaEvent_t* marks) {
+  if (a.n == 0) return cudaSuccess;
+  if (marks) cudaEventRecord(marks[0], st);
+  k_parse<<<(a.n + 127) / 128, 128, 0, st>>>(a);
+  if (marks) cudaEventRecord(marks[1], st);
+  k_huf<<<(a.n + 7) / 8, 32, sizeof(HufSmem), st>>>(a);
+  if (marks) cudaEventRecord(marks[2], st);
+  k_seq<<<(a.n + 31) / 32, 32, sizeof(SeqSmem), st>>>(a);
+  if (marks) cudaEventRecord(marks[3], st);
+  k_exec<<<(a.n + (EXEC_THREADS / 32) - 1) / (EXEC_THREADS / 32), EXEC_THREADS, 0, st>>>(a);
+  if (marks) cudaEventRecord(marks[4], st);
+  k_xxh<<<(a.n * 4 + 127) / 128, 128, 0, st>>>(a);
+  if (marks) cudaEventRecord(marks[5], st);
+  if (launches) *launches += 5;
+  return cudaGetLastError();
+}
+
+}  // namespace zb

@@ -1,0 +1,30 @@
+// decode_kernels.cuh — launch interface of the decoder kernels (decode_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "zb_decode.cuh"
+
+namespace zb {
+
+#define EXEC_THREADS 128
+
+// All pointers are device pointers.  dst_off must be non-decreasing with dst_off[i] + dst_cap[i] <= dst_off[i+1]
+// (the scratch arenas are addressed from dst_off, see DESIGN.md "HBM layout").
+struct DecodeArgs {
+  const u8* src_base; const u64* src_off; const u32* src_size;
+  u8* dst_base; const u64* dst_off; const u32* dst_cap;
+  u32* result; u32 n;
+  FrameInfo* info;     // n records
+  u8* lit_arena;       // decode_lit_arena_bytes()
+  SeqRec* seq_arena;   // decode_seq_arena_bytes()
+};
+
+size_t decode_lit_arena_bytes(u64 max_dst_bytes, u64 max_items);
+size_t decode_seq_arena_bytes(u64 max_dst_bytes, u64 max_items);
+cudaError_t decode_configure();
+// enqueues the whole decode pipeline for one batch on `st`; *launches += number of kernels launched
+cudaError_t decode_launch(const DecodeArgs& a, cudaStream_t st, int* launches, cudaEvent_t* marks = nullptr);
+// marks (optional): DECODE_KERNELS + 1 events recorded before the first kernel and after each kernel
+#define DECODE_KERNELS 5
+extern const char* const kDecodeKernelNames[DECODE_KERNELS];
+
+}  // namespace zb

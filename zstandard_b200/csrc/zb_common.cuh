@@ -1,0 +1,123 @@
+// zb_common.cuh — shared definitions for the libzstdb200 device code.
+//
+// Everything here is __host__ __device__ so that the per-thread parsers can also be compiled by g++ into
+// the host simulator used by the CPU-side tests (tests/hostsim/); the product only ever runs them on the GPU.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ZB_HD __host__ __device__ __forceinline__
+#define ZB_D __device__ __forceinline__
+#else
+#define ZB_HD inline
+#define ZB_D inline
+#endif
+
+namespace zb {
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int32_t i32;
+typedef int64_t i64;
+typedef int16_t s16;
+
+// ---- result / error encoding: identical to the reference (csharp/src/ZStdErrors.cs:61-100) ----
+enum : u32 {
+  ZE_GENERIC = 1, ZE_prefix_unknown = 10, ZE_frameParameter_unsupported = 14, ZE_frameParameter_windowTooLarge = 16,
+  ZE_corruption_detected = 20, ZE_checksum_wrong = 22, ZE_dictionary_corrupted = 30, ZE_dictionary_wrong = 32,
+  ZE_tableLog_tooLarge = 44, ZE_maxSymbolValue_tooLarge = 46, ZE_maxSymbolValue_tooSmall = 48,
+  ZE_workSpace_tooSmall = 66, ZE_dstSize_tooSmall = 70, ZE_srcSize_wrong = 72, ZE_maxCode = 120
+};
+ZB_HD u32 zerr(u32 code) { return 0u - code; }
+ZB_HD bool is_err(u32 r) { return r > zerr(ZE_maxCode); }
+
+// ---- format constants (csharp/src/ZStd.cs:386-416,1387-1389; ZStdInternal.cs:109-209) ----
+static const u32 MAGIC = 0xFD2FB528u, MAGIC_SKIP = 0x184D2A50u;
+static const u32 BLOCKSIZE_MAX = 1u << 17;
+static const u32 LONGNBSEQ = 0x7F00;
+static const u32 MaxLL = 35, MaxML = 52, MaxOff = 31, LLFSELog = 9, MLFSELog = 9, OffFSELog = 8;
+static const u32 HUF_LOG_MAX = 12;
+
+// ---- per-item record produced by the parse kernel and refined by later stages ----
+enum : u32 { FI_CHECKSUM = 1, FI_FCS_KNOWN = 2, FI_DONE = 4 /* result[] already final, later stages skip the item */,
+              FI_NEED_XXH = 8 /* set by the execute stage: verify the content checksum */ };
+struct FrameInfo {
+  u32 flags;
+  u32 body_off;      // offset within the item of the first block header of its data frame
+  u64 fcs;           // frame content size when FI_FCS_KNOWN
+  u64 window;        // window size (== fcs for single-segment frames)
+  // entropy-stage error records (first failing block of each stage; 0xFFFFFFFF = none)
+  u32 huf_err_block, huf_err_code;
+  u32 seq_err_block, seq_err_code, seq_err_index;   // seq_err_index: sequences decoded before the failure; 0xFFFFFFFF = header error
+  // set by the execute stage for the checksum stage
+  u32 trailer_off;   // offset of the 4-byte checksum within the item
+  u32 decoded;       // bytes produced
+};
+
+// ---- unaligned little-endian loads ----
+ZB_HD u32 ld16(const u8* p) { return (u32)p[0] | ((u32)p[1] << 8); }
+ZB_HD u32 ld24(const u8* p) { return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16); }
+ZB_HD u32 ld32(const u8* p) { return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24); }
+ZB_HD u64 ld64(const u8* p) { return (u64)ld32(p) | ((u64)ld32(p + 4) << 32); }
+
+ZB_HD u32 highbit(u32 v) {   // floor(log2(v)), v != 0 (csharp/src/BitStream.cs:205-215)
+#if defined(__CUDA_ARCH__)
+  return 31 - __clz(v);
+#else
+  return 31 - __builtin_clz(v);
+#endif
+}
+ZB_HD u32 fshr(u32 lo, u32 hi, u32 s) {   // low 32 bits of (hi:lo) >> (s & 31)
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, s);
+#else
+  s &= 31; return s ? (lo >> s) | (hi << (32 - s)) : lo;
+#endif
+}
+
+// ---- backward bit cursor -------------------------------------------------------------------------
+// A zstd bitstream of n bytes is read from its last byte towards its first (csharp/src/BitStream.cs:322-497).
+// We address it by P = number of still-unread bits counted from the first byte; reading k bits takes stream
+// bits [P-k, P) and leaves P-k.  Bits below 0 read as zero (the reference's container shifts zeros in) and a
+// negative P is the reference's "overflow" status.  Loads are 4-byte aligned words relative to `words`.
+struct BitCursor {
+  const u32* words;   // 4-byte aligned address at or below the first stream byte
+  i32 gofs;           // bit offset of stream bit 0 relative to words[0] (0, 8, 16 or 24)
+  i32 P;              // unread bits
+};
+
+// initialise from (src, n); returns false if n == 0 or the final byte has no end mark (BitStream.cs:324-339, 369-372)
+ZB_HD bool bc_init(BitCursor& c, const u8* src, u32 n) {
+  if (n < 1) return false;
+  u8 last = src[n - 1];
+  if (last == 0) return false;
+  uintptr_t a = (uintptr_t)src;
+  c.words = (const u32*)(a & ~(uintptr_t)3);
+  c.gofs = (i32)(a & 3) * 8;
+  c.P = (i32)(n * 8) - (i32)(8 - highbit(last));
+  return true;
+}
+
+// 64 stream bits ending at P, left aligned: bit 63 of the result is stream bit P-1.  Bits below stream bit 0
+// are zero.  Requires P >= 0 for meaningful data; for P < 64 a byte-safe path is used so that nothing below
+// `words` or before the stream is ever dereferenced.
+ZB_HD u64 bc_window64(const BitCursor& c, i32 P) {
+  if (P >= 64) {
+    i32 g = c.gofs + P - 64;          // bit offset (>= 0) of the window's lowest bit
+    const u32* w = c.words + (g >> 5);
+    u32 s = (u32)g & 31;
+    u32 w0 = w[0], w1 = w[1], w2 = s ? w[2] : 0;
+    u32 lo = fshr(w0, w1, s), hi = fshr(w1, w2, s);
+    return ((u64)hi << 32) | lo;
+  }
+  if (P <= 0) return 0;
+  // tail: gather the ceil(P/8) remaining bytes
+  const u8* b = (const u8*)c.words + (c.gofs >> 3);
+  u64 v = 0; i32 nb = (P + 7) >> 3;
+  for (i32 i = 0; i < nb; i++) v |= (u64)b[i] << (8 * i);
+  return v << (64 - P);   // bits at and above P (end mark, padding) fall off the top
+}
+
+}  // namespace zb
