@@ -195,7 +195,12 @@ def main():
     t_soff, t_ssz = torch.from_numpy(soff).to(dev), torch.from_numpy(ssz).to(dev)
     t_doff, t_dcap = torch.from_numpy(doff).to(dev), torch.from_numpy(dcap).to(dev)
     t_res = torch.zeros(n, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a non-default stream: handle 0 would mean "the context's own stream" to the C ABI
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     dargs = (t_src.data_ptr(), t_soff.data_ptr(), t_ssz.data_ptr(), t_dst.data_ptr(), t_doff.data_ptr(), t_dcap.data_ptr(),
              t_res.data_ptr(), n)
 

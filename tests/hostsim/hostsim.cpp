@@ -162,7 +162,8 @@ extern "C" uint32_t hostsim_decompress(uint8_t* dst, uint32_t cap, const uint8_t
   T.space[KIND_LL] = sim->ll.data(); T.space[KIND_ML] = sim->ml.data(); T.space[KIND_OF] = sim->of.data(); T.stride = 1;
   T.defs[KIND_LL] = sim->defLL; T.defs[KIND_OF] = sim->defOF; T.defs[KIND_ML] = sim->defML;
   SeqFrameOut res;
-  seq_decode_frame(src, size, fi.body_off, T, recs.data(), seq_capacity(cap), res, kLLbase, kMLbase);
+  s16 normBuf[53]; u16 nextBuf[53];
+  seq_decode_frame(src, size, fi.body_off, T, recs.data(), seq_capacity(cap), res, kLLbase, kMLbase, normBuf, nextBuf);
   if (res.err_block != 0xFFFFFFFFu) { fi.seq_err_block = res.err_block; fi.seq_err_code = res.err_code; fi.seq_err_index = res.err_index; }
   bool nx; u32 tr;
   static u8 dummy[8];
@@ -186,7 +187,8 @@ extern "C" uint32_t hostsim_stages(const uint8_t* src_in, uint32_t size, uint32_
   T.space[KIND_LL] = sim->ll.data(); T.space[KIND_ML] = sim->ml.data(); T.space[KIND_OF] = sim->of.data(); T.stride = 1;
   T.defs[KIND_LL] = sim->defLL; T.defs[KIND_OF] = sim->defOF; T.defs[KIND_ML] = sim->defML;
   SeqFrameOut res;
-  seq_decode_frame(src, size, fi.body_off, T, recs.data(), seq_capacity(cap), res, kLLbase, kMLbase);
+  s16 normBuf[53]; u16 nextBuf[53];
+  seq_decode_frame(src, size, fi.body_off, T, recs.data(), seq_capacity(cap), res, kLLbase, kMLbase, normBuf, nextBuf);
   memcpy(lit_out, lit.data(), cap);
   u32 n = (u32)std::min<size_t>(max_recs, recs.size());
   memcpy(rec_out, recs.data(), (size_t)n * 8);

@@ -143,7 +143,9 @@ def test_device_pointer_api(gpu_ctx, oracle):
     t_ssz = torch.from_numpy(ssz.view(np.int32)).to(dev)
     t_cap = torch.from_numpy(cap.view(np.int32)).to(dev)
     t_res = torch.zeros(len(frames), dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    ts = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    stream = ts.cuda_stream
     gpu_ctx.decompress_batch_device(t_src.data_ptr(), t_soff.data_ptr(), t_ssz.data_ptr(), t_dst.data_ptr(), t_doff.data_ptr(),
                                     t_cap.data_ptr(), t_res.data_ptr(), len(frames), stream=stream)
     torch.cuda.synchronize()

@@ -120,6 +120,8 @@ struct SeqSmem {
   u32 of[256][32];
   u32 defLL[64], defOF[32], defML[64];
   u32 llBase[36], mlBase[53];
+  s16 norm[53][32];      // per-lane scratch of the table builder, lane-interleaved like the tables
+  u16 next[53][32];
 };
 
 __global__ void __launch_bounds__(32) k_seq(DecodeArgs a) {
@@ -144,7 +146,8 @@ __global__ void __launch_bounds__(32) k_seq(DecodeArgs a) {
   T.space[KIND_LL] = &sm.ll[0][lane]; T.space[KIND_ML] = &sm.ml[0][lane]; T.space[KIND_OF] = &sm.of[0][lane]; T.stride = 32;
   T.defs[KIND_LL] = sm.defLL; T.defs[KIND_OF] = sm.defOF; T.defs[KIND_ML] = sm.defML;
   SeqFrameOut res;
-  seq_decode_frame(a.src_base + a.src_off[f], a.src_size[f], fi.body_off, T, seq_region(a, f), seq_capacity(a.dst_cap[f]), res, sm.llBase, sm.mlBase);
+  seq_decode_frame(a.src_base + a.src_off[f], a.src_size[f], fi.body_off, T, seq_region(a, f), seq_capacity(a.dst_cap[f]), res, sm.llBase, sm.mlBase,
+                   Strided<s16>{&sm.norm[0][lane], 32}, Strided<u16>{&sm.next[0][lane], 32});
   if (res.err_block != 0xFFFFFFFFu) {
     a.info[f].seq_err_block = res.err_block; a.info[f].seq_err_code = res.err_code; a.info[f].seq_err_index = res.err_index;
   }
@@ -195,6 +198,36 @@ __device__ __forceinline__ u32 warp_incl_scan(u32 v, u32 lane) {
 // =================================================================================================
 // k_exec : one warp per frame
 // =================================================================================================
+// Sequence execution is the reference's ExecSequence loop (:1265-1352, :1582-1605) re-expressed for a warp:
+// 32 sequence records are taken at a time, one per lane.  Output positions come from a warp prefix sum, all
+// literal runs of the group are copied first (they depend on nothing), then matches are resolved in rounds: a
+// match is ready once every earlier match of the group whose output overlaps its source has been written
+// (sources before the group are always ready).  Ready matches of a round are copied together, one output byte
+// per lane, by mapping a flattened byte index back to its sequence with a shuffle binary search.  Matches that
+// overlap their own output (offset < length) or are long are handled one at a time by the whole warp.
+#define FULLMASK 0xFFFFFFFFu
+
+// number of lanes whose inclusive prefix `incl` (non-decreasing over lanes) is <= x; x may differ per lane.
+// Saturates at 31: callers only ask for x < incl[31].
+__device__ __forceinline__ u32 warp_upper_bound(u32 incl, u32 x) {
+  u32 j = 0;
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) { u32 v = __shfl_sync(FULLMASK, incl, (j + s - 1) & 31); if (v <= x) j += s; }
+  return j & 31;
+}
+
+// one match copied by the whole warp; handles every offset/length relation (byte-serial semantics of :1319-1350)
+__device__ __forceinline__ void warp_match(u8* d, u32 off, u32 len, u32 lane) {
+  const u8* s = d - off;
+  if (off >= len) { warp_copy(d, s, len, lane); return; }
+  if (off >= 32) {
+    for (u32 i0 = 0; i0 < len; i0 += 32) { u32 i = i0 + lane; if (i < len) d[i] = s[i]; __syncwarp(); }
+    return;
+  }
+  u32 r = lane % off; const u32 stepm = 32 % off;          // period-`off` pattern: byte i repeats byte i mod off
+  for (u32 i = lane; i < len; i += 32) { d[i] = s[r]; r += stepm; if (r >= off) r -= off; }
+}
+
 __global__ void __launch_bounds__(EXEC_THREADS) k_exec(DecodeArgs a) {
   const u32 lane = threadIdx.x & 31;
   const u32 f = (blockIdx.x * EXEC_THREADS + threadIdx.x) >> 5;
@@ -241,56 +274,86 @@ __global__ void __launch_bounds__(EXEC_THREADS) k_exec(DecodeArgs a) {
       if (nbSeq) {
         const SeqRec* r = recs + recRun; bool done = false;
         while (!done) {
-          SeqRec rec = r[lane];
-          unsigned term = __ballot_sync(0xFFFFFFFFu, rec.x == 0);
-          u32 cnt = term ? (u32)__ffs(term) - 1 : 32; done = term != 0;
-          bool valid = lane < cnt;
-          u32 ll = valid ? (rec.y & 0xFFFF) : 0, ml = valid ? (rec.y >> 16) : 0, off = rec.x;
-          u32 tot = ll + ml;
-          u32 incl = warp_incl_scan(tot, lane), lincl = warp_incl_scan(ll, lane);
-          u64 myop = op + (incl - tot);                 // output position of this sequence's literals
-          u64 mpos = myop + ll;                         // ... and of its match
+          const SeqRec rec = r[lane];
+          const unsigned term = __ballot_sync(FULLMASK, rec.x == 0);
+          const u32 cnt = term ? (u32)__ffs(term) - 1 : 32; done = term != 0;
+          const bool valid = lane < cnt;
+          const u32 ll = valid ? (rec.y & 0xFFFF) : 0, ml = valid ? (rec.y >> 16) : 0, off = rec.x;
+          const u32 tot = ll + ml;
+          const u32 incl = warp_incl_scan(tot, lane), lincl = warp_incl_scan(ll, lane);
+          const u32 excl = incl - tot, mrel = excl + ll;   // group-relative output positions of literals / match
           // checks in the reference's order (:1278, :1279, :1290-1294)
-          bool e1 = valid && (myop + tot > cap);
-          bool e2 = valid && (litPos + lincl > litSize);
-          bool e3 = valid && ((u64)off > mpos);
-          unsigned bad = __ballot_sync(0xFFFFFFFFu, e1 | e2 | e3);
+          const bool e1 = valid && (op + incl > cap);
+          const bool e2 = valid && (litPos + lincl > litSize);
+          const bool e3 = valid && ((u64)off > op + mrel);
+          const unsigned bad = __ballot_sync(FULLMASK, e1 | e2 | e3);
           if (bad) {
-            u32 first = (u32)__ffs(bad) - 1;
-            u32 code = e1 ? ZE_dstSize_tooSmall : ZE_corruption_detected;
-            err = __shfl_sync(0xFFFFFFFFu, code, first);
+            const u32 first = (u32)__ffs(bad) - 1;
+            const u32 code = e1 ? ZE_dstSize_tooSmall : ZE_corruption_detected;
+            err = __shfl_sync(FULLMASK, code, first);
             break;
           }
-          // ---- literals of the whole group, flattened over lanes ----
-          u32 Lg = __shfl_sync(0xFFFFFFFFu, lincl, 31);
-          u32 lexcl = lincl - ll; u32 myop32 = (u32)(myop - op);
-          for (u32 t0 = 0; t0 < Lg; t0 += 32) {
-            u32 t = t0 + lane; u32 j = 0;
-#pragma unroll
-            for (int s = 16; s >= 1; s >>= 1) { u32 v = __shfl_sync(0xFFFFFFFFu, lincl, (j + s - 1) & 31); if (v <= t) j += s; }
-            j &= 31;
-            u32 dj = __shfl_sync(0xFFFFFFFFu, myop32, j), lj = __shfl_sync(0xFFFFFFFFu, lexcl, j);
-            if (t < Lg) dst[op + dj + (t - lj)] = isRle ? (u8)rleByte : lit[litPos + t];
+          u8* const g = dst + op;
+          // ---- literals: short runs flattened over the lanes, long runs by the whole warp ----
+          {
+            const bool bigL = ll >= 128;
+            unsigned bigMask = __ballot_sync(FULLMASK, bigL);
+            const u32 ls = bigL ? 0 : ll;
+            const u32 sincl = warp_incl_scan(ls, lane), sexcl = sincl - ls;
+            const u32 Ls = __shfl_sync(FULLMASK, sincl, 31);
+            const u32 lsrc = lincl - ll;                    // literal source position of this lane, relative to litPos
+            for (u32 t0 = 0; t0 < Ls; t0 += 32) {
+              const u32 t = t0 + lane, j = warp_upper_bound(sincl, t);
+              const u32 dj = __shfl_sync(FULLMASK, excl, j), sj = __shfl_sync(FULLMASK, sexcl, j), lj = __shfl_sync(FULLMASK, lsrc, j);
+              if (t < Ls) g[dj + (t - sj)] = isRle ? (u8)rleByte : lit[litPos + lj + (t - sj)];
+            }
+            while (bigMask) {
+              const u32 j = (u32)__ffs(bigMask) - 1; bigMask &= bigMask - 1;
+              const u32 dj = __shfl_sync(FULLMASK, excl, j), nj = __shfl_sync(FULLMASK, ll, j), lj = __shfl_sync(FULLMASK, lsrc, j);
+              if (isRle) warp_fill(g + dj, (u8)rleByte, nj, lane); else warp_copy(g + dj, lit + litPos + lj, nj, lane);
+            }
           }
           __syncwarp();
-          // ---- matches, in order ----
-          for (u32 j = 0; j < cnt; j++) {
-            u32 mj = __shfl_sync(0xFFFFFFFFu, ml, j);
-            if (!mj) continue;
-            u32 oj = __shfl_sync(0xFFFFFFFFu, off, j);
-            u64 dj = __shfl_sync(0xFFFFFFFFu, (unsigned long long)mpos, j);
-            u8* d = dst + dj; const u8* s = d - oj;
-            if (oj >= mj) {
-              for (u32 i = lane; i < mj; i += 32) d[i] = s[i];
-            } else if (oj >= 32) {
-              for (u32 i0 = 0; i0 < mj; i0 += 32) { u32 i = i0 + lane; if (i < mj) d[i] = s[i]; __syncwarp(); }
-            } else {
-              u32 r0 = lane % oj, stepm = 32 % oj;
-              for (u32 i = lane; i < mj; i += 32) { d[i] = s[r0]; r0 += stepm; if (r0 >= oj) r0 -= oj; }
+          // ---- matches, in dependency rounds ----
+          const bool hasM = ml > 0;
+          const unsigned matchMask = __ballot_sync(FULLMASK, hasM);
+          if (matchMask) {
+            unsigned depMask = 0;
+            {
+              const i64 slo = (i64)mrel - (i64)off;                         // source range, group-relative
+              i64 shi = slo + (i64)ml; if (shi > (i64)mrel) shi = (i64)mrel;   // own output is handled by warp_match
+              const bool dep = hasM && shi > 0;
+              const u32 needLo = slo > 0 ? (u32)slo : 0, needHi = dep ? (u32)shi : 1;
+              const u32 aIdx = warp_upper_bound(incl, dep ? needLo : 0), bIdx = warp_upper_bound(incl, needHi - 1);
+              if (dep) {
+                const unsigned upTo = bIdx >= 31 ? 0xFFFFFFFFu : ((1u << (bIdx + 1)) - 1);
+                depMask = upTo & ~((1u << aIdx) - 1) & ((1u << lane) - 1) & matchMask;
+              }
             }
-            __syncwarp();
+            unsigned doneMask = ~matchMask;
+            while (doneMask != 0xFFFFFFFFu) {
+              const bool ready = hasM && !((doneMask >> lane) & 1) && ((depMask & ~doneMask) == 0);
+              const unsigned R = __ballot_sync(FULLMASK, ready);
+              const bool plain = ready && off >= ml && ml < 128;
+              const u32 len = plain ? ml : 0;
+              const u32 pincl = warp_incl_scan(len, lane), pexcl = pincl - len;
+              const u32 Tt = __shfl_sync(FULLMASK, pincl, 31);
+              for (u32 t0 = 0; t0 < Tt; t0 += 32) {
+                const u32 t = t0 + lane, j = warp_upper_bound(pincl, t);
+                const u32 mj = __shfl_sync(FULLMASK, mrel, j), oj = __shfl_sync(FULLMASK, off, j), ej = __shfl_sync(FULLMASK, pexcl, j);
+                if (t < Tt) { u8* d = g + mj + (t - ej); *d = *(d - oj); }
+              }
+              unsigned big = __ballot_sync(FULLMASK, ready && !plain);
+              while (big) {
+                const u32 j = (u32)__ffs(big) - 1; big &= big - 1;
+                const u32 mj = __shfl_sync(FULLMASK, mrel, j), oj = __shfl_sync(FULLMASK, off, j), nj = __shfl_sync(FULLMASK, ml, j);
+                warp_match(g + mj, oj, nj, lane);
+              }
+              __syncwarp();
+              doneMask |= R;
+            }
           }
-          op += __shfl_sync(0xFFFFFFFFu, incl, 31); litPos += Lg;
+          op += __shfl_sync(FULLMASK, incl, 31); litPos += __shfl_sync(FULLMASK, lincl, 31);
           r += cnt + (done ? 1 : 0);
         }
         if (err) break;
@@ -298,7 +361,7 @@ __global__ void __launch_bounds__(EXEC_THREADS) k_exec(DecodeArgs a) {
         if (fi.seq_err_block == blk) { err = fi.seq_err_code; break; }             // :1594 after the decodable prefix
       }
       // last literals (:1599-1605)
-      u64 lastLL = litSize - litPos;
+      const u64 lastLL = litSize - litPos;
       if (lastLL > cap - op) { err = ZE_dstSize_tooSmall; break; }
       if (isRle) warp_fill(dst + op, (u8)rleByte, (u32)lastLL, lane); else warp_copy(dst + op, lit + litPos, (u32)lastLL, lane);
       op += lastLL;
@@ -360,9 +423,19 @@ __device__ u64 xxh64_group(const u8* p, u64 len, u32 sub, unsigned gmask, u32 le
   const u8* tail = p;
   if (len >= 32) {
     u64 v = sub == 0 ? XP1 + XP2 : (sub == 1 ? XP2 : (sub == 2 ? 0 : 0 - XP1));
-    u64 stripes = len / 32;
+    const u64 stripes = len / 32;
     const u8* q = p + 8 * sub;
-    for (u64 i = 0; i < stripes; i++) { v = xxh_round(v, ldg64u(q)); q += 32; }
+    u64 i = 0;
+    // the accumulator chain is serial; keep 8 independent loads in flight ahead of it
+    for (; i + 8 <= stripes; i += 8) {
+      u64 x[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) x[k] = ldg64u(q + 32 * k);
+#pragma unroll
+      for (int k = 0; k < 8; k++) v = xxh_round(v, x[k]);
+      q += 256;
+    }
+    for (; i < stripes; i++) { v = xxh_round(v, ldg64u(q)); q += 32; }
     u64 v1 = __shfl_sync(gmask, v, lead), v2 = __shfl_sync(gmask, v, lead + 1), v3 = __shfl_sync(gmask, v, lead + 2), v4 = __shfl_sync(gmask, v, lead + 3);
     h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
     h = xxh_merge(h, v1); h = xxh_merge(h, v2); h = xxh_merge(h, v3); h = xxh_merge(h, v4);
@@ -391,6 +464,7 @@ __global__ void __launch_bounds__(128) k_xxh(DecodeArgs a) {
     if ((u32)h != ld32(src + fi.trailer_off)) a.result[f] = zerr(ZE_checksum_wrong);   // :2078-2082
   }
 }
+
 
 // =================================================================================================
 // launch

@@ -56,6 +56,21 @@ struct FrameInfo {
   u32 decoded;       // bytes produced
 };
 
+// array view with a stride (bank-interleaved per-lane arrays in shared memory)
+template <class T> struct Strided {
+  T* p; u32 s;
+  ZB_HD T& operator[](u32 i) const { return p[i * s]; }
+};
+
+// Pulls a global-memory line towards the SM ahead of a dependent load (no-op on the host simulator).
+ZB_HD void prefetch_line(const void* p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
 // ---- unaligned little-endian loads ----
 ZB_HD u32 ld16(const u8* p) { return (u32)p[0] | ((u32)p[1] << 8); }
 ZB_HD u32 ld24(const u8* p) { return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16); }

@@ -18,7 +18,8 @@ namespace zb {
 struct SeqRec { u32 x, y; };
 
 // Capacity rule shared with the host side: records for a frame whose output capacity is `cap` bytes.
-// Every record with a match yields >= 3 bytes and each block adds one terminator.
+// Every record with a match yields >= 3 bytes and each block adds one terminator, so a frame that fits its
+// capacity needs fewer than 2*(cap/3) + 24 records; running out of room therefore means dstSize_tooSmall.
 ZB_HD u64 seq_capacity(u64 cap) { return 2 * (cap / 3) + 24; }
 
 struct SeqTableSet {
@@ -32,25 +33,31 @@ struct SeqFrameOut {
   u32 err_block, err_code, err_index;
 };
 
-ZB_HD void seq_emit(SeqRec* out, u64& n, u64 cap, bool& overflow, u32 off, u32 ll, u32 ml) {
-  while (ll > 65535) { if (n < cap) { out[n].x = 1; out[n].y = 65535; } else overflow = true; n++; ll -= 65535; }
-  while (ml > 65535) { if (n < cap) { out[n].x = off; out[n].y = ll | (65535u << 16); } else overflow = true; n++; ll = 0; ml -= 65535; }
-  if (n < cap) { out[n].x = off; out[n].y = ll | (ml << 16); } else overflow = true;
+// slow path of the record writer: lengths that do not fit 16 bits are split (ZStdDecompress.cs allows
+// litLength <= 131071 and matchLength <= 131074)
+ZB_HD void seq_emit_long(SeqRec* out, u64& n, u64 cap, u32 off, u32 ll, u32 ml) {
+  while (ll > 65535) { if (n < cap) { out[n].x = 1; out[n].y = 65535; } n++; ll -= 65535; }
+  while (ml > 65535) { if (n < cap) { out[n].x = off; out[n].y = ll | (65535u << 16); } n++; ll = 0; ml -= 65535; }
+  if (n < cap) { out[n].x = off; out[n].y = ll | (ml << 16); }
   n++;
 }
+
+// n bits (0..32) from the top of a left-aligned 64-bit window; the double shift makes n == 0 yield 0
+// (the reference's LookBits does the same, BitStream.cs:412-416)
+ZB_HD u32 top_bits(u64 w, u32 n) { return (u32)((w >> 1) >> (63 - n)); }
 
 // Walks the frame at item `src` (size bytes, first block header at body_off) and decodes every compressed
 // block's sequences.  Stops silently at structural errors that the execute stage will report itself from the
 // same headers; records entropy-level failures in `res`.
-// llBase/mlBase: base-value tables (any address space readable by this thread).
+// llBase/mlBase: base-value tables; norm/symbolNext: >= 53 entries of per-thread scratch each.
+template <class NormT, class NextT>
 ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, SeqTableSet& T, SeqRec* out, u64 cap, SeqFrameOut& res,
-                            const u32* llBase, const u32* mlBase) {
+                            const u32* llBase, const u32* mlBase, NormT norm, NextT symbolNext) {
   res.err_block = 0xFFFFFFFFu; res.err_code = 0; res.err_index = 0;
   u32 pos = body_off, blk = 0;
   u32 rep0 = 1, rep1 = 4, rep2 = 8;                      // ZStdInternal.cs:111, ZStdDecompress.cs:2492
   bool haveRepeat = false;
-  u64 n = 0; bool overflow = false;
-  s16 norm[53]; u16 symbolNext[53];
+  u64 n = 0;
   for (int k = 0; k < 3; k++) { T.cur[k] = T.space[k]; T.curStride[k] = T.stride; T.log[k] = 0; }
   while (true) {
     BlockHdr bh;
@@ -90,49 +97,61 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, SeqTableSet& 
         if (!bc_init(c, sp + hdr, ssz - hdr)) bad = true;                          // :1577 -> corruption_detected
         if (!bad) {
           i32 P = c.P;
+          const u8* const streamBase = (const u8*)c.words;
+          if (P > 2048) { prefetch_line(streamBase + ((c.gofs + P) >> 3) - 128); prefetch_line(streamBase + ((c.gofs + P) >> 3) - 256); }
           const u32 *tLL = T.cur[KIND_LL], *tOF = T.cur[KIND_OF], *tML = T.cur[KIND_ML];
           const u32 sLLs = T.curStride[KIND_LL], sOFs = T.curStride[KIND_OF], sMLs = T.curStride[KIND_ML];
           u32 stLL, stOF, stML;
-          { u64 w = bc_window64(c, P); u32 lg = T.log[KIND_LL]; stLL = lg ? (u32)(w >> (64 - lg)) : 0; w <<= lg; P -= (i32)lg;
-            lg = T.log[KIND_OF]; stOF = lg ? (u32)(w >> (64 - lg)) : 0; w <<= lg; P -= (i32)lg;
-            lg = T.log[KIND_ML]; stML = lg ? (u32)(w >> (64 - lg)) : 0; P -= (i32)lg; }   // :1578-1580 (<= 26 bits)
+          { u64 w = bc_window64(c, P); u32 lg = T.log[KIND_LL]; stLL = top_bits(w, lg); w <<= lg; P -= (i32)lg;
+            lg = T.log[KIND_OF]; stOF = top_bits(w, lg); w <<= lg; P -= (i32)lg;
+            lg = T.log[KIND_ML]; stML = top_bits(w, lg); P -= (i32)lg; }             // :1578-1580 (<= 26 bits)
           for (u32 i = 0; i < nbSeq; i++) {
             if (P < 0) { bad = true; break; }                                      // loop test :1582 (overflow)
-            u32 cLL = tLL[stLL * sLLs], cOF = tOF[stOF * sOFs], cML = tML[stML * sMLs];
-            u32 llBits = (cLL >> 14) & 31, mlBits = (cML >> 14) & 31, ofBits = (cOF >> 14) & 31;
-            u32 llSym = cLL >> 19, mlSym = cML >> 19;
-            u64 w = bc_window64(c, P);
-            u32 ofv = ofBits ? (u32)(w >> (64 - ofBits)) : 0; w <<= ofBits;
-            u32 mlv = mlBits ? (u32)(w >> (64 - mlBits)) : 0; w <<= mlBits;
-            u32 llv = llBits ? (u32)(w >> (64 - llBits)) : 0;
-            P -= (i32)(ofBits + mlBits + llBits);
-            if (P < 0) { bad = true; break; }     // values came from beyond the stream start (over-read)
-            u32 offset = ofBits ? of_base(ofBits) + ofv : 0;                       // :1487-1507
-            if (ofBits <= 1) {                                                     // :1509-1524
-              offset += (llSym == 0);
-              if (offset) {
-                u32 temp = offset == 3 ? rep0 - 1 : (offset == 1 ? rep1 : rep2);   // prevOffset[offset], :1514
-                temp += !temp;
-                if (offset != 1) rep2 = rep1;
-                rep1 = rep0; rep0 = offset = temp;
-              } else offset = rep0;
-            } else { rep2 = rep1; rep1 = rep0; rep0 = offset; }                    // :1527-1529
-            u32 ml = mlBase[mlSym] + mlv, ll = llBase[llSym] + llv;
-            seq_emit(out, n, cap, overflow, offset, ll, ml);
+            const u64 w0 = bc_window64(c, P);                                      // depends on P only: overlaps the table reads
+            const u32 cLL = tLL[stLL * sLLs], cOF = tOF[stOF * sOFs], cML = tML[stML * sMLs];
+            const u32 llBits = (cLL >> 14) & 31, mlBits = (cML >> 14) & 31, ofBits = (cOF >> 14) & 31;
+            const u32 nLL = (cLL >> 10) & 15, nML = (cML >> 10) & 15, nOF = (cOF >> 10) & 15;
+            const u32 llSym = cLL >> 19, mlSym = cML >> 19;
+            const u32 valBits = ofBits + mlBits + llBits, stBits = nLL + nML + nOF;
+            u64 w = w0;
+            const u32 ofv = top_bits(w, ofBits); w <<= ofBits;                     // read order: offset, matchLength, litLength
+            const u32 mlv = top_bits(w, mlBits); w <<= mlBits;                     // (:1504, :1534, :1542)
+            const u32 llv = top_bits(w, llBits); w <<= llBits;
+            const i32 Pv = P - (i32)valBits;
+            if (Pv < 0) { bad = true; break; }     // values came from beyond the stream start (DESIGN.md "over-read")
+            if (valBits + stBits > 64) w = bc_window64(c, Pv);                     // rare: more than 64 bits in one sequence
+            // repcode resolution (:1509-1530), written without data-dependent branches
+            u32 offset;
+            {
+              const u32 raw = ofBits ? of_base(ofBits) + ofv : 0;
+              const bool isRep = ofBits <= 1;
+              const u32 idx = raw + (llSym == 0);                                  // 0..3 when isRep
+              const u32 pick = idx == 0 ? rep0 : (idx == 1 ? rep1 : (idx == 2 ? rep2 : rep0 - 1));
+              const u32 repv = pick + (pick == 0);                                 // 0 is not valid: forced to 1 (:1515)
+              offset = isRep ? repv : raw;
+              const bool shift1 = !isRep || idx >= 1;                              // history changes unless idx == 0
+              const bool shift2 = !isRep || idx >= 2;
+              const u32 n2 = shift2 ? rep1 : rep2, n1 = shift1 ? rep0 : rep1;
+              rep2 = n2; rep1 = n1; rep0 = offset;
+            }
+            const u32 ml = mlBase[mlSym] + mlv, ll = llBase[llSym] + llv;
+            if ((ll | ml) <= 65535) { if (n < cap) { out[n].x = offset; out[n].y = ll | (ml << 16); } n++; }
+            else seq_emit_long(out, n, cap, offset, ll, ml);
             decoded++;
             // state update LL, ML, OF (:1547-1550); past the last sequence these bits do not exist
-            u32 nLL = (cLL >> 10) & 15, nML = (cML >> 10) & 15, nOF = (cOF >> 10) & 15;
-            u64 w2 = bc_window64(c, P);
-            stLL = (cLL & 0x3FF) + (nLL ? (u32)(w2 >> (64 - nLL)) : 0); w2 <<= nLL;
-            stML = (cML & 0x3FF) + (nML ? (u32)(w2 >> (64 - nML)) : 0); w2 <<= nML;
-            stOF = (cOF & 0x3FF) + (nOF ? (u32)(w2 >> (64 - nOF)) : 0);
-            P -= (i32)(nLL + nML + nOF);
+            stLL = (cLL & 0x3FF) + top_bits(w, nLL); w <<= nLL;
+            stML = (cML & 0x3FF) + top_bits(w, nML); w <<= nML;
+            stOF = (cOF & 0x3FF) + top_bits(w, nOF);
+            const i32 Pn = Pv - (i32)stBits;
+            if (((P ^ Pn) >> 10) != 0 && Pn > 2048) prefetch_line(streamBase + ((c.gofs + Pn) >> 3) - 256);
+            P = Pn;
           }
         }
-        // terminator
-        if (n < cap) { out[n].x = 0; out[n].y = 0; } else overflow = true;
+        // terminator; when the region is full the last slot is sacrificed so that the execute stage stops there
+        const bool overflow = n >= cap;
+        if (overflow) { out[cap - 1].x = 0; out[cap - 1].y = 0; } else { out[n].x = 0; out[n].y = 0; }
         n++;
-        if (overflow) { res.err_block = blk; res.err_code = ZE_corruption_detected; res.err_index = 0xFFFFFFFFu; return; }   // records unusable
+        if (overflow) { res.err_block = blk; res.err_code = ZE_dstSize_tooSmall; res.err_index = 0; return; }
         if (bad) { res.err_block = blk; res.err_code = ZE_corruption_detected; res.err_index = decoded; return; }
       }
     }
@@ -171,6 +190,8 @@ ZB_HD bool huf_decode_stream(const u8* src, u32 len, u8* out, u32 count, const u
   i32 P = c.P;
   u32 left = count;
   const u32 sh = 64 - tableLog;
+  const u8* const streamBase = (const u8*)c.words;
+  if (P > 2048) { prefetch_line(streamBase + ((c.gofs + P) >> 3) - 128); prefetch_line(streamBase + ((c.gofs + P) >> 3) - 256); }
   // head: reach 4-byte alignment of the output
   while (left && ((uintptr_t)out & 3)) {
     u64 w = bc_window64(c, P);
@@ -183,7 +204,9 @@ ZB_HD bool huf_decode_stream(const u8* src, u32 len, u8* out, u32 count, const u
     u32 c1 = dt[(u32)(w >> sh)]; w <<= (c1 >> 8);
     u32 c2 = dt[(u32)(w >> sh)]; w <<= (c2 >> 8);
     u32 c3 = dt[(u32)(w >> sh)];
-    P -= (i32)((c0 >> 8) + (c1 >> 8) + (c2 >> 8) + (c3 >> 8));
+    const i32 Pn = P - (i32)((c0 >> 8) + (c1 >> 8) + (c2 >> 8) + (c3 >> 8));
+    if (((P ^ Pn) >> 10) != 0 && Pn > 2048) prefetch_line(streamBase + ((c.gofs + Pn) >> 3) - 256);
+    P = Pn;
     *(u32*)out = (c0 & 0xFF) | ((c1 & 0xFF) << 8) | ((c2 & 0xFF) << 16) | ((c3 & 0xFF) << 24);
     out += 4; left -= 4;
   }

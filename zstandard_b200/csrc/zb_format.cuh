@@ -148,7 +148,9 @@ ZB_HD u32 read_seq_count(const u8* p, u32 srcSize, u32* nbSeq, u32* modes, u32* 
 // =====================================================================================================
 // FSE normalized counts (ReadNCount, EntropyCommon.cs:79-188).  Index arithmetic in i32 relative to hb.
 // =====================================================================================================
-ZB_HD u32 read_ncount(s16* norm, u32* maxSV, u32* tableLog, const u8* hb, u32 hbSize, u32* hdrBytes) {
+// NormT: anything indexable yielding s16& (plain pointer, or Strided<s16> for bank-interleaved shared memory)
+template <class NormT>
+ZB_HD u32 read_ncount(NormT norm, u32* maxSV, u32* tableLog, const u8* hb, u32 hbSize, u32* hdrBytes) {
   i32 ip = 0; const i32 iend = (i32)hbSize;
   if (hbSize < 4) return ZE_srcSize_wrong;
   u32 bitStream = ld32(hb);
@@ -231,7 +233,8 @@ ZB_HD u32 kind_nbadd(int kind, u32 sym) { return kind == KIND_LL ? kLLbits[sym] 
 
 // Builds a decode table into cells[i*stride], i < (1<<tableLog).  `scratch` = 53 u16 of per-thread storage.
 // The table must not be read through `cells` by anyone else meanwhile.
-ZB_HD void build_seq_table(u32* cells, u32 stride, const s16* norm, u32 maxSV, u32 tableLog, int kind, u16* symbolNext) {
+template <class NormT, class NextT>
+ZB_HD void build_seq_table(u32* cells, u32 stride, NormT norm, u32 maxSV, u32 tableLog, int kind, NextT symbolNext) {
   u32 maxSV1 = maxSV + 1, tableSize = 1u << tableLog, high = tableSize - 1;
   for (u32 s = 0; s < maxSV1; s++) {
     if (norm[s] == -1) { cells[(high--) * stride] = s; symbolNext[s] = 1; }
@@ -254,8 +257,9 @@ ZB_HD void build_seq_table(u32* cells, u32 stride, const s16* norm, u32 maxSV, u
 // One table descriptor of the sequences header.  mode: 0 predefined, 1 rle, 2 fse, 3 repeat.
 // On success *log = table log now in force for this kind, *used = header bytes.  `cells/stride` is the
 // lane-private table space; predefined tables live elsewhere (the caller switches pointers when *isDefault).
+template <class NormT, class NextT>
 ZB_HD u32 read_seq_table(u32 mode, int kind, const u8* p, u32 srcSize, u32* cells, u32 stride, u32* log, bool* isDefault,
-                         bool haveRepeat, u32* used, s16* norm, u16* symbolNext) {
+                         bool haveRepeat, u32* used, NormT norm, NextT symbolNext) {
   const u32 maxSym = kind == KIND_LL ? MaxLL : (kind == KIND_ML ? MaxML : MaxOff);
   const u32 maxLog = kind == KIND_LL ? LLFSELog : (kind == KIND_ML ? MLFSELog : OffFSELog);
   *used = 0;
