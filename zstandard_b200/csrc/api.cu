@@ -3,6 +3,13 @@
 // Host responsibilities: build flat descriptor tables, shard items over the context's GPUs by
 // bytes (no collective: frames are independent, ZStdDecompress.cs:2478-2499 resets all state per frame), move
 // bytes host<->device and launch the kernels.  No decoding or encoding arithmetic happens on the host.
+//
+// Data movement.  A batch is cut into sub-batches that fit the device arenas; a sub-batch is cut into slices that
+// are dealt round-robin to NSTREAMS streams, so the H2D copy of one slice, the kernels of another and the D2H
+// copy of a third overlap — and so do the latency-bound entropy kernels of one slice with the copy-bound execute
+// kernel of another.  When the caller's buffers are already laid out back to back (the layout a managed host gets
+// from one pinned array plus offsets) they are DMA'd directly; otherwise items are gathered/scattered through the
+// context's pinned staging.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -20,9 +27,13 @@ using namespace zb;
 
 namespace {
 
+constexpr int NSTREAMS = 4;
+constexpr size_t SLICE_BYTES = 48u << 20;   // uncompressed bytes per slice (several slices per stream per GiB)
+
 struct Device {
   int id = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream[NSTREAMS] = {};
+  cudaEvent_t forkEv = nullptr, joinEv[NSTREAMS] = {};
   // device memory
   u8 *d_src = nullptr, *d_dst = nullptr;       // staging for the host-pointer API
   u64 *d_srcOff = nullptr, *d_dstOff = nullptr; u32 *d_srcSize = nullptr, *d_dstCap = nullptr, *d_result = nullptr;
@@ -37,7 +48,7 @@ struct Device {
 
 struct zstdb200_ctx {
   std::vector<Device> dev;
-  size_t maxBatch = 0, maxItems = 0, srcCap = 0;
+  size_t maxBatch = 0, maxItems = 0, srcCap = 0, dstSpan = 0;
   std::string err;
   uint64_t launches = 0;
 };
@@ -57,17 +68,18 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int alloc_device(zstdb200_ctx* ctx, Device& d) {
   CK(cudaSetDevice(d.id));
-  CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+  for (auto& s : d.stream) CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&d.forkEv, cudaEventDisableTiming));
+  for (auto& e : d.joinEv) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   const size_t items = ctx->maxItems;
   CK(cudaMalloc(&d.d_src, ctx->srcCap + 256));
-  CK(cudaMalloc(&d.d_dst, ctx->maxBatch + 16 * items + 256));
+  CK(cudaMalloc(&d.d_dst, ctx->dstSpan + 256));
   CK(cudaMalloc(&d.d_srcOff, items * 8)); CK(cudaMalloc(&d.d_dstOff, items * 8));
   CK(cudaMalloc(&d.d_srcSize, items * 4)); CK(cudaMalloc(&d.d_dstCap, items * 4)); CK(cudaMalloc(&d.d_result, items * 4));
   CK(cudaMalloc(&d.d_info, items * sizeof(FrameInfo)));
-  const u64 dstSpan = ctx->maxBatch + 16 * items;
-  CK(cudaMalloc(&d.d_lit, decode_lit_arena_bytes(dstSpan, items)));
-  CK(cudaMalloc(&d.d_seq, decode_seq_arena_bytes(dstSpan, items)));
-  CK(cudaMallocHost(&d.h_src, ctx->srcCap + 256)); CK(cudaMallocHost(&d.h_dst, ctx->maxBatch + 16 * items + 256));
+  CK(cudaMalloc(&d.d_lit, decode_lit_arena_bytes(ctx->dstSpan, items)));
+  CK(cudaMalloc(&d.d_seq, decode_seq_arena_bytes(ctx->dstSpan, items)));
+  CK(cudaMallocHost(&d.h_src, ctx->srcCap + 256)); CK(cudaMallocHost(&d.h_dst, ctx->dstSpan + 256));
   CK(cudaMallocHost(&d.h_srcOff, items * 8)); CK(cudaMallocHost(&d.h_dstOff, items * 8));
   CK(cudaMallocHost(&d.h_srcSize, items * 4)); CK(cudaMallocHost(&d.h_dstCap, items * 4)); CK(cudaMallocHost(&d.h_result, items * 4));
   CK(decode_configure());
@@ -78,27 +90,27 @@ int alloc_device(zstdb200_ctx* ctx, Device& d) {
 
 void free_device(Device& d) {
   cudaSetDevice(d.id);
-  if (d.stream) cudaStreamSynchronize(d.stream);
+  for (auto& s : d.stream) if (s) cudaStreamSynchronize(s);
   cudaFree(d.d_src); cudaFree(d.d_dst); cudaFree(d.d_srcOff); cudaFree(d.d_dstOff); cudaFree(d.d_srcSize); cudaFree(d.d_dstCap);
   cudaFree(d.d_result); cudaFree(d.d_info); cudaFree(d.d_lit); cudaFree(d.d_seq);
   encode_free(d.enc);
   cudaFreeHost(d.h_src); cudaFreeHost(d.h_dst); cudaFreeHost(d.h_srcOff); cudaFreeHost(d.h_dstOff); cudaFreeHost(d.h_srcSize);
   cudaFreeHost(d.h_dstCap); cudaFreeHost(d.h_result);
-  if (d.stream) cudaStreamDestroy(d.stream);
+  for (auto& s : d.stream) if (s) cudaStreamDestroy(s);
+  if (d.forkEv) cudaEventDestroy(d.forkEv);
+  for (auto& e : d.joinEv) if (e) cudaEventDestroy(e);
 }
 
-// A sub-batch of items [lo, hi) assigned to one device.
 struct Range { size_t lo, hi; };
 
 // Greedy split of [0, n) into consecutive sub-batches that respect the per-device arena limits.
-// inBytes(i)/outBytes(i): staging bytes needed by item i on the input / output side.
 template <class FI, class FO>
 std::vector<Range> make_subbatches(size_t n, size_t maxIn, size_t maxOut, size_t maxItems, FI inBytes, FO outBytes, bool* tooBig) {
   std::vector<Range> r; size_t lo = 0; *tooBig = false;
   while (lo < n) {
     size_t in = 0, out = 0, hi = lo;
     while (hi < n && hi - lo < maxItems) {
-      size_t a = align_up(inBytes(hi), 16), b = align_up(outBytes(hi), 16);
+      size_t a = align_up(inBytes(hi), 16) + 64, b = align_up(outBytes(hi), 16);
       if (in + a > maxIn || out + b > maxOut) break;
       in += a; out += b; hi++;
     }
@@ -110,62 +122,129 @@ std::vector<Range> make_subbatches(size_t n, size_t maxIn, size_t maxOut, size_t
 
 enum class Op { Decompress, Compress };
 
-// Runs one op over items [0,n) with host pointers: sub-batches are dealt round-robin to devices; each device
-// handles its sub-batches in order on its own stream.  One host thread per device drives staging copies.
-int run_host_batch(zstdb200_ctx* ctx, Op op, int level, int checksum, const void* const* src, const uint32_t* srcSize,
-                   void* const* dst, const uint32_t* dstCap, uint32_t* result, size_t n) {
+struct Job {
+  Op op; int level, checksum;
+  const void* const* src; const uint32_t* srcSize; void* const* dst; const uint32_t* dstCap; uint32_t* result;
+};
+
+// One sub-batch [lo, hi) on one device: slices over NSTREAMS streams, direct DMA where the layout allows.
+// Returns "" or an error description.
+std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, size_t hi, uint64_t* launches) {
+  const size_t m = hi - lo;
+  auto fail = [&](const char* what, cudaError_t e) { return std::string(what) + ": " + cudaGetErrorString(e); };
+  // ---- layout analysis ----
+  bool srcDirect = true, dstDirect = true;
+  for (size_t k = 0; k + 1 < m && (srcDirect || dstDirect); k++) {
+    const size_t i = lo + k;
+    const u8 *s0 = (const u8*)j.src[i], *s1 = (const u8*)j.src[i + 1];
+    if (!(s1 >= s0 + j.srcSize[i] && s1 <= s0 + j.srcSize[i] + 64)) srcDirect = false;
+    const u8 *d0 = (const u8*)j.dst[i], *d1 = (const u8*)j.dst[i + 1];
+    if (d1 != d0 + j.dstCap[i]) dstDirect = false;
+  }
+  const u8* srcBase = (const u8*)j.src[lo]; u8* dstBase = (u8*)j.dst[lo];
+  if (srcDirect) {
+    const size_t span = (size_t)((const u8*)j.src[hi - 1] - srcBase) + j.srcSize[hi - 1];
+    const size_t lim = j.op == Op::Decompress ? ctx->srcCap : ctx->dstSpan;
+    if (span > lim || !srcBase) srcDirect = false;
+  }
+  if (dstDirect) {
+    const size_t span = (size_t)((u8*)j.dst[hi - 1] - dstBase) + j.dstCap[hi - 1];
+    const size_t lim = j.op == Op::Decompress ? ctx->dstSpan : ctx->srcCap;
+    if (span > lim || !dstBase) dstDirect = false;
+  }
+  // ---- descriptors (device offsets) ----
+  size_t in = 0, out = 0;
+  for (size_t k = 0; k < m; k++) {
+    const size_t i = lo + k;
+    d.h_srcSize[k] = j.srcSize[i]; d.h_dstCap[k] = j.dstCap[i];
+    d.h_srcOff[k] = srcDirect ? (u64)((const u8*)j.src[i] - srcBase) : in;
+    d.h_dstOff[k] = dstDirect ? (u64)((u8*)j.dst[i] - dstBase) : out;
+    in += align_up(j.srcSize[i], 16); out += align_up(j.dstCap[i], 16);
+  }
+  // ---- slices ----
+  std::vector<Range> slices;
+  {
+    size_t a = 0;
+    while (a < m) {
+      size_t b = a, bytes = 0;
+      while (b < m && (b == a || bytes + std::max(d.h_dstCap[b], d.h_srcSize[b]) <= SLICE_BYTES)) { bytes += std::max(d.h_dstCap[b], d.h_srcSize[b]); b++; }
+      slices.push_back({a, b}); a = b;
+    }
+  }
+  cudaError_t e;
+  for (size_t s = 0; s < slices.size(); s++) {
+    const size_t a = slices[s].lo, b = slices[s].hi, cnt = b - a;
+    cudaStream_t st = d.stream[s % NSTREAMS];
+    // input bytes of the slice
+    const size_t inLo = d.h_srcOff[a], inHi = d.h_srcOff[b - 1] + d.h_srcSize[b - 1];
+    if (srcDirect) {
+      if (inHi > inLo) { e = cudaMemcpyAsync(d.d_src + inLo, srcBase + inLo, inHi - inLo, cudaMemcpyHostToDevice, st); if (e) return fail("H2D src", e); }
+    } else {
+      for (size_t k = a; k < b; k++) if (d.h_srcSize[k]) memcpy(d.h_src + d.h_srcOff[k], j.src[lo + k], d.h_srcSize[k]);
+      if (inHi > inLo) { e = cudaMemcpyAsync(d.d_src + inLo, d.h_src + inLo, inHi - inLo, cudaMemcpyHostToDevice, st); if (e) return fail("H2D src", e); }
+    }
+    e = cudaMemcpyAsync(d.d_srcOff + a, d.h_srcOff + a, cnt * 8, cudaMemcpyHostToDevice, st); if (e) return fail("H2D desc", e);
+    e = cudaMemcpyAsync(d.d_dstOff + a, d.h_dstOff + a, cnt * 8, cudaMemcpyHostToDevice, st); if (e) return fail("H2D desc", e);
+    e = cudaMemcpyAsync(d.d_srcSize + a, d.h_srcSize + a, cnt * 4, cudaMemcpyHostToDevice, st); if (e) return fail("H2D desc", e);
+    e = cudaMemcpyAsync(d.d_dstCap + a, d.h_dstCap + a, cnt * 4, cudaMemcpyHostToDevice, st); if (e) return fail("H2D desc", e);
+    int nl = 0;
+    if (j.op == Op::Decompress) {
+      DecodeArgs ar{d.d_src, d.d_srcOff + a, d.d_srcSize + a, d.d_dst, d.d_dstOff + a, d.d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
+                    d.d_info + a, d.d_lit, d.d_seq};
+      e = decode_launch(ar, st, &nl);
+    } else {
+      EncodeArgs ar{d.d_src, d.d_srcOff + a, d.d_srcSize + a, d.d_dst, d.d_dstOff + a, d.d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
+                    j.level, j.checksum};
+      e = encode_launch(ar, d.enc, st, &nl);
+    }
+    *launches += nl;
+    if (e) return fail("kernel launch", e);
+    e = cudaMemcpyAsync(d.h_result + a, d.d_result + a, cnt * 4, cudaMemcpyDeviceToHost, st); if (e) return fail("D2H result", e);
+    const size_t outLo = d.h_dstOff[a], outHi = d.h_dstOff[b - 1] + d.h_dstCap[b - 1];
+    if (outHi > outLo) {
+      u8* hostDst = dstDirect ? dstBase + outLo : d.h_dst + outLo;
+      e = cudaMemcpyAsync(hostDst, d.d_dst + outLo, outHi - outLo, cudaMemcpyDeviceToHost, st); if (e) return fail("D2H dst", e);
+    }
+  }
+  for (auto& st : d.stream) { e = cudaStreamSynchronize(st); if (e) return fail("stream sync", e); }
+  for (size_t k = 0; k < m; k++) {
+    const size_t i = lo + k; const u32 r = d.h_result[k];
+    j.result[i] = r;
+    // staged output: copy what was produced; on error the reference leaves dst partially written, we copy nothing
+    if (!dstDirect && !is_err(r) && r) memcpy(j.dst[i], d.h_dst + d.h_dstOff[k], std::min<u32>(r, j.dstCap[i]));
+  }
+  return "";
+}
+
+int run_host_batch(zstdb200_ctx* ctx, const Job& j, size_t n) {
   if (n == 0) return 0;
-  if (!src || !srcSize || !dst || !dstCap || !result) { ctx->err = "null argument"; return 1; }
-  // staging limits: decode: in = compressed (srcCap), out = raw (maxBatch); encode: in = raw (maxBatch), out = frames (srcCap)
-  const size_t maxIn = op == Op::Decompress ? ctx->srcCap : ctx->maxBatch;
-  const size_t maxOut = op == Op::Decompress ? ctx->maxBatch : ctx->srcCap;
+  if (!j.src || !j.srcSize || !j.dst || !j.dstCap || !j.result) { ctx->err = "null argument"; return 1; }
+  // staging limits: decode: in = compressed (srcCap), out = raw (dstSpan); encode: in = raw, out = frames
+  const size_t maxIn = j.op == Op::Decompress ? ctx->srcCap : ctx->maxBatch;
+  const size_t maxOut = j.op == Op::Decompress ? ctx->maxBatch : ctx->srcCap;
   bool tooBig = false;
   std::vector<Range> subs = make_subbatches(n, maxIn, maxOut, ctx->maxItems,
-      [&](size_t i) { return (size_t)srcSize[i]; }, [&](size_t i) { return (size_t)dstCap[i]; }, &tooBig);
+      [&](size_t i) { return (size_t)j.srcSize[i]; }, [&](size_t i) { return (size_t)j.dstCap[i]; }, &tooBig);
   if (tooBig) { ctx->err = "an item is larger than the context's max_batch_bytes"; return 1; }
+  // a single sub-batch on a multi-GPU context is re-cut so that every device gets a share
   const size_t nd = ctx->dev.size();
+  if (nd > 1 && subs.size() < nd) {
+    std::vector<Range> cut;
+    for (auto& r : subs) {
+      const size_t parts = std::min(nd, r.hi - r.lo);
+      for (size_t p = 0; p < parts; p++) cut.push_back({r.lo + (r.hi - r.lo) * p / parts, r.lo + (r.hi - r.lo) * (p + 1) / parts});
+    }
+    subs.swap(cut);
+  }
   std::vector<std::string> errs(nd);
   std::vector<uint64_t> launches(nd, 0);
   auto worker = [&](size_t di) {
     Device& d = ctx->dev[di];
-    auto fail = [&](const char* what, cudaError_t e) { errs[di] = std::string(what) + ": " + cudaGetErrorString(e); };
     cudaError_t e = cudaSetDevice(d.id);
-    if (e != cudaSuccess) { fail("cudaSetDevice", e); return; }
+    if (e != cudaSuccess) { errs[di] = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return; }
     for (size_t s = di; s < subs.size(); s += nd) {
-      const Range rg = subs[s]; const size_t m = rg.hi - rg.lo;
-      // ---- gather into pinned staging, build descriptors ----
-      size_t in = 0, out = 0;
-      for (size_t k = 0; k < m; k++) {
-        const size_t i = rg.lo + k;
-        d.h_srcOff[k] = in; d.h_srcSize[k] = srcSize[i]; d.h_dstOff[k] = out; d.h_dstCap[k] = dstCap[i];
-        if (srcSize[i]) memcpy(d.h_src + in, src[i], srcSize[i]);
-        in += align_up(srcSize[i], 16); out += align_up(dstCap[i], 16);
-      }
-      e = cudaMemcpyAsync(d.d_src, d.h_src, in, cudaMemcpyHostToDevice, d.stream); if (e) { fail("H2D src", e); return; }
-      e = cudaMemcpyAsync(d.d_srcOff, d.h_srcOff, m * 8, cudaMemcpyHostToDevice, d.stream); if (e) { fail("H2D", e); return; }
-      e = cudaMemcpyAsync(d.d_dstOff, d.h_dstOff, m * 8, cudaMemcpyHostToDevice, d.stream); if (e) { fail("H2D", e); return; }
-      e = cudaMemcpyAsync(d.d_srcSize, d.h_srcSize, m * 4, cudaMemcpyHostToDevice, d.stream); if (e) { fail("H2D", e); return; }
-      e = cudaMemcpyAsync(d.d_dstCap, d.h_dstCap, m * 4, cudaMemcpyHostToDevice, d.stream); if (e) { fail("H2D", e); return; }
-      int nl = 0;
-      if (op == Op::Decompress) {
-        DecodeArgs a{d.d_src, d.d_srcOff, d.d_srcSize, d.d_dst, d.d_dstOff, d.d_dstCap, d.d_result, (u32)m, d.d_info, d.d_lit, d.d_seq};
-        e = decode_launch(a, d.stream, &nl);
-      } else {
-        EncodeArgs a{d.d_src, d.d_srcOff, d.d_srcSize, d.d_dst, d.d_dstOff, d.d_dstCap, d.d_result, (u32)m, level, checksum};
-        e = encode_launch(a, d.enc, d.stream, &nl);
-      }
-      launches[di] += nl;
-      if (e) { fail("kernel launch", e); return; }
-      e = cudaMemcpyAsync(d.h_result, d.d_result, m * 4, cudaMemcpyDeviceToHost, d.stream); if (e) { fail("D2H", e); return; }
-      e = cudaMemcpyAsync(d.h_dst, d.d_dst, out, cudaMemcpyDeviceToHost, d.stream); if (e) { fail("D2H dst", e); return; }
-      e = cudaStreamSynchronize(d.stream); if (e) { fail("stream sync", e); return; }
-      // ---- scatter ----
-      for (size_t k = 0; k < m; k++) {
-        const size_t i = rg.lo + k; const u32 r = d.h_result[k];
-        result[i] = r;
-        // on error the reference leaves dst partially written; we copy nothing
-        if (!is_err(r) && r) memcpy(dst[i], d.h_dst + d.h_dstOff[k], std::min<u32>(r, dstCap[i]));
-      }
+      errs[di] = run_subbatch(ctx, d, j, subs[s].lo, subs[s].hi, &launches[di]);
+      if (!errs[di].empty()) return;
     }
   };
   if (nd == 1 || subs.size() == 1) { for (size_t di = 0; di < nd; di++) worker(di); }
@@ -190,7 +269,8 @@ int zstdb200_create(zstdb200_ctx** out, const int* devices, int n_devices, size_
   if (max_batch_bytes < (1u << 20)) max_batch_bytes = 1u << 20;
   ctx->maxBatch = align_up(max_batch_bytes, 4096);
   ctx->maxItems = std::max<size_t>(65536, ctx->maxBatch / 1024);
-  ctx->srcCap = ctx->maxBatch + ctx->maxBatch / 128 + 64 * ctx->maxItems;   // >= sum of compress bounds of a full batch
+  ctx->dstSpan = ctx->maxBatch + 16 * ctx->maxItems;
+  ctx->srcCap = ctx->maxBatch + ctx->maxBatch / 128 + 128 * ctx->maxItems;   // >= sum of compress bounds of a full batch
   int one = 0;
   if (!devices || n_devices <= 0) { devices = &one; n_devices = 1; }
   for (int i = 0; i < n_devices; i++) {
@@ -216,7 +296,7 @@ uint64_t zstdb200_kernel_launches(const zstdb200_ctx* ctx) { return ctx ? ctx->l
 
 int zstdb200_is_error(uint32_t code) { return is_err(code); }
 
-// Host-only frame-header parse, ZStdDecompress.cs:518-531, 590-622 (same function the kernels use).
+// Host-only frame-header parse, ZStdDecompress.cs:518-531, 590-622 (same rules as parse_item in zb_format.cuh).
 uint64_t zstdb200_get_decompressed_size(const void* src, uint32_t srcSize) {
   const u8* p = (const u8*)src;
   if (!p || srcSize < 5) return 0;
@@ -241,7 +321,8 @@ int zstdb200_decompress_batch(zstdb200_ctx* ctx, const void* const* src, const u
                               void* const* dst, const uint32_t* dstCap, uint32_t* result, size_t n) {
   if (!ctx) return 1;
   ctx->err.clear();
-  return run_host_batch(ctx, Op::Decompress, 0, 0, src, srcSize, dst, dstCap, result, n);
+  Job j{Op::Decompress, 0, 0, src, srcSize, dst, dstCap, result};
+  return run_host_batch(ctx, j, n);
 }
 
 uint32_t zstdb200_decompress(zstdb200_ctx* ctx, void* dst, uint32_t dstCapacity, const void* src, uint32_t srcSize) {
@@ -254,6 +335,30 @@ uint32_t zstdb200_decompress(zstdb200_ctx* ctx, void* dst, uint32_t dstCapacity,
   return r;
 }
 
+// Device-resident decode: the batch is cut into slices dealt to the context's streams (forked from and joined
+// back into `stream`) so that the entropy kernels of one slice overlap the execute kernel of another.
+static int decode_device_sliced(zstdb200_ctx* ctx, Device& d, const DecodeArgs& a, cudaStream_t user, cudaEvent_t* marks) {
+  int nl = 0;
+  if (marks || a.n < 2048) {   // timed runs and small batches: one launch sequence on the caller's stream
+    CK(decode_launch(a, user, &nl, marks));
+    ctx->launches += nl;
+    return 0;
+  }
+  const u32 per = std::max<u32>(1024, (a.n + 4 * NSTREAMS - 1) / (4 * NSTREAMS));
+  CK(cudaEventRecord(d.forkEv, user));
+  for (auto& s : d.stream) CK(cudaStreamWaitEvent(s, d.forkEv, 0));
+  u32 k = 0;
+  for (u32 lo = 0; lo < a.n; lo += per, k++) {
+    DecodeArgs b = a;
+    b.src_off += lo; b.src_size += lo; b.dst_off += lo; b.dst_cap += lo; b.result += lo; b.info += lo;
+    b.n = std::min(per, a.n - lo); b.item_base = a.item_base + lo;
+    CK(decode_launch(b, d.stream[k % NSTREAMS], &nl));
+  }
+  for (int s = 0; s < NSTREAMS; s++) { CK(cudaEventRecord(d.joinEv[s], d.stream[s])); CK(cudaStreamWaitEvent(user, d.joinEv[s], 0)); }
+  ctx->launches += nl;
+  return 0;
+}
+
 int zstdb200_decompress_batch_device(zstdb200_ctx* ctx, int device_index, const void* src_base, const uint64_t* src_off,
                                      const uint32_t* src_size, void* dst_base, const uint64_t* dst_off, const uint32_t* dst_cap,
                                      uint32_t* result, size_t n, void* stream) {
@@ -263,14 +368,12 @@ int zstdb200_decompress_batch_device(zstdb200_ctx* ctx, int device_index, const 
   if (n > ctx->maxItems) { ctx->err = "n exceeds zstdb200_max_items"; return 1; }
   Device& d = ctx->dev[device_index];
   CK(cudaSetDevice(d.id));
-  DecodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, d.d_info, d.d_lit, d.d_seq};
-  int nl = 0;
-  CK(decode_launch(a, stream ? (cudaStream_t)stream : d.stream, &nl));
-  ctx->launches += nl;
-  return 0;
+  DecodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, 0, d.d_info, d.d_lit, d.d_seq};
+  return decode_device_sliced(ctx, d, a, stream ? (cudaStream_t)stream : d.stream[0], nullptr);
 }
 
-// Same launch with CUDA events between the kernels: per-kernel device times for the bench's roofline block.
+// Same work as one launch sequence with CUDA events between the kernels: per-kernel device times for the
+// bench's roofline block.
 int zstdb200_decompress_batch_device_timed(zstdb200_ctx* ctx, int device_index, const void* src_base, const uint64_t* src_off,
                                            const uint32_t* src_size, void* dst_base, const uint64_t* dst_off, const uint32_t* dst_cap,
                                            uint32_t* result, size_t n, void* stream, float* kernel_ms, int max_kernels) {
@@ -280,13 +383,11 @@ int zstdb200_decompress_batch_device_timed(zstdb200_ctx* ctx, int device_index, 
   if (n > ctx->maxItems) { ctx->err = "n exceeds zstdb200_max_items"; return 1; }
   Device& d = ctx->dev[device_index];
   CK(cudaSetDevice(d.id));
-  cudaStream_t st = stream ? (cudaStream_t)stream : d.stream;
+  cudaStream_t st = stream ? (cudaStream_t)stream : d.stream[0];
   cudaEvent_t ev[DECODE_KERNELS + 1];
   for (auto& e : ev) CK(cudaEventCreate(&e));
-  DecodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, d.d_info, d.d_lit, d.d_seq};
-  int nl = 0;
-  CK(decode_launch(a, st, &nl, ev));
-  ctx->launches += nl;
+  DecodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, 0, d.d_info, d.d_lit, d.d_seq};
+  if (decode_device_sliced(ctx, d, a, st, ev)) return 1;
   CK(cudaStreamSynchronize(st));
   for (int k = 0; k < DECODE_KERNELS && k < max_kernels; k++) CK(cudaEventElapsedTime(&kernel_ms[k], ev[k], ev[k + 1]));
   for (auto& e : ev) cudaEventDestroy(e);
@@ -301,7 +402,8 @@ int zstdb200_compress_batch(zstdb200_ctx* ctx, int level, int checksum, const vo
   if (!ctx) return 1;
   ctx->err.clear();
   if (level < 1 || level > 3) { ctx->err = "level must be 1..3"; return 1; }
-  return run_host_batch(ctx, Op::Compress, level, checksum, src, srcSize, dst, dstCap, result, n);
+  Job j{Op::Compress, level, checksum, src, srcSize, dst, dstCap, result};
+  return run_host_batch(ctx, j, n);
 }
 
 uint32_t zstdb200_compress(zstdb200_ctx* ctx, int level, int checksum, void* dst, uint32_t dstCapacity, const void* src, uint32_t srcSize) {
@@ -324,9 +426,9 @@ int zstdb200_compress_batch_device(zstdb200_ctx* ctx, int device_index, int leve
   if (n > ctx->maxItems) { ctx->err = "n exceeds zstdb200_max_items"; return 1; }
   Device& d = ctx->dev[device_index];
   CK(cudaSetDevice(d.id));
-  EncodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, level, checksum};
+  EncodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, 0, level, checksum};
   int nl = 0;
-  CK(encode_launch(a, d.enc, stream ? (cudaStream_t)stream : d.stream, &nl));
+  CK(encode_launch(a, d.enc, stream ? (cudaStream_t)stream : d.stream[0], &nl));
   ctx->launches += nl;
   return 0;
 }

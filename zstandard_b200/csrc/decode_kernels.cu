@@ -14,9 +14,9 @@ namespace zb {
 // -----------------------------------------------------------------------------------------------
 // scratch addressing shared by the stages (see DESIGN.md "HBM layout")
 // -----------------------------------------------------------------------------------------------
-__device__ __forceinline__ u8* lit_region(const DecodeArgs& a, u32 f) { return a.lit_arena + (a.dst_off[f] & ~15ull) + 64ull * f; }
+__device__ __forceinline__ u8* lit_region(const DecodeArgs& a, u32 f) { return a.lit_arena + (a.dst_off[f] & ~15ull) + 64ull * (a.item_base + f); }
 __device__ __forceinline__ u64 lit_capacity(u32 cap) { return (u64)cap + 40; }
-__device__ __forceinline__ SeqRec* seq_region(const DecodeArgs& a, u32 f) { return a.seq_arena + 2 * (a.dst_off[f] / 3) + 32ull * f; }
+__device__ __forceinline__ SeqRec* seq_region(const DecodeArgs& a, u32 f) { return a.seq_arena + 2 * (a.dst_off[f] / 3) + 32ull * (a.item_base + f); }
 
 // =================================================================================================
 // k_parse

@@ -13,6 +13,7 @@ struct DecodeArgs {
   const u8* src_base; const u64* src_off; const u32* src_size;
   u8* dst_base; const u64* dst_off; const u32* dst_cap;
   u32* result; u32 n;
+  u32 item_base;       // index of item 0 within the arena numbering (slices of one batch share the arenas)
   FrameInfo* info;     // n records
   u8* lit_arena;       // decode_lit_arena_bytes()
   SeqRec* seq_arena;   // decode_seq_arena_bytes()

@@ -11,6 +11,7 @@ struct EncodeArgs {
   const u8* src_base; const u64* src_off; const u32* src_size;
   u8* dst_base; const u64* dst_off; const u32* dst_cap;
   u32* result; u32 n;
+  u32 item_base;   // index of item 0 within the scratch numbering (slices of one batch share the arenas)
   int level, checksum;
 };
 

@@ -92,6 +92,21 @@ ZB_HD u32 fshr(u32 lo, u32 hi, u32 s) {   // low 32 bits of (hi:lo) >> (s & 31)
 #endif
 }
 
+ZB_HD u32 fshl(u32 lo, u32 hi, u32 s) {   // high 32 bits of (hi:lo) << (s & 31)
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_l(lo, hi, s);
+#else
+  s &= 31; return s ? (hi << s) | (lo >> (32 - s)) : hi;
+#endif
+}
+ZB_HD u32 shr_c(u32 x, u32 n) {   // x >> n with n clamped to 32 (so n == 32 yields 0), as PTX shr.b32 defines it
+#if defined(__CUDA_ARCH__)
+  u32 r; asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n)); return r;
+#else
+  return n >= 32 ? 0 : x >> n;
+#endif
+}
+
 // ---- backward bit cursor -------------------------------------------------------------------------
 // A zstd bitstream of n bytes is read from its last byte towards its first (csharp/src/BitStream.cs:322-497).
 // We address it by P = number of still-unread bits counted from the first byte; reading k bits takes stream

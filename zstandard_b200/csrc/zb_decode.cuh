@@ -46,6 +46,22 @@ ZB_HD void seq_emit_long(SeqRec* out, u64& n, u64 cap, u32 off, u32 ll, u32 ml) 
 // (the reference's LookBits does the same, BitStream.cs:412-416)
 ZB_HD u32 top_bits(u64 w, u32 n) { return (u32)((w >> 1) >> (63 - n)); }
 
+// Offset value of one sequence and the repeat-offset history update (DecodeSequence :1487-1531), written
+// without data-dependent branches.  ofBits is the offset code, ofv its extra bits, llSym the literal-length code.
+ZB_HD u32 rep_resolve(u32& rep0, u32& rep1, u32& rep2, u32 ofBits, u32 ofv, u32 llSym) {
+  const u32 raw = ofBits ? of_base(ofBits) + ofv : 0;
+  const bool isRep = ofBits <= 1;
+  const u32 idx = raw + (llSym == 0);                                  // 0..3 when isRep
+  const u32 pick = idx == 0 ? rep0 : (idx == 1 ? rep1 : (idx == 2 ? rep2 : rep0 - 1));
+  const u32 repv = pick + (pick == 0);                                 // 0 is not valid: forced to 1 (:1515)
+  const u32 offset = isRep ? repv : raw;
+  const bool shift1 = !isRep || idx >= 1;                              // history is untouched only when idx == 0
+  const bool shift2 = !isRep || idx >= 2;
+  const u32 n2 = shift2 ? rep1 : rep2, n1 = shift1 ? rep0 : rep1;
+  rep2 = n2; rep1 = n1; rep0 = offset;
+  return offset;
+}
+
 // Walks the frame at item `src` (size bytes, first block header at body_off) and decodes every compressed
 // block's sequences.  Stops silently at structural errors that the execute stage will report itself from the
 // same headers; records entropy-level failures in `res`.
@@ -105,46 +121,64 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, SeqTableSet& 
           { u64 w = bc_window64(c, P); u32 lg = T.log[KIND_LL]; stLL = top_bits(w, lg); w <<= lg; P -= (i32)lg;
             lg = T.log[KIND_OF]; stOF = top_bits(w, lg); w <<= lg; P -= (i32)lg;
             lg = T.log[KIND_ML]; stML = top_bits(w, lg); P -= (i32)lg; }             // :1578-1580 (<= 26 bits)
-          for (u32 i = 0; i < nbSeq; i++) {
-            if (P < 0) { bad = true; break; }                                      // loop test :1582 (overflow)
-            const u64 w0 = bc_window64(c, P);                                      // depends on P only: overlaps the table reads
+          u32 i = 0;
+          // ---- fast loop: >= 128 unread bits, so no over-read is possible (a sequence takes <= 89 bits) and
+          //      all six fields come out of 32-bit registers; leaves to the careful loop when a sequence
+          //      carries >= 32 value bits (rare: very long lengths / offsets) ----
+          while (i < nbSeq && P >= 128) {
+            const i32 g = c.gofs + P - 64;
+            const u32* wp = c.words + (g >> 5); const u32 sh = (u32)g & 31;
+            const u32 w0 = wp[0], w1 = wp[1], w2 = sh ? wp[2] : 0;
             const u32 cLL = tLL[stLL * sLLs], cOF = tOF[stOF * sOFs], cML = tML[stML * sMLs];
-            const u32 llBits = (cLL >> 14) & 31, mlBits = (cML >> 14) & 31, ofBits = (cOF >> 14) & 31;
-            const u32 nLL = (cLL >> 10) & 15, nML = (cML >> 10) & 15, nOF = (cOF >> 10) & 15;
-            const u32 llSym = cLL >> 19, mlSym = cML >> 19;
+            const u32 lo = fshr(w0, w1, sh), hi = fshr(w1, w2, sh);                // 64-bit window ending at P
+            const u32 sums = (cLL & 0xFFFF) + (cML & 0xFFFF) + (cOF & 0xFFFF);     // byte 0: value bits, byte 1: state bits
+            const u32 valBits = sums & 0xFF, stBits = sums >> 8;
+            if (valBits >= 32) break;
+            const u32 ofBits = cOF & 0xFF, mlBits = cML & 0xFF, llBits = cLL & 0xFF;
+            const u32 ofv = shr_c(hi, 32 - ofBits);                                // read order: offset, matchLength, litLength
+            const u32 mlv = shr_c(hi << ofBits, 32 - mlBits);                      // (:1504, :1534, :1542)
+            const u32 llv = shr_c(hi << (ofBits + mlBits), 32 - llBits);
+            const u32 h2 = fshl(lo, hi, valBits);                                  // the 32 bits after the value bits
+            const u32 nLL = (cLL >> 8) & 0xFF, nML = (cML >> 8) & 0xFF, nOF = (cOF >> 8) & 0xFF;
+            const u32 llSym = cLL >> 25, mlSym = cML >> 25;
+            const u32 offset = rep_resolve(rep0, rep1, rep2, ofBits, ofv, llSym);
+            const u32 ml = mlBase[mlSym] + mlv, ll = llBase[llSym] + llv;
+            if ((ll | ml) <= 65535) { if (n < cap) { out[n].x = offset; out[n].y = ll | (ml << 16); } n++; }
+            else seq_emit_long(out, n, cap, offset, ll, ml);
+            stLL = ((cLL >> 16) & 0x1FF) + shr_c(h2, 32 - nLL);                    // state update LL, ML, OF (:1547-1550)
+            stML = ((cML >> 16) & 0x1FF) + shr_c(h2 << nLL, 32 - nML);
+            stOF = ((cOF >> 16) & 0x1FF) + shr_c(h2 << (nLL + nML), 32 - nOF);
+            const i32 Pn = P - (i32)(valBits + stBits);
+            if (((P ^ Pn) >> 10) != 0) prefetch_line(streamBase + ((c.gofs + Pn) >> 3) - 256);
+            P = Pn; i++;
+          }
+          decoded = i;
+          // ---- careful loop: stream tail and oversized sequences ----
+          for (; i < nbSeq; i++) {
+            if (P < 0) { bad = true; break; }                                      // loop test :1582 (overflow)
+            const u64 w0 = bc_window64(c, P);
+            const u32 cLL = tLL[stLL * sLLs], cOF = tOF[stOF * sOFs], cML = tML[stML * sMLs];
+            const u32 llBits = cLL & 0xFF, mlBits = cML & 0xFF, ofBits = cOF & 0xFF;
+            const u32 nLL = (cLL >> 8) & 0xFF, nML = (cML >> 8) & 0xFF, nOF = (cOF >> 8) & 0xFF;
+            const u32 llSym = cLL >> 25, mlSym = cML >> 25;
             const u32 valBits = ofBits + mlBits + llBits, stBits = nLL + nML + nOF;
             u64 w = w0;
-            const u32 ofv = top_bits(w, ofBits); w <<= ofBits;                     // read order: offset, matchLength, litLength
-            const u32 mlv = top_bits(w, mlBits); w <<= mlBits;                     // (:1504, :1534, :1542)
+            const u32 ofv = top_bits(w, ofBits); w <<= ofBits;
+            const u32 mlv = top_bits(w, mlBits); w <<= mlBits;
             const u32 llv = top_bits(w, llBits); w <<= llBits;
             const i32 Pv = P - (i32)valBits;
             if (Pv < 0) { bad = true; break; }     // values came from beyond the stream start (DESIGN.md "over-read")
             if (valBits + stBits > 64) w = bc_window64(c, Pv);                     // rare: more than 64 bits in one sequence
-            // repcode resolution (:1509-1530), written without data-dependent branches
-            u32 offset;
-            {
-              const u32 raw = ofBits ? of_base(ofBits) + ofv : 0;
-              const bool isRep = ofBits <= 1;
-              const u32 idx = raw + (llSym == 0);                                  // 0..3 when isRep
-              const u32 pick = idx == 0 ? rep0 : (idx == 1 ? rep1 : (idx == 2 ? rep2 : rep0 - 1));
-              const u32 repv = pick + (pick == 0);                                 // 0 is not valid: forced to 1 (:1515)
-              offset = isRep ? repv : raw;
-              const bool shift1 = !isRep || idx >= 1;                              // history changes unless idx == 0
-              const bool shift2 = !isRep || idx >= 2;
-              const u32 n2 = shift2 ? rep1 : rep2, n1 = shift1 ? rep0 : rep1;
-              rep2 = n2; rep1 = n1; rep0 = offset;
-            }
+            const u32 offset = rep_resolve(rep0, rep1, rep2, ofBits, ofv, llSym);
             const u32 ml = mlBase[mlSym] + mlv, ll = llBase[llSym] + llv;
             if ((ll | ml) <= 65535) { if (n < cap) { out[n].x = offset; out[n].y = ll | (ml << 16); } n++; }
             else seq_emit_long(out, n, cap, offset, ll, ml);
             decoded++;
-            // state update LL, ML, OF (:1547-1550); past the last sequence these bits do not exist
-            stLL = (cLL & 0x3FF) + top_bits(w, nLL); w <<= nLL;
-            stML = (cML & 0x3FF) + top_bits(w, nML); w <<= nML;
-            stOF = (cOF & 0x3FF) + top_bits(w, nOF);
-            const i32 Pn = Pv - (i32)stBits;
-            if (((P ^ Pn) >> 10) != 0 && Pn > 2048) prefetch_line(streamBase + ((c.gofs + Pn) >> 3) - 256);
-            P = Pn;
+            // past the last sequence these bits do not exist (the stream ends after its value bits)
+            stLL = ((cLL >> 16) & 0x1FF) + top_bits(w, nLL); w <<= nLL;
+            stML = ((cML >> 16) & 0x1FF) + top_bits(w, nML); w <<= nML;
+            stOF = ((cOF >> 16) & 0x1FF) + top_bits(w, nOF);
+            P = Pv - (i32)stBits;
           }
         }
         // terminator; when the region is full the last slot is sacrificed so that the execute stage stops there

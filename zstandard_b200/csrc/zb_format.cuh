@@ -202,12 +202,13 @@ ZB_HD u32 read_ncount(NormT norm, u32* maxSV, u32* tableLog, const u8* hb, u32 h
 // Sequence-symbol decode tables (BuildFSETable :958-1034, rle :937-953, BuildSeqTable :1040-1079)
 // =====================================================================================================
 // Cell layout (one u32 per state; the reference's 8-byte SeqSymbol minus baseValue, which is recovered from
-// the symbol through the 36/53/32-entry base tables):
-//   bits  0..9   nextState base (0..511)
-//   bits 10..13  nbBits (state bits to read, 0..9)
-//   bits 14..18  nbAdditionalBits (0..31)
-//   bits 19..24  symbol (0..52)
-ZB_HD u32 seq_cell(u32 nextState, u32 nbBits, u32 nbAdd, u32 sym) { return nextState | (nbBits << 10) | (nbAdd << 14) | (sym << 19); }
+// the symbol through the 36/53/32-entry base tables).  The two bit counts sit in the low bytes so that one
+// masked add over the three cells of a sequence yields both the value-bit and the state-bit totals:
+//   bits  0..7   nbAdditionalBits (0..31)
+//   bits  8..15  nbBits (state bits to read, 0..9)
+//   bits 16..24  nextState base (0..511)
+//   bits 25..30  symbol (0..52)
+ZB_HD u32 seq_cell(u32 nextState, u32 nbBits, u32 nbAdd, u32 sym) { return nbAdd | (nbBits << 8) | (nextState << 16) | (sym << 25); }
 
 // base / extra-bit tables: ZStdInternal.cs:158-180, ZStdDecompress.cs:1081-1107
 #if defined(__CUDACC__)
@@ -250,7 +251,7 @@ ZB_HD void build_seq_table(u32* cells, u32 stride, NormT norm, u32 maxSV, u32 ta
   for (u32 u = 0; u < tableSize; u++) {
     u32 sym = cells[u * stride], next = symbolNext[sym]++;
     u32 nb = tableLog - highbit(next);
-    cells[u * stride] = seq_cell(((next << nb) - tableSize) & 0x3FF, nb, kind_nbadd(kind, sym), sym);
+    cells[u * stride] = seq_cell(((next << nb) - tableSize) & 0x1FF, nb, kind_nbadd(kind, sym), sym);
   }
 }
 
