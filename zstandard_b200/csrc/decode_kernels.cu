@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(128) k_parse(DecodeArgs a) {
 struct HufSmem {
   u16 table[8][1 << HUF_LOG_MAX];
   HufBuildWk wk[8];
+  u32 ring[16][32];      // per-lane (= per-stream) bitstream read-ahead (BitRing)
 };
 
 __global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
@@ -92,11 +93,11 @@ __global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
         if (ok) {
           bool good = true;
           if (lh.single) {
-            if (sub == 0) good = huf_decode_stream(body, bodySize, lit + litRun, lh.litSize, dt, tableLog);   // HufDecompress.cs:247-264
+            if (sub == 0) good = huf_decode_stream(body, bodySize, lit + litRun, lh.litSize, dt, tableLog, &sm.ring[0][lane], 32);   // HufDecompress.cs:247-264
           } else {
             HufStream st;
             good = huf_split4(body, bodySize, lh.litSize, sub, st);
-            if (good) good = huf_decode_stream(st.src, st.len, lit + litRun + st.outOfs, st.count, dt, tableLog);
+            if (good) good = huf_decode_stream(st.src, st.len, lit + litRun + st.outOfs, st.count, dt, tableLog, &sm.ring[0][lane], 32);
           }
           unsigned okmask = __ballot_sync(gmask, good);
           if ((okmask & gmask) != gmask) ok = false;
@@ -122,6 +123,7 @@ struct SeqSmem {
   u32 llBase[36], mlBase[53];
   s16 norm[53][32];      // per-lane scratch of the table builder, lane-interleaved like the tables
   u16 next[53][32];
+  u32 ring[16][32];      // per-lane bitstream read-ahead (BitRing)
 };
 
 __global__ void __launch_bounds__(32) k_seq(DecodeArgs a) {
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(32) k_seq(DecodeArgs a) {
   T.defs[KIND_LL] = sm.defLL; T.defs[KIND_OF] = sm.defOF; T.defs[KIND_ML] = sm.defML;
   SeqFrameOut res;
   seq_decode_frame(a.src_base + a.src_off[f], a.src_size[f], fi.body_off, T, seq_region(a, f), seq_capacity(a.dst_cap[f]), res, sm.llBase, sm.mlBase,
-                   Strided<s16>{&sm.norm[0][lane], 32}, Strided<u16>{&sm.next[0][lane], 32});
+                   Strided<s16>{&sm.norm[0][lane], 32}, Strided<u16>{&sm.next[0][lane], 32}, &sm.ring[0][lane], 32);
   if (res.err_block != 0xFFFFFFFFu) {
     a.info[f].seq_err_block = res.err_block; a.info[f].seq_err_code = res.err_code; a.info[f].seq_err_index = res.err_index;
   }

@@ -65,10 +65,11 @@ ZB_HD u32 rep_resolve(u32& rep0, u32& rep1, u32& rep2, u32 ofBits, u32 ofv, u32 
 // Walks the frame at item `src` (size bytes, first block header at body_off) and decodes every compressed
 // block's sequences.  Stops silently at structural errors that the execute stage will report itself from the
 // same headers; records entropy-level failures in `res`.
-// llBase/mlBase: base-value tables; norm/symbolNext: >= 53 entries of per-thread scratch each.
+// llBase/mlBase: base-value tables; norm/symbolNext: >= 53 entries of per-thread scratch each;
+// ringMem/ringStride: 16 words of per-thread bitstream read-ahead (BitRing).
 template <class NormT, class NextT>
 ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, SeqTableSet& T, SeqRec* out, u64 cap, SeqFrameOut& res,
-                            const u32* llBase, const u32* mlBase, NormT norm, NextT symbolNext) {
+                            const u32* llBase, const u32* mlBase, NormT norm, NextT symbolNext, u32* ringMem, u32 ringStride) {
   res.err_block = 0xFFFFFFFFu; res.err_code = 0; res.err_index = 0;
   u32 pos = body_off, blk = 0;
   u32 rep0 = 1, rep1 = 4, rep2 = 8;                      // ZStdInternal.cs:111, ZStdDecompress.cs:2492
@@ -113,8 +114,6 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, SeqTableSet& 
         if (!bc_init(c, sp + hdr, ssz - hdr)) bad = true;                          // :1577 -> corruption_detected
         if (!bad) {
           i32 P = c.P;
-          const u8* const streamBase = (const u8*)c.words;
-          if (P > 2048) { prefetch_line(streamBase + ((c.gofs + P) >> 3) - 128); prefetch_line(streamBase + ((c.gofs + P) >> 3) - 256); }
           const u32 *tLL = T.cur[KIND_LL], *tOF = T.cur[KIND_OF], *tML = T.cur[KIND_ML];
           const u32 sLLs = T.curStride[KIND_LL], sOFs = T.curStride[KIND_OF], sMLs = T.curStride[KIND_ML];
           u32 stLL, stOF, stML;
@@ -125,12 +124,12 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, SeqTableSet& 
           // ---- fast loop: >= 128 unread bits, so no over-read is possible (a sequence takes <= 89 bits) and
           //      all six fields come out of 32-bit registers; leaves to the careful loop when a sequence
           //      carries >= 32 value bits (rare: very long lengths / offsets) ----
+          BitRing ring;
+          if (nbSeq && P >= 128) ring_init(ring, ringMem, ringStride, sp + hdr, ssz - hdr);
           while (i < nbSeq && P >= 128) {
-            const i32 g = c.gofs + P - 64;
-            const u32* wp = c.words + (g >> 5); const u32 sh = (u32)g & 31;
-            const u32 w0 = wp[0], w1 = wp[1], w2 = sh ? wp[2] : 0;
+            u32 lo, hi;
+            ring_window(ring, P, lo, hi);                                          // 64-bit window ending at P
             const u32 cLL = tLL[stLL * sLLs], cOF = tOF[stOF * sOFs], cML = tML[stML * sMLs];
-            const u32 lo = fshr(w0, w1, sh), hi = fshr(w1, w2, sh);                // 64-bit window ending at P
             const u32 sums = (cLL & 0xFFFF) + (cML & 0xFFFF) + (cOF & 0xFFFF);     // byte 0: value bits, byte 1: state bits
             const u32 valBits = sums & 0xFF, stBits = sums >> 8;
             if (valBits >= 32) break;
@@ -149,7 +148,7 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, SeqTableSet& 
             stML = ((cML >> 16) & 0x1FF) + shr_c(h2 << nLL, 32 - nML);
             stOF = ((cOF >> 16) & 0x1FF) + shr_c(h2 << (nLL + nML), 32 - nOF);
             const i32 Pn = P - (i32)(valBits + stBits);
-            if (((P ^ Pn) >> 10) != 0) prefetch_line(streamBase + ((c.gofs + Pn) >> 3) - 256);
+            ring_advance(ring, Pn);
             P = Pn; i++;
           }
           decoded = i;
@@ -218,19 +217,35 @@ ZB_HD bool huf_split4(const u8* body, u32 bodySize, u32 n, u32 lane, HufStream& 
 
 // Decodes `count` symbols of one backward stream into out[0..count).  true iff the stream was consumed
 // exactly (EndOfDStream, HufDecompress.cs:350-353 / :261) — which also implies it was never over-read.
-ZB_HD bool huf_decode_stream(const u8* src, u32 len, u8* out, u32 count, const u16* dt, u32 tableLog) {
+ZB_HD bool huf_decode_stream(const u8* src, u32 len, u8* out, u32 count, const u16* dt, u32 tableLog, u32* ringMem, u32 ringStride) {
   BitCursor c;
   if (!bc_init(c, src, len)) return false;                                         // InitDStream errors :304-307
   i32 P = c.P;
   u32 left = count;
   const u32 sh = 64 - tableLog;
-  const u8* const streamBase = (const u8*)c.words;
-  if (P > 2048) { prefetch_line(streamBase + ((c.gofs + P) >> 3) - 128); prefetch_line(streamBase + ((c.gofs + P) >> 3) - 256); }
   // head: reach 4-byte alignment of the output
   while (left && ((uintptr_t)out & 3)) {
     u64 w = bc_window64(c, P);
     u32 cell = dt[(u32)(w >> sh)];
     *out++ = (u8)cell; P -= (i32)(cell >> 8); left--;
+  }
+  // fast loop: 4 symbols (<= 48 bits) per iteration out of the shared-memory ring
+  if (left >= 4 && P >= 128) {
+    BitRing ring;
+    ring_init(ring, ringMem, ringStride, src, len);
+    const u32 sh32 = 32 - tableLog;
+    while (left >= 4 && P >= 128) {
+      u32 lo, hi;
+      ring_window(ring, P, lo, hi);
+      const u32 c0 = dt[hi >> sh32]; u32 used = c0 >> 8;
+      const u32 c1 = dt[fshl(lo, hi, used) >> sh32]; used += c1 >> 8;
+      const u32 c2 = dt[fshl(lo, hi, used) >> sh32]; used += c2 >> 8;
+      const u32 c3 = dt[(used < 32 ? fshl(lo, hi, used) : (lo << (used - 32))) >> sh32]; used += c3 >> 8;
+      *(u32*)out = (c0 & 0xFF) | ((c1 & 0xFF) << 8) | ((c2 & 0xFF) << 16) | ((c3 & 0xFF) << 24);
+      out += 4; left -= 4;
+      P -= (i32)used;
+      ring_advance(ring, P);
+    }
   }
   while (left >= 4) {
     u64 w = bc_window64(c, P);
@@ -238,9 +253,7 @@ ZB_HD bool huf_decode_stream(const u8* src, u32 len, u8* out, u32 count, const u
     u32 c1 = dt[(u32)(w >> sh)]; w <<= (c1 >> 8);
     u32 c2 = dt[(u32)(w >> sh)]; w <<= (c2 >> 8);
     u32 c3 = dt[(u32)(w >> sh)];
-    const i32 Pn = P - (i32)((c0 >> 8) + (c1 >> 8) + (c2 >> 8) + (c3 >> 8));
-    if (((P ^ Pn) >> 10) != 0 && Pn > 2048) prefetch_line(streamBase + ((c.gofs + Pn) >> 3) - 256);
-    P = Pn;
+    P -= (i32)((c0 >> 8) + (c1 >> 8) + (c2 >> 8) + (c3 >> 8));
     *(u32*)out = (c0 & 0xFF) | ((c1 & 0xFF) << 8) | ((c2 & 0xFF) << 16) | ((c3 & 0xFF) << 24);
     out += 4; left -= 4;
   }
