@@ -482,7 +482,10 @@ cudaError_t decode_configure() {
 
 const char* const kDecodeKernelNames[DECODE_KERNELS] = {"k_parse", "k_huf", "k_seq", "k_exec", "k_xxh"};
 
-cudaError_t decode_launch(const DecodeArgs& a, cudaStream_t st, int* launches, cudaEvent_t* marks) {
+// The pipeline in two halves so that callers can put them on different streams: the entropy half is latency
+// bound (few warps per SM, shared-memory limited), the execute half is issue/LSU bound and needs no shared
+// memory, so the two co-reside on an SM when they belong to different slices of a batch.
+cudaError_t decode_launch_entropy(const DecodeArgs& a, cudaStream_t st, int* launches, cudaEvent_t* marks) {
   if (a.n == 0) return cudaSuccess;
   if (marks) cudaEventRecord(marks[0], st);
   k_parse<<<(a.n + 127) / 128, 128, 0, st>>>(a);
@@ -491,12 +494,22 @@ cudaError_t decode_launch(const DecodeArgs& a, cudaStream_t st, int* launches, c
   if (marks) cudaEventRecord(marks[2], st);
   k_seq<<<(a.n + 31) / 32, 32, sizeof(SeqSmem), st>>>(a);
   if (marks) cudaEventRecord(marks[3], st);
+  if (launches) *launches += 3;
+  return cudaGetLastError();
+}
+cudaError_t decode_launch_exec(const DecodeArgs& a, cudaStream_t st, int* launches, cudaEvent_t* marks) {
+  if (a.n == 0) return cudaSuccess;
   k_exec<<<(a.n + (EXEC_THREADS / 32) - 1) / (EXEC_THREADS / 32), EXEC_THREADS, 0, st>>>(a);
   if (marks) cudaEventRecord(marks[4], st);
   k_xxh<<<(a.n * 4 + 127) / 128, 128, 0, st>>>(a);
   if (marks) cudaEventRecord(marks[5], st);
-  if (launches) *launches += 5;
+  if (launches) *launches += 2;
   return cudaGetLastError();
+}
+cudaError_t decode_launch(const DecodeArgs& a, cudaStream_t st, int* launches, cudaEvent_t* marks) {
+  cudaError_t e = decode_launch_entropy(a, st, launches, marks);
+  if (e != cudaSuccess) return e;
+  return decode_launch_exec(a, st, launches, marks);
 }
 
 }  // namespace zb
