@@ -27,14 +27,13 @@ using namespace zb;
 
 namespace {
 
-constexpr int NSTREAMS = 4;          // streams 0,1: copies in + entropy kernels; streams 2,3: execute kernels + copies out
-constexpr int NSLICE_EVENTS = 64;
+constexpr int NSTREAMS = 4;
 constexpr size_t SLICE_BYTES = 48u << 20;   // uncompressed bytes per slice (several slices per stream per GiB)
 
 struct Device {
   int id = 0;
   cudaStream_t stream[NSTREAMS] = {};
-  cudaEvent_t forkEv = nullptr, joinEv[NSTREAMS] = {}, sliceEv[NSLICE_EVENTS] = {};
+  cudaEvent_t forkEv = nullptr, joinEv[NSTREAMS] = {};
   // device memory
   u8 *d_src = nullptr, *d_dst = nullptr;       // staging for the host-pointer API
   u64 *d_srcOff = nullptr, *d_dstOff = nullptr; u32 *d_srcSize = nullptr, *d_dstCap = nullptr, *d_result = nullptr;
@@ -72,7 +71,6 @@ int alloc_device(zstdb200_ctx* ctx, Device& d) {
   for (auto& s : d.stream) CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&d.forkEv, cudaEventDisableTiming));
   for (auto& e : d.joinEv) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  for (auto& e : d.sliceEv) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   const size_t items = ctx->maxItems;
   CK(cudaMalloc(&d.d_src, ctx->srcCap + 256));
   CK(cudaMalloc(&d.d_dst, ctx->dstSpan + 256));
@@ -101,7 +99,6 @@ void free_device(Device& d) {
   for (auto& s : d.stream) if (s) cudaStreamDestroy(s);
   if (d.forkEv) cudaEventDestroy(d.forkEv);
   for (auto& e : d.joinEv) if (e) cudaEventDestroy(e);
-  for (auto& e : d.sliceEv) if (e) cudaEventDestroy(e);
 }
 
 struct Range { size_t lo, hi; };
@@ -177,8 +174,7 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
   cudaError_t e;
   for (size_t s = 0; s < slices.size(); s++) {
     const size_t a = slices[s].lo, b = slices[s].hi, cnt = b - a;
-    cudaStream_t st = d.stream[s % 2];            // copies in + entropy kernels (decode) / everything (encode)
-    cudaStream_t sx = j.op == Op::Decompress ? d.stream[2 + s % 2] : st;   // execute kernels + copies out
+    cudaStream_t st = d.stream[s % NSTREAMS];
     // input bytes of the slice
     const size_t inLo = d.h_srcOff[a], inHi = d.h_srcOff[b - 1] + d.h_srcSize[b - 1];
     if (srcDirect) {
@@ -195,10 +191,7 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     if (j.op == Op::Decompress) {
       DecodeArgs ar{d.d_src, d.d_srcOff + a, d.d_srcSize + a, d.d_dst, d.d_dstOff + a, d.d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
                     d.d_info + a, d.d_lit, d.d_seq};
-      e = decode_launch_entropy(ar, st, &nl);
-      if (!e) e = cudaEventRecord(d.sliceEv[s % NSLICE_EVENTS], st);
-      if (!e) e = cudaStreamWaitEvent(sx, d.sliceEv[s % NSLICE_EVENTS], 0);
-      if (!e) e = decode_launch_exec(ar, sx, &nl);
+      e = decode_launch(ar, st, &nl);
     } else {
       EncodeArgs ar{d.d_src, d.d_srcOff + a, d.d_srcSize + a, d.d_dst, d.d_dstOff + a, d.d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
                     j.level, j.checksum};
@@ -206,11 +199,11 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     }
     *launches += nl;
     if (e) return fail("kernel launch", e);
-    e = cudaMemcpyAsync(d.h_result + a, d.d_result + a, cnt * 4, cudaMemcpyDeviceToHost, sx); if (e) return fail("D2H result", e);
+    e = cudaMemcpyAsync(d.h_result + a, d.d_result + a, cnt * 4, cudaMemcpyDeviceToHost, st); if (e) return fail("D2H result", e);
     const size_t outLo = d.h_dstOff[a], outHi = d.h_dstOff[b - 1] + d.h_dstCap[b - 1];
     if (outHi > outLo) {
       u8* hostDst = dstDirect ? dstBase + outLo : d.h_dst + outLo;
-      e = cudaMemcpyAsync(hostDst, d.d_dst + outLo, outHi - outLo, cudaMemcpyDeviceToHost, sx); if (e) return fail("D2H dst", e);
+      e = cudaMemcpyAsync(hostDst, d.d_dst + outLo, outHi - outLo, cudaMemcpyDeviceToHost, st); if (e) return fail("D2H dst", e);
     }
   }
   for (auto& st : d.stream) { e = cudaStreamSynchronize(st); if (e) return fail("stream sync", e); }
@@ -359,11 +352,7 @@ static int decode_device_sliced(zstdb200_ctx* ctx, Device& d, const DecodeArgs& 
     DecodeArgs b = a;
     b.src_off += lo; b.src_size += lo; b.dst_off += lo; b.dst_cap += lo; b.result += lo; b.info += lo;
     b.n = std::min(per, a.n - lo); b.item_base = a.item_base + lo;
-    cudaStream_t se = d.stream[k % 2], sx = d.stream[2 + k % 2];
-    CK(decode_launch_entropy(b, se, &nl));
-    CK(cudaEventRecord(d.sliceEv[k % NSLICE_EVENTS], se));
-    CK(cudaStreamWaitEvent(sx, d.sliceEv[k % NSLICE_EVENTS], 0));
-    CK(decode_launch_exec(b, sx, &nl));
+    CK(decode_launch(b, d.stream[k % NSTREAMS], &nl));
   }
   for (int s = 0; s < NSTREAMS; s++) { CK(cudaEventRecord(d.joinEv[s], d.stream[s])); CK(cudaStreamWaitEvent(user, d.joinEv[s], 0)); }
   ctx->launches += nl;
