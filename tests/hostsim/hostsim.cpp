@@ -8,6 +8,7 @@
 #include <cstring>
 #include <vector>
 #include "../../zstandard_b200/csrc/zb_decode.cuh"
+#include "../../zstandard_b200/csrc/zb_encode.cuh"
 
 using namespace zb;
 
@@ -194,4 +195,17 @@ extern "C" uint32_t hostsim_stages(const uint8_t* src_in, uint32_t size, uint32_
   memcpy(rec_out, recs.data(), (size_t)n * 8);
   info_out[0] = fi.huf_err_block; info_out[1] = fi.huf_err_code; info_out[2] = res.err_block; info_out[3] = res.err_code; info_out[4] = res.err_index;
   return 0;
+}
+
+// ---- encoder replay: one frame through zb_encode.cuh's encode_frame (checksum slot left for the caller) ----
+extern "C" uint32_t hostsim_compress(uint8_t* dst, uint32_t cap, const uint8_t* src_in, uint32_t size, int level, int checksum) {
+  std::vector<u8> padded(size + 64, 0);
+  u8* src = padded.data() + 16;
+  if (size) memcpy(src, src_in, size);
+  const u32 seqCap = BLOCKSIZE_MAX / 4 + 64;
+  std::vector<u32> table(enc_table_words(level)); std::vector<u8> lits(BLOCKSIZE_MAX + 64); std::vector<u32> seqs(2 * seqCap);
+  std::vector<u8> codes(3 * seqCap); std::vector<u16> ct(3 * 514 + 16); std::vector<u8> tmp(BLOCKSIZE_MAX + 4096);
+  EncScratch sc; sc.table = table.data(); sc.lits = lits.data(); sc.seqs = seqs.data(); sc.seqCap = seqCap; sc.codes = codes.data();
+  sc.ctables = ct.data(); sc.tmp = tmp.data();
+  return encode_frame(src, size, dst, cap, level, checksum, sc);
 }

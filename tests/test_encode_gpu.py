@@ -1,0 +1,82 @@
+"""GPU encoder through the C ABI: frames must be accepted by the oracle (the reference decoder's rules) and libzstd,
+round-trip bit-exact, match the CPU replay of the same code byte for byte, and stay in the ratio band."""
+import ctypes
+import random
+
+import numpy as np
+import pytest
+
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [0, 1, 2, 5, 17, 63, 64, 100, 255, 256, 1000, 1024, 4096, 5000, 16384, 65536, 70000, 131072, 131073, 200000, 300000]
+
+
+def _compress(ctx, payloads, level, checksum=True, caps=None):
+    import zstandard_b200 as zb
+    caps = caps or [zb.ZStdCompress.CompressBound(len(p)) for p in payloads]
+    dsts = [np.zeros(max(c, 1), dtype=np.uint8)[:c] for c in caps]
+    res = ctx.compress_batch(payloads, dsts, level=level, checksum=checksum)
+    return res, dsts
+
+
+def test_frames_round_trip_through_reference_rules(gpu_ctx, oracle, hostsim):
+    from tools import zstd_ref
+    lib = hostsim.lib
+    lib.hostsim_compress.restype = ctypes.c_uint32
+    lib.hostsim_compress.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int]
+    rng = random.Random(6)
+    payloads = [helpers.sample_payload(rng, t % 6, rng.choice(SIZES)) for t in range(120)]
+    for level in (1, 2, 3):
+        for checksum in (True, False):
+            res, dsts = _compress(gpu_ctx, payloads, level, checksum)
+            for p, r, d in zip(payloads, res, dsts):
+                assert not helpers.is_err(int(r)), hex(int(r))
+                f = d[:int(r)].tobytes()
+                ro, oo, _ = oracle.decompress(f, len(p))
+                assert ro == len(p) and oo == p, (len(p), level, hex(ro))
+                assert zstd_ref.decompress(f, len(p)) == p
+                # the GPU must produce exactly what the CPU replay of the same code produces
+                cap = len(p) + len(p) // 128 + 128
+                buf = ctypes.create_string_buffer(cap)
+                n = lib.hostsim_compress(buf, cap, p, len(p), level, 1 if checksum else 0)
+                assert f[:n] == buf.raw[:n] and len(f) == n + (4 if checksum else 0)
+
+
+def test_gpu_frames_decode_on_gpu(gpu_ctx):
+    rng = random.Random(7)
+    payloads = [helpers.sample_payload(rng, t % 6, rng.choice(SIZES)) for t in range(60)]
+    res, dsts = _compress(gpu_ctx, payloads, 3, True)
+    frames = [d[:int(r)] for r, d in zip(res, dsts)]
+    outs = [np.zeros(max(len(p), 1), dtype=np.uint8)[:len(p)] for p in payloads]
+    dres = gpu_ctx.decompress_batch(frames, outs)
+    for p, r, o in zip(payloads, dres, outs):
+        assert int(r) == len(p) and o.tobytes() == p
+
+
+@pytest.mark.parametrize("kind", ["log", "tick", "mixed"])
+def test_ratio_band_and_properties_at_size(gpu_ctx, kind):
+    """16 MiB in 128 KiB chunks (BASELINE.json config 3 shape): ratio within 3 % of libzstd at the same level,
+    every frame decodes back (through libzstd, an independent decoder) to its chunk."""
+    from tools import corpus, zstd_ref
+    total, chunk = 16 << 20, 131072
+    raw = corpus.make(kind, total)
+    chunks = [raw[i:i + chunk] for i in range(0, total, chunk)]
+    for level in (1, 2, 3):
+        res, dsts = _compress(gpu_ctx, chunks, level, True)
+        assert not any(helpers.is_err(int(r)) for r in res)
+        ours = int(res.astype(np.int64).sum())
+        _, off = zstd_ref.compress_chunks(raw, chunk, level=level, checksum=True)
+        ref = int(off[-1])
+        assert ours <= ref * 1.03, (kind, level, ours, ref)
+        for k in range(0, len(chunks), 7):
+            assert zstd_ref.decompress(dsts[k][:int(res[k])].tobytes(), chunk) == chunks[k].tobytes()
+
+
+def test_destination_too_small_is_per_item(gpu_ctx):
+    from tools import corpus
+    a, b = corpus.log(5000).tobytes(), corpus.tick(5000).tobytes()
+    res, dsts = _compress(gpu_ctx, [a, b, a], 3, True, caps=[6000, 50, 6000])
+    assert not helpers.is_err(int(res[0])) and not helpers.is_err(int(res[2]))
+    assert int(res[1]) == helpers.err(70)
