@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <string>
@@ -339,7 +340,8 @@ uint32_t zstdb200_decompress(zstdb200_ctx* ctx, void* dst, uint32_t dstCapacity,
 // back into `stream`) so that the entropy kernels of one slice overlap the execute kernel of another.
 static int decode_device_sliced(zstdb200_ctx* ctx, Device& d, const DecodeArgs& a, cudaStream_t user, cudaEvent_t* marks) {
   int nl = 0;
-  if (marks || a.n < 2048) {   // timed runs and small batches: one launch sequence on the caller's stream
+  static const bool noSlice = getenv("ZSTDB200_NO_SLICE") != nullptr;   // profiling aid: whole-batch kernels
+  if (marks || a.n < 2048 || noSlice) {   // timed runs and small batches: one launch sequence on the caller's stream
     CK(decode_launch(a, user, &nl, marks));
     ctx->launches += nl;
     return 0;
