@@ -15,19 +15,22 @@ using namespace zb;
 namespace {
 
 struct Sim {
-  std::vector<u32> ll, ml, of;       // lane-private tables, stride 1 here
-  u32 defLL[64], defOF[32], defML[64];
+  std::vector<u16> ll, ml, of;       // lane-private tables, stride 1 here
+  u16 defLL[64], defOF[32], defML[64];
+  u32 llInfo[36], mlInfo[53];
   Sim() : ll(512), ml(512), of(256) {
     u16 sn[53]; s16 norm[53];
-    for (int i = 0; i < 36; i++) norm[i] = kLLnorm[i]; build_seq_table(defLL, 1, norm, 35, 6, KIND_LL, sn);
-    for (int i = 0; i < 29; i++) norm[i] = kOFnorm[i]; build_seq_table(defOF, 1, norm, 28, 5, KIND_OF, sn);
-    for (int i = 0; i < 53; i++) norm[i] = kMLnorm[i]; build_seq_table(defML, 1, norm, 52, 6, KIND_ML, sn);
+    for (int i = 0; i < 36; i++) norm[i] = kLLnorm[i]; build_seq_table(defLL, 1, norm, 35, 6, sn);
+    for (int i = 0; i < 29; i++) norm[i] = kOFnorm[i]; build_seq_table(defOF, 1, norm, 28, 5, sn);
+    for (int i = 0; i < 53; i++) norm[i] = kMLnorm[i]; build_seq_table(defML, 1, norm, 52, 6, sn);
+    for (u32 i = 0; i < 36; i++) llInfo[i] = ll_info(i);
+    for (u32 i = 0; i < 53; i++) mlInfo[i] = ml_info(i);
   }
 };
 
 // mirrors k_huf for one frame; returns first failing block / code through fi
 void sim_huf(const u8* src, u32 size, FrameInfo& fi, u8* lit, u64 litCap) {
-  static thread_local u16 dt[1 << HUF_LOG_MAX]; static thread_local HufBuildWk wk; u32 ringBuf[16];
+  static thread_local u16 dt[1 << HUF_LOG_MAX]; static thread_local HufBuildWk wk; alignas(16) u32 ringBuf[ZB_RING_WORDS];
   u32 pos = fi.body_off, blk = 0; u64 litRun = 0; u32 tableLog = 0; bool haveTable = false;
   while (true) {
     BlockHdr bh;
@@ -57,10 +60,10 @@ void sim_huf(const u8* src, u32 size, FrameInfo& fi, u8* lit, u64 litCap) {
           }
         }
         if (ok) {
-          if (lh.single) ok = huf_decode_stream(body, bodySize, lit + litRun, lh.litSize, dt, tableLog, ringBuf, 1);
+          if (lh.single) ok = huf_decode_stream(body, bodySize, lit + litRun, lh.litSize, dt, tableLog, ringBuf);
           else for (u32 sub = 0; sub < 4; sub++) {
             HufStream st; bool good = huf_split4(body, bodySize, lh.litSize, sub, st);
-            if (good) good = huf_decode_stream(st.src, st.len, lit + litRun + st.outOfs, st.count, dt, tableLog, ringBuf, 1);
+            if (good) good = huf_decode_stream(st.src, st.len, lit + litRun + st.outOfs, st.count, dt, tableLog, ringBuf);
             if (!good) ok = false;
           }
         }
@@ -163,8 +166,8 @@ extern "C" uint32_t hostsim_decompress(uint8_t* dst, uint32_t cap, const uint8_t
   T.space[KIND_LL] = sim->ll.data(); T.space[KIND_ML] = sim->ml.data(); T.space[KIND_OF] = sim->of.data(); T.stride = 1;
   T.defs[KIND_LL] = sim->defLL; T.defs[KIND_OF] = sim->defOF; T.defs[KIND_ML] = sim->defML;
   SeqFrameOut res;
-  s16 normBuf[53]; u16 nextBuf[53]; u32 ringBuf[16];
-  seq_decode_frame(src, size, fi.body_off, T, recs.data(), seq_capacity(cap), res, kLLbase, kMLbase, normBuf, nextBuf, ringBuf, 1);
+  s16 normBuf[53]; u16 nextBuf[53]; alignas(16) u32 ringBuf[ZB_RING_WORDS];
+  seq_decode_frame(src, size, fi.body_off, T, recs.data(), seq_capacity(cap), res, sim->llInfo, sim->mlInfo, normBuf, nextBuf, ringBuf);
   if (res.err_block != 0xFFFFFFFFu) { fi.seq_err_block = res.err_block; fi.seq_err_code = res.err_code; fi.seq_err_index = res.err_index; }
   bool nx; u32 tr;
   static u8 dummy[8];
@@ -188,8 +191,8 @@ extern "C" uint32_t hostsim_stages(const uint8_t* src_in, uint32_t size, uint32_
   T.space[KIND_LL] = sim->ll.data(); T.space[KIND_ML] = sim->ml.data(); T.space[KIND_OF] = sim->of.data(); T.stride = 1;
   T.defs[KIND_LL] = sim->defLL; T.defs[KIND_OF] = sim->defOF; T.defs[KIND_ML] = sim->defML;
   SeqFrameOut res;
-  s16 normBuf[53]; u16 nextBuf[53]; u32 ringBuf[16];
-  seq_decode_frame(src, size, fi.body_off, T, recs.data(), seq_capacity(cap), res, kLLbase, kMLbase, normBuf, nextBuf, ringBuf, 1);
+  s16 normBuf[53]; u16 nextBuf[53]; alignas(16) u32 ringBuf[ZB_RING_WORDS];
+  seq_decode_frame(src, size, fi.body_off, T, recs.data(), seq_capacity(cap), res, sim->llInfo, sim->mlInfo, normBuf, nextBuf, ringBuf);
   memcpy(lit_out, lit.data(), cap);
   u32 n = (u32)std::min<size_t>(max_recs, recs.size());
   memcpy(rec_out, recs.data(), (size_t)n * 8);

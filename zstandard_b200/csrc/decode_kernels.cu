@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(128) k_parse(DecodeArgs a) {
 struct HufSmem {
   u16 table[8][1 << HUF_LOG_MAX];
   HufBuildWk wk[8];
-  u32 ring[16][32];      // per-lane (= per-stream) bitstream read-ahead (BitRing)
+  __align__(16) u32 ring[32][ZB_RING_WORDS + 4];   // per-lane (= per-stream) bitstream read-ahead (BitRing)
 };
 
 __global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
@@ -94,11 +94,11 @@ __global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
         if (ok) {
           bool good = true;
           if (lh.single) {
-            if (sub == 0) good = huf_decode_stream(body, bodySize, lit + litRun, lh.litSize, dt, tableLog, &sm.ring[0][lane], 32);   // HufDecompress.cs:247-264
+            if (sub == 0) good = huf_decode_stream(body, bodySize, lit + litRun, lh.litSize, dt, tableLog, &sm.ring[lane][0]);   // HufDecompress.cs:247-264
           } else {
             HufStream st;
             good = huf_split4(body, bodySize, lh.litSize, sub, st);
-            if (good) good = huf_decode_stream(st.src, st.len, lit + litRun + st.outOfs, st.count, dt, tableLog, &sm.ring[0][lane], 32);
+            if (good) good = huf_decode_stream(st.src, st.len, lit + litRun + st.outOfs, st.count, dt, tableLog, &sm.ring[lane][0]);
           }
           unsigned okmask = __ballot_sync(gmask, good);
           if ((okmask & gmask) != gmask) ok = false;
@@ -117,29 +117,30 @@ __global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
 // k_seq : one warp per CTA, one frame per lane, tables bank-interleaved across lanes
 // =================================================================================================
 struct SeqSmem {
-  u32 ll[512][32];
-  u32 ml[512][32];
-  u32 of[256][32];
-  u32 defLL[64], defOF[32], defML[64];
-  u32 llBase[36], mlBase[53];
+  u16 ll[512][32];       // lane-interleaved: cell[state][lane]
+  u16 ml[512][32];
+  u16 of[256][32];
+  u16 defLL[64], defOF[32], defML[64];
+  u32 llInfo[36], mlInfo[53];
   s16 norm[53][32];      // per-lane scratch of the table builder, lane-interleaved like the tables
   u16 next[53][32];
-  u32 ring[16][32];      // per-lane bitstream read-ahead (BitRing)
+  __align__(16) u32 ring[32][ZB_RING_WORDS + 4];   // per-lane bitstream read-ahead (BitRing), skewed by 4 banks per lane
 };
 
 __global__ void __launch_bounds__(32) k_seq(DecodeArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SeqSmem& sm = *reinterpret_cast<SeqSmem*>(smem_raw);
   const u32 lane = threadIdx.x;
-  // predefined tables + base LUTs, built once per CTA
+  // predefined tables + info LUTs, built once per CTA
   if (lane < 3) {
-    u16 symbolNext[53]; s16 norm[53];
-    if (lane == 0) { for (int i = 0; i < 36; i++) norm[i] = kLLnorm[i]; build_seq_table(sm.defLL, 1, norm, 35, 6, KIND_LL, symbolNext); }
-    if (lane == 1) { for (int i = 0; i < 29; i++) norm[i] = kOFnorm[i]; build_seq_table(sm.defOF, 1, norm, 28, 5, KIND_OF, symbolNext); }
-    if (lane == 2) { for (int i = 0; i < 53; i++) norm[i] = kMLnorm[i]; build_seq_table(sm.defML, 1, norm, 52, 6, KIND_ML, symbolNext); }
+    s16* norm = &sm.norm[0][lane]; u16* next = &sm.next[0][lane];
+    Strided<s16> nv{norm, 32}; Strided<u16> sn{next, 32};
+    if (lane == 0) { for (int i = 0; i < 36; i++) nv[i] = kLLnorm[i]; build_seq_table(sm.defLL, 1, nv, 35, 6, sn); }
+    if (lane == 1) { for (int i = 0; i < 29; i++) nv[i] = kOFnorm[i]; build_seq_table(sm.defOF, 1, nv, 28, 5, sn); }
+    if (lane == 2) { for (int i = 0; i < 53; i++) nv[i] = kMLnorm[i]; build_seq_table(sm.defML, 1, nv, 52, 6, sn); }
   }
-  for (u32 i = lane; i < 36; i += 32) sm.llBase[i] = kLLbase[i];
-  for (u32 i = lane; i < 53; i += 32) sm.mlBase[i] = kMLbase[i];
+  for (u32 i = lane; i < 36; i += 32) sm.llInfo[i] = ll_info(i);
+  for (u32 i = lane; i < 53; i += 32) sm.mlInfo[i] = ml_info(i);
   __syncwarp();
   const u32 f = blockIdx.x * 32 + lane;
   if (f >= a.n) return;
@@ -149,8 +150,8 @@ __global__ void __launch_bounds__(32) k_seq(DecodeArgs a) {
   T.space[KIND_LL] = &sm.ll[0][lane]; T.space[KIND_ML] = &sm.ml[0][lane]; T.space[KIND_OF] = &sm.of[0][lane]; T.stride = 32;
   T.defs[KIND_LL] = sm.defLL; T.defs[KIND_OF] = sm.defOF; T.defs[KIND_ML] = sm.defML;
   SeqFrameOut res;
-  seq_decode_frame(a.src_base + a.src_off[f], a.src_size[f], fi.body_off, T, seq_region(a, f), seq_capacity(a.dst_cap[f]), res, sm.llBase, sm.mlBase,
-                   Strided<s16>{&sm.norm[0][lane], 32}, Strided<u16>{&sm.next[0][lane], 32}, &sm.ring[0][lane], 32);
+  seq_decode_frame(a.src_base + a.src_off[f], a.src_size[f], fi.body_off, T, seq_region(a, f), seq_capacity(a.dst_cap[f]), res, sm.llInfo, sm.mlInfo,
+                   Strided<s16>{&sm.norm[0][lane], 32}, Strided<u16>{&sm.next[0][lane], 32}, &sm.ring[lane][0]);
   if (res.err_block != 0xFFFFFFFFu) {
     a.info[f].seq_err_block = res.err_block; a.info[f].seq_err_code = res.err_code; a.info[f].seq_err_index = res.err_index;
   }

@@ -154,64 +154,72 @@ ZB_HD u64 bc_window64(const BitCursor& c, i32 P) {
 // ---- per-thread read-ahead of a backward bitstream through shared memory ---------------------------
 // Every lane of the entropy kernels walks its own bitstream, so its loads can never coalesce with its
 // neighbours', and L1 is sectored: read straight from global memory nearly every step waits on an L2/HBM
-// sector.  BitRing keeps the 64 bytes around the cursor in a 16-word ring (ring[(word & 15) * stride], lane-
-// interleaved in shared memory => conflict-free) and fetches the next lower 16-byte chunk one refill ahead
-// into registers, so the dependent chain only ever sees shared-memory latency.
-struct U4 { u32 x, y, z, w; };
-ZB_HD U4 load_chunk16(const u8* p) {   // p is 16-byte aligned
-#if defined(__CUDA_ARCH__)
-  const uint4 v = *reinterpret_cast<const uint4*>(p);
-  return U4{v.x, v.y, v.z, v.w};
-#else
-  U4 v; memcpy(&v, p, 16); return v;
-#endif
-}
+// sector.  BitRing keeps the 256 bytes at and below the cursor in a per-lane ring of 16 chunks of 16 bytes in
+// shared memory, filled by cp.async (LDGSTS: global -> shared without a register, so no lane's refill can stall
+// another lane's use through the warp-wide register scoreboard).  A chunk is requested 13 chunks ahead of its
+// first use; one commit group per step and `wait_group 12` make it certain to have landed by then.
+#define ZB_RING_WORDS 64          // 16 chunks x 4 words, per lane, contiguous and 16-byte aligned
+#define ZB_RING_AHEAD 13
 
 struct BitRing {
-  u32* ring; u32 stride;
+  u32* ring;             // this lane's 64-word ring
   const u8* base16;      // 16-byte aligned address at or below the first stream byte
   i32 gofs;              // bit offset of stream bit 0 relative to base16 (0..120)
-  i32 lowChunk;          // ring holds chunks lowChunk .. lowChunk+3 (chunk k = bytes [16k, 16k+16) from base16)
-  U4 pend;               // chunk lowChunk-1, requested at the previous refill (zeros when below the stream)
+  i32 lowChunk;          // ring holds chunks lowChunk .. lowChunk+15 (chunk k = bytes [16k, 16k+16) from base16)
 };
 
-ZB_HD void ring_store(const BitRing& r, i32 chunk, const U4& v) {
-  const u32 w = ((u32)chunk * 4) & 15;
-  r.ring[(w + 0) * r.stride] = v.x; r.ring[(w + 1) * r.stride] = v.y;
-  r.ring[(w + 2) * r.stride] = v.z; r.ring[(w + 3) * r.stride] = v.w;
+ZB_HD void ring_request(const BitRing& r, i32 chunk) {   // asynchronous on the device
+  if (chunk < 0) return;                                 // below the stream: never read as data
+  u32* dst = r.ring + (((u32)chunk & 15) << 2);
+  const u8* src = r.base16 + (size_t)chunk * 16;
+#if defined(__CUDA_ARCH__)
+  const u32 saddr = (u32)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src) : "memory");
+#else
+  memcpy(dst, src, 16);
+#endif
 }
-ZB_HD U4 ring_fetch(const BitRing& r, i32 chunk) {
-  if (chunk < 0) return U4{0, 0, 0, 0};
-  return load_chunk16(r.base16 + (size_t)chunk * 16);
+ZB_HD void ring_commit() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
 }
-// Prepares the ring for a stream of `nbits` total bits (including the end-mark padding) starting at src.
-// Only valid when the cursor starts at P >= 128.
-ZB_HD void ring_init(BitRing& r, u32* ring, u32 stride, const u8* src, u32 nbytes) {
+ZB_HD void ring_wait_steady() {   // all but the 12 most recent groups have landed
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_group 12;" ::: "memory");
+#endif
+}
+ZB_HD void ring_wait_all() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+// Prepares the ring for the stream src[0..nbytes).  Only valid when the cursor starts at P >= 128.
+ZB_HD void ring_init(BitRing& r, u32* ring, const u8* src, u32 nbytes) {
   const uintptr_t a = (uintptr_t)src;
-  r.ring = ring; r.stride = stride;
+  r.ring = ring;
   r.base16 = (const u8*)(a & ~(uintptr_t)15);
   r.gofs = (i32)(a & 15) * 8;
   const i32 ctop = (r.gofs + (i32)nbytes * 8 - 1) >> 7;
-  r.lowChunk = ctop - 3;
-  for (i32 k = 0; k < 4; k++) ring_store(r, r.lowChunk + k, ring_fetch(r, r.lowChunk + k));
-  r.pend = ring_fetch(r, r.lowChunk - 1);
+  r.lowChunk = ctop - 15;
+  for (i32 k = 0; k < 16; k++) ring_request(r, r.lowChunk + k);
+  ring_commit();
+  ring_wait_all();
 }
-// 64 stream bits ending at P (P >= 64 and inside the ring's coverage): lo = bits [P-64, P-32), hi = [P-32, P)
+// 64 stream bits ending at P (P >= 128): lo = bits [P-64, P-32), hi = [P-32, P)
 ZB_HD void ring_window(const BitRing& r, i32 P, u32& lo, u32& hi) {
+  ring_wait_steady();
   const i32 g = r.gofs + P - 64;
   const u32 wi = (u32)(g >> 5), sh = (u32)g & 31;
-  const u32 w0 = r.ring[(wi & 15) * r.stride], w1 = r.ring[((wi + 1) & 15) * r.stride], w2 = r.ring[((wi + 2) & 15) * r.stride];
+  const u32 w0 = r.ring[wi & 63], w1 = r.ring[(wi + 1) & 63], w2 = r.ring[(wi + 2) & 63];
   lo = fshr(w0, w1, sh); hi = fshr(w1, w2, sh);   // sh == 0 ignores w2
 }
-// Call after the cursor moved to Pn (by at most 127 bits since the last call): keeps one chunk of margin below
-// the window and at most one chunk in flight.
+// Call once per step after the cursor moved to Pn (by fewer than 128 bits): keeps the ring ZB_RING_AHEAD chunks
+// ahead of the window and closes this step's commit group.
 ZB_HD void ring_advance(BitRing& r, i32 Pn) {
   const i32 wc = (r.gofs + Pn - 64) >> 7;
-  if (wc <= r.lowChunk) {
-    r.lowChunk -= 1;
-    ring_store(r, r.lowChunk, r.pend);
-    r.pend = ring_fetch(r, r.lowChunk - 1);
-  }
+  if (r.lowChunk > wc - ZB_RING_AHEAD) { r.lowChunk -= 1; ring_request(r, r.lowChunk); }
+  ring_commit();
 }
 
 }  // namespace zb

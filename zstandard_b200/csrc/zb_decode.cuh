@@ -23,10 +23,10 @@ struct SeqRec { u32 x, y; };
 ZB_HD u64 seq_capacity(u64 cap) { return 2 * (cap / 3) + 24; }
 
 struct SeqTableSet {
-  u32* space[3];            // lane-private cells for LL, OF, ML (index with *stride)
+  u16* space[3];            // lane-private cells for LL, OF, ML (index with *stride)
   u32 stride;
-  const u32* defs[3];       // predefined tables, stride 1
-  const u32* cur[3]; u32 curStride[3]; u32 log[3];
+  const u16* defs[3];       // predefined tables, stride 1
+  const u16* cur[3]; u32 curStride[3]; u32 log[3];
 };
 
 struct SeqFrameOut {
@@ -65,11 +65,11 @@ ZB_HD u32 rep_resolve(u32& rep0, u32& rep1, u32& rep2, u32 ofBits, u32 ofv, u32 
 // Walks the frame at item `src` (size bytes, first block header at body_off) and decodes every compressed
 // block's sequences.  Stops silently at structural errors that the execute stage will report itself from the
 // same headers; records entropy-level failures in `res`.
-// llBase/mlBase: base-value tables; norm/symbolNext: >= 53 entries of per-thread scratch each;
-// ringMem/ringStride: 16 words of per-thread bitstream read-ahead (BitRing).
+// llInfo/mlInfo: per-symbol base | extra bits << 24 (ll_info/ml_info); norm/symbolNext: >= 53 entries of per-thread scratch each;
+// ringMem: ZB_RING_WORDS words of per-thread bitstream read-ahead (BitRing), 16-byte aligned.
 template <class NormT, class NextT>
 ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, SeqTableSet& T, SeqRec* out, u64 cap, SeqFrameOut& res,
-                            const u32* llBase, const u32* mlBase, NormT norm, NextT symbolNext, u32* ringMem, u32 ringStride) {
+                            const u32* llInfo, const u32* mlInfo, NormT norm, NextT symbolNext, u32* ringMem) {
   res.err_block = 0xFFFFFFFFu; res.err_code = 0; res.err_index = 0;
   u32 pos = body_off, blk = 0;
   u32 rep0 = 1, rep1 = 4, rep2 = 8;                      // ZStdInternal.cs:111, ZStdDecompress.cs:2492
@@ -114,7 +114,7 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, SeqTableSet& 
         if (!bc_init(c, sp + hdr, ssz - hdr)) bad = true;                          // :1577 -> corruption_detected
         if (!bad) {
           i32 P = c.P;
-          const u32 *tLL = T.cur[KIND_LL], *tOF = T.cur[KIND_OF], *tML = T.cur[KIND_ML];
+          const u16 *tLL = T.cur[KIND_LL], *tOF = T.cur[KIND_OF], *tML = T.cur[KIND_ML];
           const u32 sLLs = T.curStride[KIND_LL], sOFs = T.curStride[KIND_OF], sMLs = T.curStride[KIND_ML];
           u32 stLL, stOF, stML;
           { u64 w = bc_window64(c, P); u32 lg = T.log[KIND_LL]; stLL = top_bits(w, lg); w <<= lg; P -= (i32)lg;
@@ -125,29 +125,30 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, SeqTableSet& 
           //      all six fields come out of 32-bit registers; leaves to the careful loop when a sequence
           //      carries >= 32 value bits (rare: very long lengths / offsets) ----
           BitRing ring;
-          if (nbSeq && P >= 128) ring_init(ring, ringMem, ringStride, sp + hdr, ssz - hdr);
+          if (nbSeq && P >= 128) ring_init(ring, ringMem, sp + hdr, ssz - hdr);
           while (i < nbSeq && P >= 128) {
             u32 lo, hi;
             ring_window(ring, P, lo, hi);                                          // 64-bit window ending at P
-            const u32 cLL = tLL[stLL * sLLs], cOF = tOF[stOF * sOFs], cML = tML[stML * sMLs];
-            const u32 sums = (cLL & 0xFFFF) + (cML & 0xFFFF) + (cOF & 0xFFFF);     // byte 0: value bits, byte 1: state bits
-            const u32 valBits = sums & 0xFF, stBits = sums >> 8;
+            const u32 yLL = tLL[stLL * sLLs], yOF = tOF[stOF * sOFs], yML = tML[stML * sMLs];
+            const u32 llSym = yLL >> 10, mlSym = yML >> 10, ofBits = yOF >> 10;   // the offset code is its own extra-bit count
+            const u32 iLL = llInfo[llSym], iML = mlInfo[mlSym];
+            const u32 llBits = iLL >> 24, mlBits = iML >> 24;
+            const u32 valBits = ofBits + mlBits + llBits;
             if (valBits >= 32) break;
-            const u32 ofBits = cOF & 0xFF, mlBits = cML & 0xFF, llBits = cLL & 0xFF;
+            const u32 lLL = yLL & 0x3FF, lOF = yOF & 0x3FF, lML = yML & 0x3FF;
+            const u32 nLL = cell_nb(lLL), nML = cell_nb(lML), nOF = cell_nb(lOF);
             const u32 ofv = shr_c(hi, 32 - ofBits);                                // read order: offset, matchLength, litLength
             const u32 mlv = shr_c(hi << ofBits, 32 - mlBits);                      // (:1504, :1534, :1542)
             const u32 llv = shr_c(hi << (ofBits + mlBits), 32 - llBits);
             const u32 h2 = fshl(lo, hi, valBits);                                  // the 32 bits after the value bits
-            const u32 nLL = (cLL >> 8) & 0xFF, nML = (cML >> 8) & 0xFF, nOF = (cOF >> 8) & 0xFF;
-            const u32 llSym = cLL >> 25, mlSym = cML >> 25;
             const u32 offset = rep_resolve(rep0, rep1, rep2, ofBits, ofv, llSym);
-            const u32 ml = mlBase[mlSym] + mlv, ll = llBase[llSym] + llv;
+            const u32 ml = (iML & 0xFFFFFF) + mlv, ll = (iLL & 0xFFFFFF) + llv;
             if ((ll | ml) <= 65535) { if (n < cap) { out[n].x = offset; out[n].y = ll | (ml << 16); } n++; }
             else seq_emit_long(out, n, cap, offset, ll, ml);
-            stLL = ((cLL >> 16) & 0x1FF) + shr_c(h2, 32 - nLL);                    // state update LL, ML, OF (:1547-1550)
-            stML = ((cML >> 16) & 0x1FF) + shr_c(h2 << nLL, 32 - nML);
-            stOF = ((cOF >> 16) & 0x1FF) + shr_c(h2 << (nLL + nML), 32 - nOF);
-            const i32 Pn = P - (i32)(valBits + stBits);
+            stLL = cell_base(lLL) + shr_c(h2, 32 - nLL);                           // state update LL, ML, OF (:1547-1550)
+            stML = cell_base(lML) + shr_c(h2 << nLL, 32 - nML);
+            stOF = cell_base(lOF) + shr_c(h2 << (nLL + nML), 32 - nOF);
+            const i32 Pn = P - (i32)(valBits + nLL + nML + nOF);
             ring_advance(ring, Pn);
             P = Pn; i++;
           }
@@ -156,10 +157,12 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, SeqTableSet& 
           for (; i < nbSeq; i++) {
             if (P < 0) { bad = true; break; }                                      // loop test :1582 (overflow)
             const u64 w0 = bc_window64(c, P);
-            const u32 cLL = tLL[stLL * sLLs], cOF = tOF[stOF * sOFs], cML = tML[stML * sMLs];
-            const u32 llBits = cLL & 0xFF, mlBits = cML & 0xFF, ofBits = cOF & 0xFF;
-            const u32 nLL = (cLL >> 8) & 0xFF, nML = (cML >> 8) & 0xFF, nOF = (cOF >> 8) & 0xFF;
-            const u32 llSym = cLL >> 25, mlSym = cML >> 25;
+            const u32 yLL = tLL[stLL * sLLs], yOF = tOF[stOF * sOFs], yML = tML[stML * sMLs];
+            const u32 llSym = yLL >> 10, mlSym = yML >> 10, ofBits = yOF >> 10;
+            const u32 iLL = llInfo[llSym], iML = mlInfo[mlSym];
+            const u32 llBits = iLL >> 24, mlBits = iML >> 24;
+            const u32 lLL = yLL & 0x3FF, lOF = yOF & 0x3FF, lML = yML & 0x3FF;
+            const u32 nLL = cell_nb(lLL), nML = cell_nb(lML), nOF = cell_nb(lOF);
             const u32 valBits = ofBits + mlBits + llBits, stBits = nLL + nML + nOF;
             u64 w = w0;
             const u32 ofv = top_bits(w, ofBits); w <<= ofBits;
@@ -169,14 +172,14 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, SeqTableSet& 
             if (Pv < 0) { bad = true; break; }     // values came from beyond the stream start (DESIGN.md "over-read")
             if (valBits + stBits > 64) w = bc_window64(c, Pv);                     // rare: more than 64 bits in one sequence
             const u32 offset = rep_resolve(rep0, rep1, rep2, ofBits, ofv, llSym);
-            const u32 ml = mlBase[mlSym] + mlv, ll = llBase[llSym] + llv;
+            const u32 ml = (iML & 0xFFFFFF) + mlv, ll = (iLL & 0xFFFFFF) + llv;
             if ((ll | ml) <= 65535) { if (n < cap) { out[n].x = offset; out[n].y = ll | (ml << 16); } n++; }
             else seq_emit_long(out, n, cap, offset, ll, ml);
             decoded++;
             // past the last sequence these bits do not exist (the stream ends after its value bits)
-            stLL = ((cLL >> 16) & 0x1FF) + top_bits(w, nLL); w <<= nLL;
-            stML = ((cML >> 16) & 0x1FF) + top_bits(w, nML); w <<= nML;
-            stOF = ((cOF >> 16) & 0x1FF) + top_bits(w, nOF);
+            stLL = cell_base(lLL) + top_bits(w, nLL); w <<= nLL;
+            stML = cell_base(lML) + top_bits(w, nML); w <<= nML;
+            stOF = cell_base(lOF) + top_bits(w, nOF);
             P = Pv - (i32)stBits;
           }
         }
@@ -217,7 +220,7 @@ ZB_HD bool huf_split4(const u8* body, u32 bodySize, u32 n, u32 lane, HufStream& 
 
 // Decodes `count` symbols of one backward stream into out[0..count).  true iff the stream was consumed
 // exactly (EndOfDStream, HufDecompress.cs:350-353 / :261) — which also implies it was never over-read.
-ZB_HD bool huf_decode_stream(const u8* src, u32 len, u8* out, u32 count, const u16* dt, u32 tableLog, u32* ringMem, u32 ringStride) {
+ZB_HD bool huf_decode_stream(const u8* src, u32 len, u8* out, u32 count, const u16* dt, u32 tableLog, u32* ringMem) {
   BitCursor c;
   if (!bc_init(c, src, len)) return false;                                         // InitDStream errors :304-307
   i32 P = c.P;
@@ -232,7 +235,7 @@ ZB_HD bool huf_decode_stream(const u8* src, u32 len, u8* out, u32 count, const u
   // fast loop: 4 symbols (<= 48 bits) per iteration out of the shared-memory ring
   if (left >= 4 && P >= 128) {
     BitRing ring;
-    ring_init(ring, ringMem, ringStride, src, len);
+    ring_init(ring, ringMem, src, len);
     const u32 sh32 = 32 - tableLog;
     while (left >= 4 && P >= 128) {
       u32 lo, hi;

@@ -201,14 +201,20 @@ ZB_HD u32 read_ncount(NormT norm, u32* maxSV, u32* tableLog, const u8* hb, u32 h
 // =====================================================================================================
 // Sequence-symbol decode tables (BuildFSETable :958-1034, rle :937-953, BuildSeqTable :1040-1079)
 // =====================================================================================================
-// Cell layout (one u32 per state; the reference's 8-byte SeqSymbol minus baseValue, which is recovered from
-// the symbol through the 36/53/32-entry base tables).  The two bit counts sit in the low bytes so that one
-// masked add over the three cells of a sequence yields both the value-bit and the state-bit totals:
-//   bits  0..7   nbAdditionalBits (0..31)
-//   bits  8..15  nbBits (state bits to read, 0..9)
-//   bits 16..24  nextState base (0..511)
-//   bits 25..30  symbol (0..52)
-ZB_HD u32 seq_cell(u32 nextState, u32 nbBits, u32 nbAdd, u32 sym) { return nbAdd | (nbBits << 8) | (nextState << 16) | (sym << 25); }
+// Cell layout: one u16 per state (the reference's 8-byte SeqSymbol squeezed so that a frame's three tables take
+// 2.5 KB of shared memory instead of 10):
+//   bits 0..9   next-state base and state-bit count, jointly: ((base >> nb) << 1 | 1) << nb — base is always a
+//               multiple of 1 << nb, so the lowest set bit marks nb and clearing it and halving gives base
+//   bits 10..15 symbol (0..52); extra-bit count and base value come from the per-kind info tables below
+ZB_HD u16 seq_cell(u32 nextState, u32 nbBits, u32 sym) { return (u16)(((((nextState >> nbBits) << 1) | 1) << nbBits) | (sym << 10)); }
+ZB_HD u32 cell_nb(u32 low10) {
+#if defined(__CUDA_ARCH__)
+  return (u32)__ffs((int)low10) - 1;
+#else
+  return (u32)__builtin_ffs((int)low10) - 1;
+#endif
+}
+ZB_HD u32 cell_base(u32 low10) { return (low10 & (low10 - 1)) >> 1; }
 
 // base / extra-bit tables: ZStdInternal.cs:158-180, ZStdDecompress.cs:1081-1107
 #if defined(__CUDACC__)
@@ -232,26 +238,30 @@ ZB_HD u32 of_base(u32 code) { return code == 0 ? 0 : (code == 1 ? 1 : (1u << cod
 enum { KIND_LL = 0, KIND_OF = 1, KIND_ML = 2 };
 ZB_HD u32 kind_nbadd(int kind, u32 sym) { return kind == KIND_LL ? kLLbits[sym] : (kind == KIND_ML ? kMLbits[sym] : sym); }
 
+// per-symbol info word of the LL / ML kinds: base value | extra-bit count << 24
+ZB_HD u32 ll_info(u32 sym) { return kLLbase[sym] | ((u32)kLLbits[sym] << 24); }
+ZB_HD u32 ml_info(u32 sym) { return kMLbase[sym] | ((u32)kMLbits[sym] << 24); }
+
 // Builds a decode table into cells[i*stride], i < (1<<tableLog).  `scratch` = 53 u16 of per-thread storage.
 // The table must not be read through `cells` by anyone else meanwhile.
 template <class NormT, class NextT>
-ZB_HD void build_seq_table(u32* cells, u32 stride, NormT norm, u32 maxSV, u32 tableLog, int kind, NextT symbolNext) {
+ZB_HD void build_seq_table(u16* cells, u32 stride, NormT norm, u32 maxSV, u32 tableLog, NextT symbolNext) {
   u32 maxSV1 = maxSV + 1, tableSize = 1u << tableLog, high = tableSize - 1;
   for (u32 s = 0; s < maxSV1; s++) {
-    if (norm[s] == -1) { cells[(high--) * stride] = s; symbolNext[s] = 1; }
+    if (norm[s] == -1) { cells[(high--) * stride] = (u16)s; symbolNext[s] = 1; }
     else symbolNext[s] = (u16)norm[s];
   }
   u32 mask = tableSize - 1, step = (tableSize >> 1) + (tableSize >> 3) + 3, pos = 0;   // Fse.cs:714-717
   for (u32 s = 0; s < maxSV1; s++)
     for (i32 i = 0; i < norm[s]; i++) {
-      cells[pos * stride] = s;
+      cells[pos * stride] = (u16)s;
       pos = (pos + step) & mask;
       while (pos > high) pos = (pos + step) & mask;
     }
   for (u32 u = 0; u < tableSize; u++) {
     u32 sym = cells[u * stride], next = symbolNext[sym]++;
     u32 nb = tableLog - highbit(next);
-    cells[u * stride] = seq_cell(((next << nb) - tableSize) & 0x1FF, nb, kind_nbadd(kind, sym), sym);
+    cells[u * stride] = seq_cell(((next << nb) - tableSize) & 0x1FF, nb, sym);
   }
 }
 
@@ -259,7 +269,7 @@ ZB_HD void build_seq_table(u32* cells, u32 stride, NormT norm, u32 maxSV, u32 ta
 // On success *log = table log now in force for this kind, *used = header bytes.  `cells/stride` is the
 // lane-private table space; predefined tables live elsewhere (the caller switches pointers when *isDefault).
 template <class NormT, class NextT>
-ZB_HD u32 read_seq_table(u32 mode, int kind, const u8* p, u32 srcSize, u32* cells, u32 stride, u32* log, bool* isDefault,
+ZB_HD u32 read_seq_table(u32 mode, int kind, const u8* p, u32 srcSize, u16* cells, u32 stride, u32* log, bool* isDefault,
                          bool haveRepeat, u32* used, NormT norm, NextT symbolNext) {
   const u32 maxSym = kind == KIND_LL ? MaxLL : (kind == KIND_ML ? MaxML : MaxOff);
   const u32 maxLog = kind == KIND_LL ? LLFSELog : (kind == KIND_ML ? MLFSELog : OffFSELog);
@@ -269,7 +279,7 @@ ZB_HD u32 read_seq_table(u32 mode, int kind, const u8* p, u32 srcSize, u32* cell
       if (srcSize == 0) return ZE_srcSize_wrong;
       u32 sym = p[0];
       if (sym > maxSym) return ZE_corruption_detected;
-      cells[0] = seq_cell(0, 0, kind_nbadd(kind, sym), sym);
+      cells[0] = seq_cell(0, 0, sym);
       *log = 0; *isDefault = false; *used = 1; return 0;
     }
     case 0: *isDefault = true; *log = kind == KIND_OF ? 5 : 6; return 0;
@@ -279,7 +289,7 @@ ZB_HD u32 read_seq_table(u32 mode, int kind, const u8* p, u32 srcSize, u32* cell
       u32 e = read_ncount(norm, &max, &tl, p, srcSize, &h);
       if (e) return ZE_corruption_detected;                                        // :1070
       if (tl > maxLog) return ZE_corruption_detected;                              // :1071
-      build_seq_table(cells, stride, norm, max, tl, kind, symbolNext);
+      build_seq_table(cells, stride, norm, max, tl, symbolNext);
       *log = tl; *isDefault = false; *used = h; return 0;
     }
   }
