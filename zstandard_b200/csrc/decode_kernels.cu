@@ -220,6 +220,36 @@ __device__ __forceinline__ u32 warp_upper_bound(u32 incl, u32 x) {
   return j & 31;
 }
 
+// Flattened copy of many short runs, one output byte per lane and row, U rows in flight per pass so that the U
+// shuffle binary searches and the U loads overlap instead of serialising on their latencies.  Run of lane j
+// covers flattened indices [incl_j - len_j, incl_j); its bytes go to g + dpos_j + k and come from
+// (src ? src + spos_j + k : g + dpos_j + k - spos_j)  — i.e. spos is a match offset when src is null.
+template <int U>
+__device__ __forceinline__ void flat_copy(u8* g, const u8* src, bool fill, u8 fillByte, u32 total, u32 incl, u32 excl, u32 dpos, u32 spos, u32 lane) {
+  for (u32 t0 = 0; t0 < total; t0 += 32 * U) {
+    u32 t[U], j[U], dj[U], ej[U], sj[U]; u8 v[U];
+#pragma unroll
+    for (int k = 0; k < U; k++) { t[k] = t0 + 32 * k + lane; j[k] = 0; }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+#pragma unroll
+      for (int k = 0; k < U; k++) { const u32 x = __shfl_sync(FULLMASK, incl, (j[k] + s - 1) & 31); if (x <= t[k]) j[k] += s; }
+    }
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      j[k] &= 31;
+      dj[k] = __shfl_sync(FULLMASK, dpos, j[k]); ej[k] = __shfl_sync(FULLMASK, excl, j[k]); sj[k] = __shfl_sync(FULLMASK, spos, j[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      v[k] = fillByte;
+      if (t[k] < total && !fill) { const u32 rel = t[k] - ej[k]; v[k] = src ? src[sj[k] + rel] : *(g + dj[k] + rel - (size_t)sj[k]); }   // a match source may lie before the group
+    }
+#pragma unroll
+    for (int k = 0; k < U; k++) if (t[k] < total) g[dj[k] + (t[k] - ej[k])] = v[k];
+  }
+}
+
 // one match copied by the whole warp; handles every offset/length relation (byte-serial semantics of :1319-1350)
 __device__ __forceinline__ void warp_match(u8* d, u32 off, u32 len, u32 lane) {
   const u8* s = d - off;
@@ -232,7 +262,7 @@ __device__ __forceinline__ void warp_match(u8* d, u32 off, u32 len, u32 lane) {
   for (u32 i = lane; i < len; i += 32) { d[i] = s[r]; r += stepm; if (r >= off) r -= off; }
 }
 
-__global__ void __launch_bounds__(EXEC_THREADS) k_exec(DecodeArgs a) {
+__global__ void __launch_bounds__(EXEC_THREADS, 8) k_exec(DecodeArgs a) {
   const u32 lane = threadIdx.x & 31;
   const u32 f = (blockIdx.x * EXEC_THREADS + threadIdx.x) >> 5;
   if (f >= a.n) return;
@@ -306,11 +336,7 @@ __global__ void __launch_bounds__(EXEC_THREADS) k_exec(DecodeArgs a) {
             const u32 sincl = warp_incl_scan(ls, lane), sexcl = sincl - ls;
             const u32 Ls = __shfl_sync(FULLMASK, sincl, 31);
             const u32 lsrc = lincl - ll;                    // literal source position of this lane, relative to litPos
-            for (u32 t0 = 0; t0 < Ls; t0 += 32) {
-              const u32 t = t0 + lane, j = warp_upper_bound(sincl, t);
-              const u32 dj = __shfl_sync(FULLMASK, excl, j), sj = __shfl_sync(FULLMASK, sexcl, j), lj = __shfl_sync(FULLMASK, lsrc, j);
-              if (t < Ls) g[dj + (t - sj)] = isRle ? (u8)rleByte : lit[litPos + lj + (t - sj)];
-            }
+            if (Ls) flat_copy<2>(g, isRle ? g : lit + litPos, isRle, (u8)rleByte, Ls, sincl, sexcl, excl, lsrc, lane);
             while (bigMask) {
               const u32 j = (u32)__ffs(bigMask) - 1; bigMask &= bigMask - 1;
               const u32 dj = __shfl_sync(FULLMASK, excl, j), nj = __shfl_sync(FULLMASK, ll, j), lj = __shfl_sync(FULLMASK, lsrc, j);
@@ -342,11 +368,7 @@ __global__ void __launch_bounds__(EXEC_THREADS) k_exec(DecodeArgs a) {
               const u32 len = plain ? ml : 0;
               const u32 pincl = warp_incl_scan(len, lane), pexcl = pincl - len;
               const u32 Tt = __shfl_sync(FULLMASK, pincl, 31);
-              for (u32 t0 = 0; t0 < Tt; t0 += 32) {
-                const u32 t = t0 + lane, j = warp_upper_bound(pincl, t);
-                const u32 mj = __shfl_sync(FULLMASK, mrel, j), oj = __shfl_sync(FULLMASK, off, j), ej = __shfl_sync(FULLMASK, pexcl, j);
-                if (t < Tt) { u8* d = g + mj + (t - ej); *d = *(d - oj); }
-              }
+              if (Tt) flat_copy<4>(g, nullptr, false, 0, Tt, pincl, pexcl, mrel, off, lane);
               unsigned big = __ballot_sync(FULLMASK, ready && !plain);
               while (big) {
                 const u32 j = (u32)__ffs(big) - 1; big &= big - 1;
