@@ -195,7 +195,7 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
       e = decode_launch(ar, st, &nl);
     } else {
       EncodeArgs ar{d.d_src, d.d_srcOff + a, d.d_srcSize + a, d.d_dst, d.d_dstOff + a, d.d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
-                    j.level, j.checksum};
+                    j.level, j.checksum, (u32)(s % NSTREAMS)};
       e = encode_launch(ar, d.enc, st, &nl);
     }
     *launches += nl;
@@ -341,7 +341,8 @@ uint32_t zstdb200_decompress(zstdb200_ctx* ctx, void* dst, uint32_t dstCapacity,
 static int decode_device_sliced(zstdb200_ctx* ctx, Device& d, const DecodeArgs& a, cudaStream_t user, cudaEvent_t* marks) {
   int nl = 0;
   static const bool noSlice = getenv("ZSTDB200_NO_SLICE") != nullptr;   // profiling aid: whole-batch kernels
-  if (marks || a.n < 2048 || noSlice) {   // timed runs and small batches: one launch sequence on the caller's stream
+  if (marks || a.n < (1u << 30) || noSlice) {   // slicing the device-resident path does not pay: whole-batch kernels fill the GPU better
+   // timed runs and small batches: one launch sequence on the caller's stream
     CK(decode_launch(a, user, &nl, marks));
     ctx->launches += nl;
     return 0;
@@ -428,7 +429,7 @@ int zstdb200_compress_batch_device(zstdb200_ctx* ctx, int device_index, int leve
   if (n > ctx->maxItems) { ctx->err = "n exceeds zstdb200_max_items"; return 1; }
   Device& d = ctx->dev[device_index];
   CK(cudaSetDevice(d.id));
-  EncodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, 0, level, checksum};
+  EncodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, 0, level, checksum, 0};
   int nl = 0;
   CK(encode_launch(a, d.enc, stream ? (cudaStream_t)stream : d.stream[0], &nl));
   ctx->launches += nl;

@@ -7,23 +7,29 @@ namespace zb {
 
 // All pointers are device pointers.  Item i: src_base[src_off[i] .. +src_size[i]) -> one zstd frame written at
 // dst_base[dst_off[i] ..] (at most dst_cap[i] bytes); result[i] = frame size or an error code.
+// src_off must be non-decreasing with src_off[i] + src_size[i] <= src_off[i+1] (the match stage's scratch is
+// addressed from it) and the source buffer must be readable up to 8 bytes past its last item.
 struct EncodeArgs {
   const u8* src_base; const u64* src_off; const u32* src_size;
   u8* dst_base; const u64* dst_off; const u32* dst_cap;
   u32* result; u32 n;
-  u32 item_base;   // unused by the encoder's slot-based scratch; kept symmetric with DecodeArgs
+  u32 item_base;     // index of item 0 within the scratch numbering (slices of one batch share the arenas)
   int level, checksum;
+  u32 stream_slot;   // which quarter of the entropy stage's slot arena to use (launches on different streams run concurrently)
 };
 
-// Per-device scratch owned by the context: `slots` independent work areas; a GPU thread owns one slot and
-// encodes frames slot, slot + slots, ... with it.
+// Per-device scratch owned by the context (allocated on the first compress call).
 struct EncodeScratch {
-  u8* arena = nullptr;
-  size_t slotBytes = 0; u32 slots = 0;
+  u8* lit = nullptr;       // literals of every block, addressed from src_off
+  u32* seq = nullptr;      // sequence stores (2 words per sequence)
+  void* meta = nullptr;    // per block: sequence and literal counts
+  u8* slots = nullptr;     // entropy-stage work areas (code arrays, FSE state tables), one per resident thread
+  size_t maxBytes = 0, maxItems = 0;
+  int sms = 148;
 };
 
 size_t encode_bound(size_t srcSize);
-cudaError_t encode_alloc(EncodeScratch& s, size_t maxBatchBytes, size_t maxItems);   // lazy: allocates on first launch
+cudaError_t encode_alloc(EncodeScratch& s, size_t maxBatchBytes, size_t maxItems);   // records sizes; memory comes lazily
 void encode_free(EncodeScratch& s);
 cudaError_t encode_launch(const EncodeArgs& a, EncodeScratch& s, cudaStream_t st, int* launches);
 

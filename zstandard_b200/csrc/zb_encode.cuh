@@ -688,7 +688,14 @@ ZB_HD u32 enc_sequences(u8* out, u32 cap, const SeqStore& st, u8* codes, u16* ct
 // ------------------------------------------------------------------------------------------------
 // Writes a complete frame for src[0..size) at dst (capacity cap).  Returns the frame size without the
 // 4-byte content checksum slot (the checksum kernel fills it), or an error code.
-ZB_HD u32 encode_frame(const u8* src, u32 size, u8* dst, u32 cap, int level, int checksum, const EncScratch& sc) {
+//
+// `blockSeqs(st, blockIndex, bstart, bsize)` supplies the block's sequence store: either by running a match
+// finder right here (SerialMatcher: the thread-per-frame replay used by tests/hostsim) or by pointing at what
+// the warp-parallel match kernel left in HBM (StoredMatcher, encode_kernels.cu).
+// Block bodies are written straight into dst and replaced by a raw copy when they do not pay.
+template <class BlockSeqs>
+ZB_HD u32 encode_frame_with(const u8* src, u32 size, u8* dst, u32 cap, int level, int checksum, u8* codes, u16* ctables, u8* symScratch,
+                            BlockSeqs& blockSeqs) {
   u32 op = 0;
   const u32 fcsCode = size < 256 ? 0 : (size < 65536 + 256 ? 1 : 2);
   const u32 fhs = 4 + 1 + (fcsCode == 0 ? 1 : (fcsCode == 1 ? 2 : 4));
@@ -700,44 +707,37 @@ ZB_HD u32 encode_frame(const u8* src, u32 size, u8* dst, u32 cap, int level, int
   else { dst[5] = (u8)size; dst[6] = (u8)(size >> 8); dst[7] = (u8)(size >> 16); dst[8] = (u8)(size >> 24); }
   op = fhs;
   const u32 tail = checksum ? 4 : 0;
-  const EncParams pr = enc_params(level, size);
-  const u32 tw = (1u << pr.hashLog) + (pr.dfast ? (1u << pr.chainLog) : 0);
-  for (u32 i = 0; i < tw; i++) sc.table[i] = 0;
-  u32 rep[2] = {1, 4};
-  u32 pos = 0;
+  u32 pos = 0, blk = 0;
   do {
     const u32 bsize = size - pos < BLOCKSIZE_MAX ? size - pos : BLOCKSIZE_MAX;
     const u32 last = pos + bsize == size;
     const u8* bstart = src + pos;
     if (op + 3 + tail > cap) return zerr(ZE_dstSize_tooSmall);
-    // RLE block?
     bool rle = bsize > 0;
     for (u32 i = 1; i < bsize && rle; i++) if (bstart[i] != bstart[0]) rle = false;
-    u32 csize = 0; bool compressed = false;
+    SeqStore st; st.n = 0; st.nlits = 0; st.seqs = nullptr; st.lits = nullptr; st.cap = 0;
+    const bool haveSeqs = blockSeqs(st, blk, bstart, bsize, rle && bsize >= 2);   // always called: keeps matcher state in step
     if (rle && bsize >= 2) {
       if (op + 4 + tail > cap) return zerr(ZE_dstSize_tooSmall);
       const u32 h = last | (1u << 1) | (bsize << 3);
       dst[op] = (u8)h; dst[op + 1] = (u8)(h >> 8); dst[op + 2] = (u8)(h >> 16); dst[op + 3] = bstart[0]; op += 4;
     } else {
-      if (bsize >= 64) {
-        SeqStore st; st.seqs = sc.seqs; st.n = 0; st.cap = sc.seqCap; st.lits = sc.lits; st.nlits = 0;
-        u32 savedRep[2] = {rep[0], rep[1]};
-        if (pr.dfast) match_dfast(st, sc.table, pr.hashLog, sc.table + (1u << pr.hashLog), pr.chainLog, pr.minMatch, src, bstart, bstart + bsize, rep);
-        else match_fast(st, sc.table, pr.hashLog, pr.minMatch, src, bstart, bstart + bsize, rep);
-        const u32 room = bsize - 1 < BLOCKSIZE_MAX - 1 ? bsize - 1 : BLOCKSIZE_MAX - 1;   // a compressed block must beat raw and stay < 128 KiB (:1880)
-        u32 l = enc_literals(sc.tmp, room, st.lits, st.nlits, sc.ctables, sc.tmp + BLOCKSIZE_MAX + 16);
+      u32 csize = 0; bool compressed = false;
+      if (haveSeqs) {
+        u32 room = bsize - 1 < BLOCKSIZE_MAX - 1 ? bsize - 1 : BLOCKSIZE_MAX - 1;   // must beat raw and stay < 128 KiB (:1880)
+        const u32 avail = cap - op - 3 - tail;
+        if (room > avail) room = avail;
+        u8* body = dst + op + 3;
+        const u32 l = enc_literals(body, room, st.lits, st.nlits, ctables, symScratch);
         if (l) {
-          u32 s = enc_sequences(sc.tmp + l, room - l, st, sc.codes, sc.ctables, sc.tmp + BLOCKSIZE_MAX + 16, level);
+          const u32 s = enc_sequences(body + l, room - l, st, codes, ctables, symScratch, level);
           if (s && l + s < bsize) { csize = l + s; compressed = true; }
         }
-        if (!compressed) { rep[0] = savedRep[0]; rep[1] = savedRep[1]; }
+        blockSeqs.done(compressed);
       }
       if (compressed) {
-        if (op + 3 + csize + tail > cap) return zerr(ZE_dstSize_tooSmall);
         const u32 h = last | (2u << 1) | (csize << 3);
-        dst[op] = (u8)h; dst[op + 1] = (u8)(h >> 8); dst[op + 2] = (u8)(h >> 16); op += 3;
-        for (u32 i = 0; i < csize; i++) dst[op + i] = sc.tmp[i];
-        op += csize;
+        dst[op] = (u8)h; dst[op + 1] = (u8)(h >> 8); dst[op + 2] = (u8)(h >> 16); op += 3 + csize;
       } else {
         if (op + 3 + bsize + tail > cap) return zerr(ZE_dstSize_tooSmall);
         const u32 h = last | (0u << 1) | (bsize << 3);
@@ -746,9 +746,33 @@ ZB_HD u32 encode_frame(const u8* src, u32 size, u8* dst, u32 cap, int level, int
         op += bsize;
       }
     }
-    pos += bsize;
+    pos += bsize; blk++;
   } while (pos < size);
   return op;
+}
+
+// match finding inside the encoding thread (thread-per-frame replay)
+struct SerialMatcher {
+  const EncScratch& sc; EncParams pr; const u8* base; u32 rep[2], savedRep[2];
+  ZB_HD SerialMatcher(const EncScratch& s, int level, const u8* src, u32 size) : sc(s), pr(enc_params(level, size)), base(src) {
+    const u32 tw = (1u << pr.hashLog) + (pr.dfast ? (1u << pr.chainLog) : 0);
+    for (u32 i = 0; i < tw; i++) sc.table[i] = 0;
+    rep[0] = 1; rep[1] = 4; savedRep[0] = 1; savedRep[1] = 4;
+  }
+  ZB_HD bool operator()(SeqStore& st, u32, const u8* bstart, u32 bsize, bool isRle) {
+    if (isRle || bsize < 64) return false;
+    st.seqs = sc.seqs; st.n = 0; st.cap = sc.seqCap; st.lits = sc.lits; st.nlits = 0;
+    savedRep[0] = rep[0]; savedRep[1] = rep[1];
+    if (pr.dfast) match_dfast(st, sc.table, pr.hashLog, sc.table + (1u << pr.hashLog), pr.chainLog, pr.minMatch, base, bstart, bstart + bsize, rep);
+    else match_fast(st, sc.table, pr.hashLog, pr.minMatch, base, bstart, bstart + bsize, rep);
+    return true;
+  }
+  ZB_HD void done(bool compressed) { if (!compressed) { rep[0] = savedRep[0]; rep[1] = savedRep[1]; } }   // a raw block leaves the decoder's history alone
+};
+
+ZB_HD u32 encode_frame(const u8* src, u32 size, u8* dst, u32 cap, int level, int checksum, const EncScratch& sc) {
+  SerialMatcher m(sc, level, src, size);
+  return encode_frame_with(src, size, dst, cap, level, checksum, sc.codes, sc.ctables, sc.tmp, m);
 }
 
 }  // namespace zb
