@@ -6,6 +6,7 @@
 // warp-cooperative k_exec) so that tests/test_hostsim.py can compare them with the oracle before any GPU time
 // is spent.  It is never linked into libzstdb200.so.
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 #include "../../zstandard_b200/csrc/zb_decode.cuh"
 #include "../../zstandard_b200/csrc/zb_encode.cuh"
@@ -211,4 +212,96 @@ extern "C" uint32_t hostsim_compress(uint8_t* dst, uint32_t cap, const uint8_t* 
   EncScratch sc; sc.table = table.data(); sc.lits = lits.data(); sc.seqs = seqs.data(); sc.seqCap = seqCap; sc.codes = codes.data();
   sc.ctables = ct.data(); sc.tmp = tmp.data();
   return encode_frame(src, size, dst, cap, level, checksum, sc);
+}
+
+// ---- lock-step CPU emulation of the warp-parallel match finder (k_enc_match in encode_kernels.cu) ----
+// Same algorithm, lanes emulated by loops; used to study ratio without a GPU and as a second replay in tests.
+namespace {
+struct WarpMatcher {
+  std::vector<u16> tab; u32 hlogL, hlogS, mls; bool dfast;
+  const u8* src; u32 size; u32 rep1 = 1, rep2 = 4;
+  std::vector<u32> seqs; std::vector<u8> lits;
+  static u32 h64(u64 v, u32 hlog, u32 mls) {
+    if (mls >= 8) return (u32)((v * 0xCF1BBCDCB7A56463ull) >> (64 - hlog));
+    if (mls == 6) return (u32)(((v << 16) * 0xCF1BBCDCBF9Bull) >> (64 - hlog));
+    return (u32)(((v << 24) * 0xCF1BBCDCBBull) >> (64 - hlog));
+  }
+  static bool candFrom(u32 p, u32 e, u32& c) { u32 d = (p - e) & 0xFFFF; if (!d) d = 0x10000; c = p - d; return d <= p; }
+  u32 extend(u32 a, u32 off, u32 end) { u32 n = 0; while (a + n < end && src[a + n] == src[a + n - off]) n++; return n; }
+  bool operator()(SeqStore& st, u32 blk, const u8* bstart, u32 bsize, bool isRle) {
+    if (isRle || bsize < 64) return false;
+    seqs.assign(2 * (BLOCKSIZE_MAX / 4 + 64), 0); lits.assign(BLOCKSIZE_MAX + 64, 0);
+    u32 nseq = 0, nlits = 0;
+    const u32 bpos = (u32)(bstart - src), bend = bpos + bsize;
+    if (blk > 0) { rep1 = 0; rep2 = 0; }
+    u16* tabL = tab.data(); u16* tabS = tab.data() + (1u << hlogL);
+    u32 anchor = bpos; const u32 ilimit = bend - 8; u32 p0 = bpos + (bpos == 0 ? 1 : 0);
+    while (p0 < ilimit) {
+      const u32 step = 1 + ((p0 - anchor) >> 8);
+      u32 p[32], hL[32], hS[32], candL[32], candS[32]; bool act[32], vL[32], vS[32], okL[32], okS[32], rok[32]; u64 v[32];
+      for (u32 l = 0; l < 32; l++) {
+        p[l] = p0 + l * step; act[l] = p[l] < ilimit; v[l] = act[l] ? ld64(src + p[l]) : 0;
+        hL[l] = act[l] ? h64(v[l], hlogL, dfast ? 8 : mls) : (0x80000000u | l);
+        hS[l] = act[l] ? h64(v[l], hlogS, mls) : (0x80000000u | l);
+      }
+      for (u32 l = 0; l < 32; l++) {
+        i32 low = -1; for (i32 k = (i32)l - 1; k >= 0; k--) if (hL[k] == hL[l]) { low = k; break; }
+        if (low >= 0) { candL[l] = p[low]; vL[l] = act[l]; } else vL[l] = act[l] && candFrom(p[l], tabL[hL[l] & 0xFFFFFF], candL[l]);
+        vS[l] = false;
+        if (dfast) { low = -1; for (i32 k = (i32)l - 1; k >= 0; k--) if (hS[k] == hS[l]) { low = k; break; }
+          if (low >= 0) { candS[l] = p[low]; vS[l] = act[l]; } else vS[l] = act[l] && candFrom(p[l], tabS[hS[l] & 0xFFFFFF], candS[l]); }
+      }
+      i32 fl = -1;
+      for (u32 l = 0; l < 32; l++) {
+        okL[l] = vL[l] && (dfast ? ld64(src + candL[l]) == v[l] : ld32(src + candL[l]) == (u32)v[l]);
+        okS[l] = dfast && vS[l] && ld32(src + candS[l]) == (u32)v[l];
+        rok[l] = act[l] && rep1 != 0 && rep1 <= p[l] && ld32(src + p[l] - rep1) == (u32)v[l];
+        if (fl < 0 && (okL[l] || okS[l] || rok[l])) fl = (i32)l;
+      }
+      // a repeat-offset match a few bytes further on beats a table match here (cheaper to code)
+      if (fl >= 0 && !rok[fl]) { const int look = 3; for (i32 l = fl + 1; l <= fl + look && l < 32; l++) if (rok[l]) { fl = l; break; } }
+      auto insert = [&](u32 limit) {   // ascending lanes: last writer wins; nothing at or beyond the restart position
+        for (u32 l = 0; l < 32; l++) if (act[l] && p[l] < limit) { tabL[hL[l]] = (u16)p[l]; if (dfast) tabS[hS[l]] = (u16)p[l]; } };
+      if (fl < 0) { insert(0xFFFFFFFFu); p0 += 32 * step; continue; }
+      u32 pos = p[fl]; const u32 kind = rok[fl] ? 0 : (okL[fl] ? 1 : 2);
+      u32 cnd = kind == 0 ? pos - rep1 : (kind == 1 ? candL[fl] : candS[fl]);
+      const u32 off = pos - cnd;
+      u32 mlen = 4 + extend(pos + 4, off, bend);
+      while (pos > anchor && cnd > 0 && src[pos - 1] == src[cnd - 1]) { pos--; cnd--; mlen++; }
+      insert(pos + mlen);
+      const u32 ll = pos - anchor; u32 offBase;
+      if (kind == 0 && ll > 0) offBase = 1; else { offBase = off + 3; rep2 = rep1; rep1 = off; }
+      memcpy(lits.data() + nlits, src + anchor, ll);
+      seqs[2 * nseq] = (ll & 0xFFFF) | (((mlen - 3) & 0xFFFF) << 16);
+      seqs[2 * nseq + 1] = (offBase & 0x3FFFFFFFu) | ((((mlen - 3) >> 16) & 1) << 30) | (((ll >> 16) & 1) << 31);
+      nlits += ll; nseq++;
+      anchor = pos + mlen; p0 = anchor;
+      if (p0 <= ilimit) {
+        const u32 q = p0 - 2; tabL[h64(ld64(src + q), hlogL, dfast ? 8 : mls)] = (u16)q; if (dfast) tabS[h64(ld64(src + q), hlogS, mls)] = (u16)q;
+        while (rep2 != 0 && p0 <= ilimit && ld32(src + p0) == ld32(src + p0 - rep2)) {
+          const u32 rlen = 4 + extend(p0 + 4, rep2, bend);
+          std::swap(rep1, rep2);
+          tabL[h64(ld64(src + p0), hlogL, dfast ? 8 : mls)] = (u16)p0; if (dfast) tabS[h64(ld64(src + p0), hlogS, mls)] = (u16)p0;
+          seqs[2 * nseq] = ((rlen - 3) & 0xFFFF) << 16; seqs[2 * nseq + 1] = 1u | ((((rlen - 3) >> 16) & 1) << 30);
+          nseq++; p0 += rlen; anchor = p0;
+        }
+      }
+    }
+    const u32 ll = bend - anchor; memcpy(lits.data() + nlits, src + anchor, ll); nlits += ll;
+    st.seqs = seqs.data(); st.n = nseq; st.cap = BLOCKSIZE_MAX / 4 + 64; st.lits = lits.data(); st.nlits = nlits;
+    return true;
+  }
+  void done(bool) {}
+};
+}  // namespace
+
+extern "C" uint32_t hostsim_compress_warp(uint8_t* dst, uint32_t cap, const uint8_t* src_in, uint32_t size, int level, int checksum) {
+  std::vector<u8> padded(size + 64, 0);
+  u8* src = padded.data() + 16;
+  if (size) memcpy(src, src_in, size);
+  WarpMatcher m; m.src = src; m.size = size; m.dfast = level >= 3; m.hlogL = level <= 1 ? 13 : 15; m.hlogS = 14; m.mls = level <= 1 ? 6 : 5;
+  m.tab.assign((1u << m.hlogL) + (1u << m.hlogS), 0);
+  const u32 seqCap = BLOCKSIZE_MAX / 4 + 64;
+  std::vector<u8> codes(3 * seqCap), sym(4096); std::vector<u16> ct(3 * 514 + 16);
+  return encode_frame_with(src, size, dst, cap, level, checksum, codes.data(), ct.data(), sym.data(), m);
 }

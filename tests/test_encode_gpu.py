@@ -36,6 +36,23 @@ def test_frames_round_trip_through_reference_rules(gpu_ctx, oracle):
                 assert zstd_ref.decompress(f, len(p)) == p
 
 
+def test_gpu_matches_lockstep_cpu_emulation(gpu_ctx, hostsim):
+    """tests/hostsim emulates the warp-parallel match finder lane by lane: the GPU must produce the same bytes."""
+    import ctypes
+    lib = hostsim.lib
+    lib.hostsim_compress_warp.restype = ctypes.c_uint32
+    lib.hostsim_compress_warp.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int]
+    rng = random.Random(8)
+    payloads = [helpers.sample_payload(rng, t % 6, rng.choice(SIZES)) for t in range(48)]
+    for level in (1, 2, 3):
+        res, dsts = _compress(gpu_ctx, payloads, level, False)
+        for p, r, d in zip(payloads, res, dsts):
+            cap = len(p) + len(p) // 128 + 128
+            buf = ctypes.create_string_buffer(cap)
+            n = lib.hostsim_compress_warp(buf, cap, p, len(p), level, 0)
+            assert int(r) == n and d[:n].tobytes() == buf.raw[:n], (len(p), level, int(r), n)
+
+
 def test_gpu_frames_decode_on_gpu(gpu_ctx):
     rng = random.Random(7)
     payloads = [helpers.sample_payload(rng, t % 6, rng.choice(SIZES)) for t in range(60)]

@@ -57,6 +57,35 @@ def test_ratio_band_against_libzstd(enc):
                 assert ours <= ref * 1.03, (kind, chunk, level, ours, ref)
 
 
+def test_warp_matcher_emulation_round_trips_and_ratio(hostsim, oracle):
+    """The lock-step CPU emulation of the GPU's warp-parallel match finder (k_enc_match): valid frames, ratio band."""
+    lib = hostsim.lib
+    lib.hostsim_compress_warp.restype = ctypes.c_uint32
+    lib.hostsim_compress_warp.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int]
+
+    def comp(data, level):
+        cap = len(data) + len(data) // 128 + 128
+        buf = ctypes.create_string_buffer(max(cap, 1))
+        r = lib.hostsim_compress_warp(buf, cap, bytes(data), len(data), level, 0)
+        assert not helpers.is_err(r)
+        return buf.raw[:r]
+    rng = random.Random(9)
+    for t in range(90):
+        n = rng.choice(SIZES)
+        data = helpers.sample_payload(rng, t % 6, n)
+        for level in (1, 2, 3):
+            f = comp(data, level)
+            ro, oo, _ = oracle.decompress(f, n)
+            assert ro == n and oo == data, (t, n, level, hex(ro))
+    for kind in ("log", "tick"):
+        raw = corpus.make(kind, 1 << 20).tobytes()
+        for chunk in (65536, 131072):
+            for level in (1, 2, 3):
+                ours = sum(len(comp(raw[i:i + chunk], level)) for i in range(0, len(raw), chunk))
+                ref = sum(len(zstd_ref.compress(raw[i:i + chunk], level, checksum=False)) for i in range(0, len(raw), chunk))
+                assert ours <= ref * 1.03, (kind, chunk, level, ours, ref)
+
+
 def test_incompressible_and_constant_inputs(enc, oracle):
     rnd = corpus.random_(200000).tobytes()
     for level in (1, 2, 3):

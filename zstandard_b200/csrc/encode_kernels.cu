@@ -15,6 +15,8 @@
 #include "encode_kernels.cuh"
 #include "zb_encode.cuh"
 #include "xxh_device.cuh"
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace zb {
 
@@ -117,16 +119,21 @@ __global__ void __launch_bounds__(32) k_enc_match(EncodeArgs a, EncodeScratch sc
             const unsigned lowS = mS & ((1u << lane) - 1);
             if (lowS) { candS = p0 + (31 - __clz(lowS)) * step; validS = act; } else validS = cand_from_entry(p, eS, candS) && act;
           }
-          __syncwarp();
-          if (act && (mL >> lane) == 1) tabL[hL] = (u16)p;            // the last position of each hash group is the one kept
-          if (DFAST && act && (mS >> lane) == 1) tabS[hS] = (u16)p;
           bool okL = false, okS = false;
           if (validL) okL = DFAST ? (ldu64(src + candL) == v) : (ldu32(src + candL) == (u32)v);
           if (DFAST && validS) okS = ldu32(src + candS) == (u32)v;
           const bool rok = act && rep1 != 0 && rep1 <= p && ldu32(src + p - rep1) == (u32)v;
-          const unsigned found = __ballot_sync(FULLMASK, okL | okS | rok);
-          if (!found) { p0 += 32 * step; continue; }
-          const u32 fl = (u32)__ffs(found) - 1;
+          const unsigned fRep = __ballot_sync(FULLMASK, rok);
+          const unsigned found = __ballot_sync(FULLMASK, okL | okS) | fRep;
+          if (!found) {                                                // no match in the window: enter every position, move on
+            if (act && (mL >> lane) == 1) tabL[hL] = (u16)p;          // the last position of each hash group is the one kept
+            if (DFAST && act && (mS >> lane) == 1) tabS[hS] = (u16)p;
+            __syncwarp();
+            p0 += 32 * step; continue;
+          }
+          u32 fl = (u32)__ffs(found) - 1;
+          // a repeat-offset match up to 3 positions further on beats a table match here (it is cheaper to code)
+          if (!((fRep >> fl) & 1)) { const unsigned nearRep = fRep & (0xEu << fl); if (nearRep) fl = (u32)__ffs(nearRep) - 1; }
           u32 pos = p0 + fl * step;
           const u32 kind = rok ? 0 : (okL ? 1 : 2);                   // at the winning lane: repeat offset > long/main table > short table
           const u32 kf = __shfl_sync(FULLMASK, kind, fl);
@@ -135,6 +142,15 @@ __global__ void __launch_bounds__(32) k_enc_match(EncodeArgs a, EncodeScratch sc
           const u32 off = pos - cnd;
           u32 mlen = 4 + warp_extend(src, pos + 4, off, bend, lane);
           while (pos > anchor && cnd > 0 && src[pos - 1] == src[cnd - 1]) { pos--; cnd--; mlen++; }   // catch up
+ {
+            // enter the window's positions up to the end of the match: nothing at or beyond the restart position may
+            // go in, or it would later be found as its own candidate
+            const bool ins = act && p < pos + mlen;
+            const unsigned insMask = __ballot_sync(FULLMASK, ins);
+            if (ins && ((mL & insMask) >> lane) == 1) tabL[hL] = (u16)p;
+            if (DFAST && ins && ((mS & insMask) >> lane) == 1) tabS[hS] = (u16)p;
+            __syncwarp();
+          }
           const u32 ll = pos - anchor;
           u32 offBase;
           if (kf == 0 && ll > 0) offBase = 1;                          // repeat offset 1; history unchanged
@@ -261,11 +277,21 @@ cudaError_t encode_launch(const EncodeArgs& a, EncodeScratch& s, cudaStream_t st
   const size_t smem = ((size_t)(1u << hlogL) + (dfast ? (1u << hlogS) : 0)) * 2;
   u32 perSm = (u32)((220 * 1024) / smem); if (perSm > 16) perSm = 16;
   u32 grid = (u32)s.sms * perSm; if (grid > a.n) grid = a.n;
+  static const bool timing = getenv("ZSTDB200_ENC_TIMING") != nullptr;   // debug aid: per-kernel times on stderr
+  cudaEvent_t ev[3];
+  if (timing) { for (auto& x : ev) cudaEventCreate(&x); cudaEventRecord(ev[0], st); }
   if (dfast) k_enc_match<true><<<grid, 32, smem, st>>>(a, s, hlogL, hlogS, mls);
   else k_enc_match<false><<<grid, 32, smem, st>>>(a, s, hlogL, hlogS, mls);
   const u32 part = a.stream_slot % kStreamSlots;
   const u32 slots = a.n < kSlotsPerStream ? a.n : kSlotsPerStream;
+  if (timing) cudaEventRecord(ev[1], st);
   k_enc_entropy<<<(slots + 63) / 64, 64, 0, st>>>(a, s, part * kSlotsPerStream, slots);
+  if (timing) {
+    cudaEventRecord(ev[2], st); cudaEventSynchronize(ev[2]);
+    float m1 = 0, m2 = 0; cudaEventElapsedTime(&m1, ev[0], ev[1]); cudaEventElapsedTime(&m2, ev[1], ev[2]);
+    fprintf(stderr, "[zstdb200] encode level %d n %u: k_enc_match %.3f ms (grid %u, smem %zu), k_enc_entropy %.3f ms (slots %u)\n", a.level, a.n, m1, grid, smem, m2, slots);
+    for (auto& x : ev) cudaEventDestroy(x);
+  }
   if (launches) *launches += 2;
   if (a.checksum) { k_enc_xxh<<<(a.n * 4 + 127) / 128, 128, 0, st>>>(a); if (launches) *launches += 1; }
   return cudaGetLastError();
