@@ -206,19 +206,233 @@ struct StoredMatcher {
 };
 
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
-__host__ __device__ inline size_t slot_bytes() { return align16((size_t)kBlockSeqCap * 3) + align16(3 * 514 * 2 + 32) + 1024; }
+static constexpr u32 kStreamTmp = 48 * 1024;   // worst case of one Huffman stream: 32 Ki symbols x 11 bits
+__host__ __device__ inline size_t slot_bytes() { return align16((size_t)kBlockSeqCap * 3) + 4 * (size_t)kStreamTmp; }
 
-__global__ void __launch_bounds__(64) k_enc_entropy(EncodeArgs a, EncodeScratch sc, u32 slot0, u32 slots) {
-  const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= slots) return;
-  u8* p = sc.slots + (size_t)(slot0 + t) * slot_bytes();
-  u8* codes = p; p += align16((size_t)kBlockSeqCap * 3);
-  u16* ctables = (u16*)p; p += align16(3 * 514 * 2 + 32);
-  u8* sym = p;
-  for (u32 f = t; f < a.n; f += slots) {
-    StoredMatcher m{lit_base(a, sc, f), seq_base(a, sc, f), meta_base(a, sc, f)};
-    a.result[f] = encode_frame_with(a.src_base + a.src_off[f], a.src_size[f], a.dst_base + a.dst_off[f], a.dst_cap[f], a.level, a.checksum,
-                                    codes, ctables, sym, m);
+// ---- entropy stage, one warp per frame -------------------------------------------------------------
+// Same decisions and same bytes as enc_literals / enc_sequences / encode_frame_with in zb_encode.cuh (the
+// serial replay), with the data-parallel parts spread over the lanes: histograms (shared-memory atomics),
+// the four Huffman streams (one lane each, into scratch, then concatenated), code computation, block copies.
+// Table construction (Huffman tree, FSE normalisation) and the FSE bitstream stay on lane 0.
+struct EntWarp {
+  u32 hist[256];
+  HufEnc he;
+  u32 cnt[3][64];
+  u16 state[3][514 + 2];
+  FseCTable ct[3];
+  u8 sym[512 + 16];
+};
+
+__device__ __forceinline__ void wcopy(u8* dst, const u8* src, u32 n, u32 lane) {
+  if (n >= 64 && ((((uintptr_t)dst) ^ ((uintptr_t)src)) & 15) == 0) {
+    const u32 head = (u32)(-(intptr_t)dst) & 15;
+    if (lane < head) dst[lane] = src[lane];
+    const u32 body = (n - head) & ~15u;
+    const uint4* s4 = (const uint4*)(src + head); uint4* d4 = (uint4*)(dst + head);
+    for (u32 i = lane; i < body / 16; i += 32) d4[i] = s4[i];
+    for (u32 i = head + body + lane; i < n; i += 32) dst[i] = src[i];
+    return;
+  }
+  for (u32 i = lane; i < n; i += 32) dst[i] = src[i];
+}
+__device__ __forceinline__ u32 wmax(u32 v) {
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) { const u32 t = __shfl_xor_sync(FULLMASK, v, d); v = t > v ? t : v; }
+  return v;
+}
+
+// literals section; returns bytes written, 0 = no room (mirror of enc_literals)
+__device__ u32 warp_enc_literals(u8* out, u32 cap, const u8* lits, u32 n, EntWarp& w, u8* tmp, u32 lane) {
+  const u32 rawLh = n < 32 ? 1 : (n < 4096 ? 2 : 3);
+  auto raw = [&]() -> u32 {
+    if (rawLh + n > cap) return 0;
+    if (lane == 0) {
+      if (rawLh == 1) out[0] = (u8)(n << 3); else if (rawLh == 2) { const u32 v = (1u << 2) | (n << 4); out[0] = (u8)v; out[1] = (u8)(v >> 8); }
+      else { const u32 v = (3u << 2) | (n << 4); out[0] = (u8)v; out[1] = (u8)(v >> 8); out[2] = (u8)(v >> 16); }
+    }
+    wcopy(out + rawLh, lits, n, lane);
+    __syncwarp();
+    return rawLh + n;
+  };
+  if (n < 64) return raw();
+  for (u32 i = lane; i < 256; i += 32) w.hist[i] = 0;
+  __syncwarp();
+  for (u32 i = lane; i < n; i += 32) atomicAdd(&w.hist[lits[i]], 1u);
+  __syncwarp();
+  u32 myMaxSym = 0, myLargest = 0;
+  for (u32 sI = lane; sI < 256; sI += 32) { const u32 c = w.hist[sI]; if (c) myMaxSym = sI; if (c > myLargest) myLargest = c; }
+  const u32 maxSym = wmax(myMaxSym), largest = wmax(myLargest);
+  if (largest == n) {
+    if (rawLh + 1 > cap) return 0;
+    if (lane == 0) {
+      if (rawLh == 1) out[0] = (u8)(1 | (n << 3)); else if (rawLh == 2) { const u32 v = 1 | (1u << 2) | (n << 4); out[0] = (u8)v; out[1] = (u8)(v >> 8); }
+      else { const u32 v = 1 | (3u << 2) | (n << 4); out[0] = (u8)v; out[1] = (u8)(v >> 8); out[2] = (u8)(v >> 16); }
+      out[rawLh] = lits[0];
+    }
+    __syncwarp();
+    return rawLh + 1;
+  }
+  if (largest <= (n >> 7) + 4) return raw();
+  u32 maxBits = fse_optimal_log(11, n, maxSym, 1); if (maxBits > 11) maxBits = 11;
+  u32 ok = 0;
+  if (lane == 0) ok = huf_build(w.he, w.hist, maxSym, maxBits) ? 1 : 0;
+  ok = __shfl_sync(FULLMASK, ok, 0);
+  if (!ok) return raw();
+  const bool single = n < 256;
+  const u32 lhSize = 3 + (n >= 1024) + (n >= 16384);
+  if (lhSize + 8 > cap) return 0;
+  u8* body = out + lhSize; const u32 bodyCap = cap - lhSize;
+  u32 hdr = 0;
+  if (lane == 0) hdr = huf_write_header(body, bodyCap, w.he, w.state[0], w.sym);
+  hdr = __shfl_sync(FULLMASK, hdr, 0);
+  if (!hdr) return raw();
+  __syncwarp();
+  u32 csize = hdr;
+  if (single) {
+    u32 sz = 0;
+    if (lane == 0) sz = huf_encode_stream(body + csize, bodyCap - csize, lits, n, w.he);
+    sz = __shfl_sync(FULLMASK, sz, 0);
+    if (!sz) return raw();
+    csize += sz;
+  } else {
+    const u32 seg = (n + 3) / 4;
+    if (csize + 6 > bodyCap) return raw();
+    u32 sz = 0;
+    if (lane < 4) { const u32 from = lane * seg, len = lane < 3 ? seg : n - 3 * seg; sz = huf_encode_stream(tmp + (size_t)lane * kStreamTmp, kStreamTmp, lits + from, len, w.he); }
+    const u32 s0 = __shfl_sync(FULLMASK, sz, 0), s1 = __shfl_sync(FULLMASK, sz, 1), s2 = __shfl_sync(FULLMASK, sz, 2), s3 = __shfl_sync(FULLMASK, sz, 3);
+    if (!s0 || !s1 || !s2 || !s3 || s0 > 65535 || s1 > 65535 || s2 > 65535 || s3 > 65535) return raw();
+    if (csize + 6 + s0 + s1 + s2 + s3 > bodyCap) return raw();
+    if (lane == 0) { u8* j = body + csize; j[0] = (u8)s0; j[1] = (u8)(s0 >> 8); j[2] = (u8)s1; j[3] = (u8)(s1 >> 8); j[4] = (u8)s2; j[5] = (u8)(s2 >> 8); }
+    csize += 6;
+    __syncwarp();
+    wcopy(body + csize, tmp, s0, lane); csize += s0;
+    wcopy(body + csize, tmp + kStreamTmp, s1, lane); csize += s1;
+    wcopy(body + csize, tmp + 2 * (size_t)kStreamTmp, s2, lane); csize += s2;
+    wcopy(body + csize, tmp + 3 * (size_t)kStreamTmp, s3, lane); csize += s3;
+  }
+  const u32 minGain = (n >> 6) + 2;
+  if (csize + minGain >= n) return raw();
+  if (lane == 0) {
+    if (lhSize == 3) { const u32 v = 2 | ((single ? 0u : 1u) << 2) | (n << 4) | (csize << 14); out[0] = (u8)v; out[1] = (u8)(v >> 8); out[2] = (u8)(v >> 16); }
+    else if (lhSize == 4) { const u32 v = 2 | (2u << 2) | (n << 4) | (csize << 18); out[0] = (u8)v; out[1] = (u8)(v >> 8); out[2] = (u8)(v >> 16); out[3] = (u8)(v >> 24); }
+    else { const u32 v = 2 | (3u << 2) | (n << 4) | (csize << 22); out[0] = (u8)v; out[1] = (u8)(v >> 8); out[2] = (u8)(v >> 16); out[3] = (u8)(v >> 24); out[4] = (u8)(csize >> 10); }
+  }
+  __syncwarp();
+  return lhSize + csize;
+}
+
+// sequences section; returns bytes written, 0 on failure (mirror of enc_sequences)
+__device__ u32 warp_enc_sequences(u8* out, u32 cap, const SeqStore& st, u8* codes, EntWarp& w, int level, u32 lane) {
+  const u32 nbSeq = st.n;
+  if (cap < 4) return 0;
+  u32 op = 0;
+  if (lane == 0) op = enc_seq_count_header(out, nbSeq);
+  op = __shfl_sync(FULLMASK, op, 0);
+  if (nbSeq == 0) { __syncwarp(); return op; }
+  u8 *llc = codes, *ofc = codes + st.cap, *mlc = codes + 2 * st.cap;
+  for (u32 i = lane; i < 3 * 64; i += 32) (&w.cnt[0][0])[i] = 0;
+  __syncwarp();
+  for (u32 i = lane; i < nbSeq; i += 32) {
+    u32 ll, ob, mlm3; seq_get(st, i, ll, ob, mlm3);
+    const u32 lc = ll_code(ll), oc = highbit(ob), mc = ml_code(mlm3);
+    llc[i] = (u8)lc; ofc[i] = (u8)oc; mlc[i] = (u8)mc;
+    atomicAdd(&w.cnt[KIND_LL][lc], 1u); atomicAdd(&w.cnt[KIND_OF][oc], 1u); atomicAdd(&w.cnt[KIND_ML][mc], 1u);
+  }
+  __syncwarp();
+  u32 total = 0;
+  if (lane == 0) {
+    bool good = true; u32 used, o2 = op;
+    u8* modeByte = out + o2++;
+    const SeqKind kLL = seq_kind(KIND_LL), kOF = seq_kind(KIND_OF), kML = seq_kind(KIND_ML);
+    u32 mLL = 0, mOF = 0, mML = 0;
+    mLL = enc_seq_table_counts(w.ct[0], w.state[0], w.sym, w.cnt[KIND_LL], llc[nbSeq - 1], nbSeq, kLL, level, out + o2, cap - o2, &used);
+    if (mLL == 0xFF) good = false; else o2 += used;
+    if (good) { mOF = enc_seq_table_counts(w.ct[1], w.state[1], w.sym, w.cnt[KIND_OF], ofc[nbSeq - 1], nbSeq, kOF, level, out + o2, cap - o2, &used); if (mOF == 0xFF) good = false; else o2 += used; }
+    if (good) { mML = enc_seq_table_counts(w.ct[2], w.state[2], w.sym, w.cnt[KIND_ML], mlc[nbSeq - 1], nbSeq, kML, level, out + o2, cap - o2, &used); if (mML == 0xFF) good = false; else o2 += used; }
+    if (good) {
+      *modeByte = (u8)((mLL << 6) | (mOF << 4) | (mML << 2));
+      u8* e = enc_seq_bitstream(out + o2, out + cap, st, llc, ofc, mlc, w.ct[0], w.ct[1], w.ct[2]);
+      if (e) total = (u32)(e - out);
+    }
+  }
+  total = __shfl_sync(FULLMASK, total, 0);
+  __syncwarp();
+  return total;
+}
+
+__global__ void __launch_bounds__(128) k_enc_entropy(EncodeArgs a, EncodeScratch sc, u32 slot0, u32 nwarps) {
+  __shared__ EntWarp sm[4];
+  const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const u32 wid = blockIdx.x * 4 + wib;
+  if (wid >= nwarps) return;
+  EntWarp& w = sm[wib];
+  u8* slot = sc.slots + (size_t)(slot0 + wid) * slot_bytes();
+  u8* codes = slot; u8* tmp = slot + align16((size_t)kBlockSeqCap * 3);
+  for (u32 f = wid; f < a.n; f += nwarps) {
+    const u8* src = a.src_base + a.src_off[f]; const u32 size = a.src_size[f];
+    u8* dst = a.dst_base + a.dst_off[f]; const u32 cap = a.dst_cap[f];
+    u8* const lits0 = lit_base(a, sc, f); u32* const seqs0 = seq_base(a, sc, f); const BlockMeta* meta = meta_base(a, sc, f);
+    // frame header (mirror of encode_frame_with)
+    const u32 fcsCode = size < 256 ? 0 : (size < 65536 + 256 ? 1 : 2);
+    const u32 fhs = 4 + 1 + (fcsCode == 0 ? 1 : (fcsCode == 1 ? 2 : 4));
+    const u32 tail = a.checksum ? 4 : 0;
+    u32 res = 0; bool failed = false;
+    if (cap < fhs + 3 + tail) { failed = true; res = zerr(ZE_dstSize_tooSmall); }
+    u32 op = fhs;
+    if (!failed && lane == 0) {
+      dst[0] = 0x28; dst[1] = 0xB5; dst[2] = 0x2F; dst[3] = 0xFD;
+      dst[4] = (u8)((fcsCode << 6) | (1u << 5) | (a.checksum ? 4 : 0));
+      if (fcsCode == 0) dst[5] = (u8)size;
+      else if (fcsCode == 1) { const u32 v = size - 256; dst[5] = (u8)v; dst[6] = (u8)(v >> 8); }
+      else { dst[5] = (u8)size; dst[6] = (u8)(size >> 8); dst[7] = (u8)(size >> 16); dst[8] = (u8)(size >> 24); }
+    }
+    u32 pos = 0, blk = 0;
+    if (!failed) do {
+      const u32 bsize = size - pos < BLOCKSIZE_MAX ? size - pos : BLOCKSIZE_MAX;
+      const u32 last = pos + bsize == size;
+      const u8* bstart = src + pos;
+      if (op + 3 + tail > cap) { failed = true; res = zerr(ZE_dstSize_tooSmall); break; }
+      bool rle = bsize >= 2;
+      if (rle) {
+        const u8 b0 = bstart[0];
+        for (u32 i0 = 0; i0 < bsize && rle; i0 += 32) { const u32 i = i0 + lane; if (__ballot_sync(FULLMASK, i < bsize && bstart[i] != b0)) rle = false; }
+      }
+      if (rle) {
+        if (op + 4 + tail > cap) { failed = true; res = zerr(ZE_dstSize_tooSmall); break; }
+        if (lane == 0) { const u32 h = last | (1u << 1) | (bsize << 3); dst[op] = (u8)h; dst[op + 1] = (u8)(h >> 8); dst[op + 2] = (u8)(h >> 16); dst[op + 3] = bstart[0]; }
+        op += 4;
+      } else {
+        u32 csize = 0; bool compressed = false;
+        if (bsize >= 64) {
+          SeqStore st; st.seqs = seqs0 + 2 * (size_t)blk * kBlockSeqCap; st.n = meta[blk].nseq; st.cap = kBlockSeqCap;
+          st.lits = lits0 + (size_t)blk * BLOCKSIZE_MAX; st.nlits = meta[blk].nlits;
+          u32 room = bsize - 1 < BLOCKSIZE_MAX - 1 ? bsize - 1 : BLOCKSIZE_MAX - 1;
+          const u32 avail = cap - op - 3 - tail;
+          if (room > avail) room = avail;
+          u8* body = dst + op + 3;
+          const u32 l = warp_enc_literals(body, room, st.lits, st.nlits, w, tmp, lane);
+          if (l) {
+            const u32 sq = warp_enc_sequences(body + l, room - l, st, codes, w, a.level, lane);
+            if (sq && l + sq < bsize) { csize = l + sq; compressed = true; }
+          }
+        }
+        if (compressed) {
+          if (lane == 0) { const u32 h = last | (2u << 1) | (csize << 3); dst[op] = (u8)h; dst[op + 1] = (u8)(h >> 8); dst[op + 2] = (u8)(h >> 16); }
+          op += 3 + csize;
+        } else {
+          if (op + 3 + bsize + tail > cap) { failed = true; res = zerr(ZE_dstSize_tooSmall); break; }
+          if (lane == 0) { const u32 h = last | (0u << 1) | (bsize << 3); dst[op] = (u8)h; dst[op + 1] = (u8)(h >> 8); dst[op + 2] = (u8)(h >> 16); }
+          op += 3;
+          __syncwarp();
+          wcopy(dst + op, bstart, bsize, lane);
+          op += bsize;
+        }
+      }
+      __syncwarp();
+      pos += bsize; blk++;
+    } while (pos < size);
+    if (lane == 0) a.result[f] = failed ? res : op;
+    __syncwarp();
   }
 }
 
@@ -239,7 +453,7 @@ __global__ void __launch_bounds__(128) k_enc_xxh(EncodeArgs a) {
 
 size_t encode_bound(size_t srcSize) { return srcSize + (srcSize >> 8) + 32 + 3 * ((srcSize >> 17) + 1); }
 
-static constexpr u32 kSlotsPerStream = 148 * 32;
+static constexpr u32 kSlotsPerStream = 148 * 16;   // resident entropy-stage warps per stream partition
 static constexpr u32 kStreamSlots = 4;
 
 cudaError_t encode_alloc(EncodeScratch& s, size_t maxBatchBytes, size_t maxItems) {
@@ -273,7 +487,7 @@ cudaError_t encode_launch(const EncodeArgs& a, EncodeScratch& s, cudaStream_t st
   if (e != cudaSuccess) return e;
   // match stage: table sizes per level (u16 entries); as many resident warps as shared memory allows
   const bool dfast = a.level >= 3;
-  const u32 hlogL = a.level <= 1 ? 13 : 15, hlogS = 14, mls = a.level <= 1 ? 6 : 5;
+  const u32 hlogL = a.level <= 1 ? 13 : 14, hlogS = 13, mls = a.level <= 1 ? 6 : 5;   // u16 entries: 16 / 32 / 48 KB per warp
   const size_t smem = ((size_t)(1u << hlogL) + (dfast ? (1u << hlogS) : 0)) * 2;
   u32 perSm = (u32)((220 * 1024) / smem); if (perSm > 16) perSm = 16;
   u32 grid = (u32)s.sms * perSm; if (grid > a.n) grid = a.n;
@@ -285,7 +499,7 @@ cudaError_t encode_launch(const EncodeArgs& a, EncodeScratch& s, cudaStream_t st
   const u32 part = a.stream_slot % kStreamSlots;
   const u32 slots = a.n < kSlotsPerStream ? a.n : kSlotsPerStream;
   if (timing) cudaEventRecord(ev[1], st);
-  k_enc_entropy<<<(slots + 63) / 64, 64, 0, st>>>(a, s, part * kSlotsPerStream, slots);
+  k_enc_entropy<<<(slots + 3) / 4, 128, 0, st>>>(a, s, part * kSlotsPerStream, slots);
   if (timing) {
     cudaEventRecord(ev[2], st); cudaEventSynchronize(ev[2]);
     float m1 = 0, m2 = 0; cudaEventElapsedTime(&m1, ev[0], ev[1]); cudaEventElapsedTime(&m2, ev[1], ev[2]);

@@ -604,10 +604,9 @@ ZB_HD u32 ml_code(u32 mlm3) {
 struct SeqKind { u32 maxSym, maxLog, defLog; const s16* defNorm; };
 
 // chooses the table mode for one symbol kind and emits its description; returns the mode or 0xFF on failure
-ZB_HD u32 enc_seq_table(FseCTable& ct, u16* stateTable, u8* symScratch, const u8* codes, u32 nbSeq, const SeqKind& k, int level,
-                        u8* out, u32 cap, u32* used) {
-  u32 count[53]; for (u32 i = 0; i <= k.maxSym; i++) count[i] = 0;
-  for (u32 i = 0; i < nbSeq; i++) count[codes[i]]++;
+// count[] = histogram of the nbSeq codes of one kind (it is modified), lastCode = code of the last sequence
+ZB_HD u32 enc_seq_table_counts(FseCTable& ct, u16* stateTable, u8* symScratch, u32* count, u32 lastCode, u32 nbSeq, const SeqKind& k, int level,
+                               u8* out, u32 cap, u32* used) {
   u32 maxSym = k.maxSym; while (maxSym > 0 && !count[maxSym]) maxSym--;
   u32 most = 0; for (u32 s = 0; s <= maxSym; s++) if (count[s] > most) most = count[s];
   *used = 0;
@@ -628,7 +627,7 @@ ZB_HD u32 enc_seq_table(FseCTable& ct, u16* stateTable, u8* symScratch, const u8
   }
   u32 tl = fse_optimal_log(k.maxLog, nbSeq, maxSym);
   u32 total = nbSeq;
-  if (count[codes[nbSeq - 1]] > 1) { count[codes[nbSeq - 1]]--; total--; }   // the last symbol costs no bits
+  if (count[lastCode] > 1) { count[lastCode]--; total--; }   // the last symbol costs no bits
   if (!fse_normalize(norm, tl, count, total, maxSym)) return 0xFF;
   u32 h = fse_write_ncount(out, cap, norm, maxSym, tl);
   if (!h) return 0xFF;
@@ -636,30 +635,28 @@ ZB_HD u32 enc_seq_table(FseCTable& ct, u16* stateTable, u8* symScratch, const u8
   fse_build_ctable(ct, stateTable, norm, maxSym, tl, symScratch);
   return 2;
 }
+ZB_HD u32 enc_seq_table(FseCTable& ct, u16* stateTable, u8* symScratch, const u8* codes, u32 nbSeq, const SeqKind& k, int level,
+                        u8* out, u32 cap, u32* used) {
+  u32 count[53]; for (u32 i = 0; i <= k.maxSym; i++) count[i] = 0;
+  for (u32 i = 0; i < nbSeq; i++) count[codes[i]]++;
+  return enc_seq_table_counts(ct, stateTable, symScratch, count, codes[nbSeq - 1], nbSeq, k, level, out, cap, used);
+}
 
-// Returns bytes written, 0 on failure (caller falls back to a raw block).
-ZB_HD u32 enc_sequences(u8* out, u32 cap, const SeqStore& st, u8* codes, u16* ctables, u8* symScratch, int level) {
-  const u32 nbSeq = st.n; u32 op = 0;
-  if (cap < 4) return 0;
+ZB_HD u32 enc_seq_count_header(u8* out, u32 nbSeq) {
+  u32 op = 0;
   if (nbSeq < 128) out[op++] = (u8)nbSeq;
   else if (nbSeq < LONGNBSEQ) { out[op++] = (u8)((nbSeq >> 8) + 0x80); out[op++] = (u8)nbSeq; }
   else { out[op++] = 0xFF; out[op++] = (u8)(nbSeq - LONGNBSEQ); out[op++] = (u8)((nbSeq - LONGNBSEQ) >> 8); }
-  if (nbSeq == 0) return op;
-  u8 *llc = codes, *ofc = codes + st.cap, *mlc = codes + 2 * st.cap;
-  for (u32 i = 0; i < nbSeq; i++) {
-    u32 ll, ob, mlm3; seq_get(st, i, ll, ob, mlm3);
-    llc[i] = (u8)ll_code(ll); ofc[i] = (u8)highbit(ob); mlc[i] = (u8)ml_code(mlm3);
-  }
-  const SeqKind kLL = {MaxLL, LLFSELog, 6, kLLnorm}, kOF = {MaxOff, OffFSELog, 5, kOFnorm}, kML = {MaxML, MLFSELog, 6, kMLnorm};
-  u8* modeByte = out + op++; u32 used;
-  FseCTable ctLL, ctOF, ctML;
-  const u32 mLL = enc_seq_table(ctLL, ctables, symScratch, llc, nbSeq, kLL, level, out + op, cap - op, &used); if (mLL == 0xFF) return 0; op += used;
-  const u32 mOF = enc_seq_table(ctOF, ctables + 514, symScratch, ofc, nbSeq, kOF, level, out + op, cap - op, &used); if (mOF == 0xFF) return 0; op += used;
-  const u32 mML = enc_seq_table(ctML, ctables + 1028, symScratch, mlc, nbSeq, kML, level, out + op, cap - op, &used); if (mML == 0xFF) return 0; op += used;
-  *modeByte = (u8)((mLL << 6) | (mOF << 4) | (mML << 2));
-  // bitstream: sequences last to first; per sequence the decoder reads offset, matchLength, litLength extra
-  // bits, then the LL, ML, OF state bits (:1504-1550) — so we write them in the opposite order
-  BitWriter w; bw_init(w, out + op, out + cap);
+  return op;
+}
+
+// bitstream: sequences last to first; per sequence the decoder reads offset, matchLength, litLength extra
+// bits, then the LL, ML, OF state bits (:1504-1550) — so we write them in the opposite order.
+// Returns the end of the stream or nullptr when out of room.
+ZB_HD u8* enc_seq_bitstream(u8* out, u8* end, const SeqStore& st, const u8* llc, const u8* ofc, const u8* mlc,
+                            const FseCTable& ctLL, const FseCTable& ctOF, const FseCTable& ctML) {
+  const u32 nbSeq = st.n;
+  BitWriter w; bw_init(w, out, end);
   u32 sLL, sOF, sML;
   {
     const u32 i = nbSeq - 1; u32 ll, ob, mlm3; seq_get(st, i, ll, ob, mlm3);
@@ -678,7 +675,34 @@ ZB_HD u32 enc_sequences(u8* out, u32 cap, const SeqStore& st, u8* codes, u16* ct
     bw_add(w, ob - (1u << oc), oc); bw_flush(w);
   }
   fse_flush_state(w, ctML, sML); fse_flush_state(w, ctOF, sOF); fse_flush_state(w, ctLL, sLL);
-  u8* e = bw_close(w);
+  return bw_close(w);
+}
+
+ZB_HD SeqKind seq_kind(int kind) {
+  if (kind == KIND_LL) return SeqKind{MaxLL, LLFSELog, 6, kLLnorm};
+  if (kind == KIND_OF) return SeqKind{MaxOff, OffFSELog, 5, kOFnorm};
+  return SeqKind{MaxML, MLFSELog, 6, kMLnorm};
+}
+
+// Returns bytes written, 0 on failure (caller falls back to a raw block).
+ZB_HD u32 enc_sequences(u8* out, u32 cap, const SeqStore& st, u8* codes, u16* ctables, u8* symScratch, int level) {
+  const u32 nbSeq = st.n;
+  if (cap < 4) return 0;
+  u32 op = enc_seq_count_header(out, nbSeq);
+  if (nbSeq == 0) return op;
+  u8 *llc = codes, *ofc = codes + st.cap, *mlc = codes + 2 * st.cap;
+  for (u32 i = 0; i < nbSeq; i++) {
+    u32 ll, ob, mlm3; seq_get(st, i, ll, ob, mlm3);
+    llc[i] = (u8)ll_code(ll); ofc[i] = (u8)highbit(ob); mlc[i] = (u8)ml_code(mlm3);
+  }
+  const SeqKind kLL = seq_kind(KIND_LL), kOF = seq_kind(KIND_OF), kML = seq_kind(KIND_ML);
+  u8* modeByte = out + op++; u32 used;
+  FseCTable ctLL, ctOF, ctML;
+  const u32 mLL = enc_seq_table(ctLL, ctables, symScratch, llc, nbSeq, kLL, level, out + op, cap - op, &used); if (mLL == 0xFF) return 0; op += used;
+  const u32 mOF = enc_seq_table(ctOF, ctables + 514, symScratch, ofc, nbSeq, kOF, level, out + op, cap - op, &used); if (mOF == 0xFF) return 0; op += used;
+  const u32 mML = enc_seq_table(ctML, ctables + 1028, symScratch, mlc, nbSeq, kML, level, out + op, cap - op, &used); if (mML == 0xFF) return 0; op += used;
+  *modeByte = (u8)((mLL << 6) | (mOF << 4) | (mML << 2));
+  u8* e = enc_seq_bitstream(out + op, out + cap, st, llc, ofc, mlc, ctLL, ctOF, ctML);
   if (!e) return 0;
   return (u32)(e - out);
 }
