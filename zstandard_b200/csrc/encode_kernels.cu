@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(32) k_enc_match(EncodeArgs a, EncodeScratch sc
         u32 p0 = bpos + (bpos == 0 ? 1 : 0);
         while (p0 < ilimit) {
           const u32 step = 1 + ((p0 - anchor) >> 8);                 // skim incompressible runs
+          if (lane < 4) prefetch_line(src + p0 + 384 + 128 * lane);   // the source streams in from HBM: keep ~4 lines ahead in L1
           const u32 p = p0 + lane * step;
           const bool act = p < ilimit;
           const u64 v = act ? ldu64(src + p) : 0;
@@ -487,7 +488,7 @@ cudaError_t encode_launch(const EncodeArgs& a, EncodeScratch& s, cudaStream_t st
   if (e != cudaSuccess) return e;
   // match stage: table sizes per level (u16 entries); as many resident warps as shared memory allows
   const bool dfast = a.level >= 3;
-  const u32 hlogL = a.level <= 1 ? 13 : 14, hlogS = 13, mls = a.level <= 1 ? 6 : 5;   // u16 entries: 16 / 32 / 48 KB per warp
+  const u32 hlogL = 13, hlogS = 12, mls = a.level <= 1 ? 6 : 5;   // u16 entries: 16 KB (levels 1-2) / 24 KB (level 3) per warp
   const size_t smem = ((size_t)(1u << hlogL) + (dfast ? (1u << hlogS) : 0)) * 2;
   u32 perSm = (u32)((220 * 1024) / smem); if (perSm > 16) perSm = 16;
   u32 grid = (u32)s.sms * perSm; if (grid > a.n) grid = a.n;
