@@ -250,6 +250,46 @@ __device__ __forceinline__ void flat_copy(u8* g, const u8* src, bool fill, u8 fi
   }
 }
 
+// Flattened copy of many short non-overlapping matches in units of 4 bytes: run of lane j has len_j bytes
+// (off_j >= len_j), i.e. (len_j + 3) / 4 units; unit u moves bytes [4u, min(4u + 4, len_j)) from g + mrel_j - off_j.
+// The source word is assembled from two aligned loads (bytes past the run's end are read and dropped).
+template <int U>
+__device__ __forceinline__ void flat_copy_m4(u8* g, u32 totalUnits, u32 uincl, u32 uexcl, u32 mrel, u32 off, u32 len, u32 lane) {
+  for (u32 t0 = 0; t0 < totalUnits; t0 += 32 * U) {
+    u32 t[U], j[U], dj[U], ej[U], oj[U], nj[U], v[U];
+#pragma unroll
+    for (int k = 0; k < U; k++) { t[k] = t0 + 32 * k + lane; j[k] = 0; }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+#pragma unroll
+      for (int k = 0; k < U; k++) { const u32 x = __shfl_sync(FULLMASK, uincl, (j[k] + s - 1) & 31); if (x <= t[k]) j[k] += s; }
+    }
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      j[k] &= 31;
+      dj[k] = __shfl_sync(FULLMASK, mrel, j[k]); ej[k] = __shfl_sync(FULLMASK, uexcl, j[k]);
+      oj[k] = __shfl_sync(FULLMASK, off, j[k]); nj[k] = __shfl_sync(FULLMASK, len, j[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      v[k] = 0;
+      if (t[k] < totalUnits) {
+        const u8* sp = g + dj[k] + 4 * (t[k] - ej[k]) - (size_t)oj[k];
+        const u32* w = (const u32*)((uintptr_t)sp & ~(uintptr_t)3); const u32 sh = ((u32)(uintptr_t)sp & 3) * 8;
+        const u32 a0 = w[0], a1 = sh ? w[1] : 0;
+        v[k] = __funnelshift_r(a0, a1, sh);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < U; k++) if (t[k] < totalUnits) {
+      const u32 b0 = 4 * (t[k] - ej[k]); const u32 cnt = nj[k] - b0;   // >= 1
+      u8* d = g + dj[k] + b0;
+      if (cnt >= 4 && (((uintptr_t)d) & 3) == 0) *(u32*)d = v[k];
+      else { d[0] = (u8)v[k]; if (cnt > 1) d[1] = (u8)(v[k] >> 8); if (cnt > 2) d[2] = (u8)(v[k] >> 16); if (cnt > 3) d[3] = (u8)(v[k] >> 24); }
+    }
+  }
+}
+
 // one match copied by the whole warp; handles every offset/length relation (byte-serial semantics of :1319-1350)
 __device__ __forceinline__ void warp_match(u8* d, u32 off, u32 len, u32 lane) {
   const u8* s = d - off;
@@ -336,7 +376,8 @@ __global__ void __launch_bounds__(EXEC_THREADS, 8) k_exec(DecodeArgs a) {
             const u32 sincl = warp_incl_scan(ls, lane), sexcl = sincl - ls;
             const u32 Ls = __shfl_sync(FULLMASK, sincl, 31);
             const u32 lsrc = lincl - ll;                    // literal source position of this lane, relative to litPos
-            if (Ls) flat_copy<2>(g, isRle ? g : lit + litPos, isRle, (u8)rleByte, Ls, sincl, sexcl, excl, lsrc, lane);
+            if (Ls > 32) flat_copy<2>(g, isRle ? g : lit + litPos, isRle, (u8)rleByte, Ls, sincl, sexcl, excl, lsrc, lane);
+            else if (Ls) flat_copy<1>(g, isRle ? g : lit + litPos, isRle, (u8)rleByte, Ls, sincl, sexcl, excl, lsrc, lane);
             while (bigMask) {
               const u32 j = (u32)__ffs(bigMask) - 1; bigMask &= bigMask - 1;
               const u32 dj = __shfl_sync(FULLMASK, excl, j), nj = __shfl_sync(FULLMASK, ll, j), lj = __shfl_sync(FULLMASK, lsrc, j);
@@ -365,10 +406,12 @@ __global__ void __launch_bounds__(EXEC_THREADS, 8) k_exec(DecodeArgs a) {
               const bool ready = hasM && !((doneMask >> lane) & 1) && ((depMask & ~doneMask) == 0);
               const unsigned R = __ballot_sync(FULLMASK, ready);
               const bool plain = ready && off >= ml && ml < 128;
-              const u32 len = plain ? ml : 0;
-              const u32 pincl = warp_incl_scan(len, lane), pexcl = pincl - len;
+              const u32 len = plain ? ml : 0, units = (len + 3) >> 2;
+              const u32 pincl = warp_incl_scan(units, lane), pexcl = pincl - units;
               const u32 Tt = __shfl_sync(FULLMASK, pincl, 31);
-              if (Tt) flat_copy<4>(g, nullptr, false, 0, Tt, pincl, pexcl, mrel, off, lane);
+              if (Tt > 64) flat_copy_m4<4>(g, Tt, pincl, pexcl, mrel, off, len, lane);
+              else if (Tt > 32) flat_copy_m4<2>(g, Tt, pincl, pexcl, mrel, off, len, lane);
+              else if (Tt) flat_copy_m4<1>(g, Tt, pincl, pexcl, mrel, off, len, lane);
               unsigned big = __ballot_sync(FULLMASK, ready && !plain);
               while (big) {
                 const u32 j = (u32)__ffs(big) - 1; big &= big - 1;
