@@ -74,18 +74,20 @@ class HostSim:
         h.hostsim_decompress.restype = ctypes.c_uint32
         h.hostsim_decompress.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint32,
                                          ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_int)]
+        h.hostsim_decompress2.restype = ctypes.c_uint32
+        h.hostsim_decompress2.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint32,
+                                          ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_int),
+                                          ctypes.POINTER(ctypes.c_uint32), ctypes.c_void_p]
         self.lib = h
 
     def decompress(self, frame, cap, oracle):
+        """One item through the replayed stages, one pass per data frame; the oracle's XXH64 stands in for k_xxh."""
         frame = bytes(frame)
         buf = ctypes.create_string_buffer(max(cap, 1))
-        tr = ctypes.c_uint32(0)
-        nx = ctypes.c_int(0)
-        r = self.lib.hostsim_decompress(buf, cap, frame, len(frame), ctypes.byref(tr), ctypes.byref(nx))
+        tr, nx, lb = ctypes.c_uint32(0), ctypes.c_int(0), ctypes.c_uint32(0)
+        xxh = ctypes.cast(oracle.lib.oracle_xxh64, ctypes.c_void_p)
+        r = self.lib.hostsim_decompress2(buf, cap, frame, len(frame), ctypes.byref(tr), ctypes.byref(nx), ctypes.byref(lb), xxh)
         out = buf.raw[:r] if not is_err(r) else None
-        if out is not None and nx.value:   # the checksum kernel's job; emulate with the oracle's XXH64
-            if (oracle.xxh64(out) & 0xFFFFFFFF) != int.from_bytes(frame[tr.value:tr.value + 4], "little"):
-                return err(22), None
         return r, out
 
 
@@ -150,3 +152,38 @@ def mutate(rng, frame):
 
 def skippable(payload, nibble=0):
     return (0x184D2A50 + nibble).to_bytes(4, "little") + len(payload).to_bytes(4, "little") + payload
+
+
+def multi_frame_items(seed=11, count=40):
+    """[(item bytes, capacity)] of items holding several data frames (DecompressMultiFrame, ZStdDecompress.cs:2096-2160):
+    2..6 frames with and without checksum, skippable frames between them, one corrupted / truncated / short-capacity
+    variant each."""
+    rng = random.Random(seed)
+    pool = make_frames(seed, 60, sizes=[0, 1, 100, 1000, 5000, 70000, 140000])
+    items = []
+    for t in range(count):
+        k = rng.randint(2, 6)
+        parts = [pool[rng.randrange(len(pool))] for _ in range(k)]
+        blob, total = b"", 0
+        for frame, data in parts:
+            if rng.random() < 0.3:
+                blob += skippable(bytes(rng.randrange(256) for _ in range(rng.randint(0, 20))))
+            blob += frame
+            total += len(data)
+        if rng.random() < 0.3:
+            blob += skippable(b"end")
+        items.append((blob, total))
+        items.append((blob, total + 7))
+        if total:
+            items.append((blob, max(0, total - 1 - rng.randrange(min(total, 3000)))))   # some frame no longer fits
+        items.append((blob[:len(blob) - 1 - rng.randrange(min(len(blob) - 1, 200))], total))   # truncated in the tail
+        last = parts[-1][0]
+        if len(last) > 12:                                                  # corruption inside the last data frame
+            pos = len(blob) - rng.randrange(4, min(len(last), 60))
+            mutated = bytearray(blob); mutated[pos] ^= 1 << rng.randrange(8)
+            items.append((bytes(mutated), total))
+        first = parts[0][0]
+        if len(first) > 12 and len(parts[0][1]) > 0:                        # corruption inside the first data frame
+            mutated = bytearray(blob); mutated[blob.index(first) + len(first) - 2] ^= 0x10
+            items.append((bytes(mutated), total))
+    return items

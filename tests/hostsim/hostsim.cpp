@@ -44,10 +44,10 @@ void sim_huf(const u8* src, u32 size, FrameInfo& fi, u8* lit, u64 litCap) {
       if (read_lit_hdr(bp, bsz, lh, &needs)) break;
       if (lh.type >= 2) {
         if (lh.type == 3 && !haveTable) break;
-        bool ok = true; u32 code = ZE_corruption_detected;
+        bool ok = true;
         const u8* body = bp + lh.lhSize; u32 bodySize = lh.litCSize;
-        if (litRun + lh.litSize + 3 > litCap) { ok = false; code = ZE_dstSize_tooSmall; }
-        if (ok && lh.type == 2) {
+        const bool dry = litRun + lh.litSize + 3 > litCap;
+        if (lh.type == 2) {
           if (!lh.single && (lh.litSize == 0 || bodySize == 0)) ok = false;
           u32 hdr = 0, nbSym = 0, tl = 0;
           if (ok) {
@@ -61,14 +61,14 @@ void sim_huf(const u8* src, u32 size, FrameInfo& fi, u8* lit, u64 litCap) {
           }
         }
         if (ok) {
-          if (lh.single) ok = huf_decode_stream(body, bodySize, lit + litRun, lh.litSize, dt, tableLog, ringBuf);
+          if (lh.single) ok = dry ? huf_check_stream(body, bodySize, lh.litSize, dt, tableLog) : huf_decode_stream(body, bodySize, lit + litRun, lh.litSize, dt, tableLog, ringBuf);
           else for (u32 sub = 0; sub < 4; sub++) {
             HufStream st; bool good = huf_split4(body, bodySize, lh.litSize, sub, st);
-            if (good) good = huf_decode_stream(st.src, st.len, lit + litRun + st.outOfs, st.count, dt, tableLog, ringBuf);
+            if (good) good = dry ? huf_check_stream(st.src, st.len, st.count, dt, tableLog) : huf_decode_stream(st.src, st.len, lit + litRun + st.outOfs, st.count, dt, tableLog, ringBuf);
             if (!good) ok = false;
           }
         }
-        if (!ok) { fi.huf_err_block = blk; fi.huf_err_code = code; break; }
+        if (!ok || dry) { fi.huf_err_block = blk; fi.huf_err_code = ok ? HUF_DRY : ZE_corruption_detected; break; }
         litRun += lh.litSize;
       }
     }
@@ -78,8 +78,8 @@ void sim_huf(const u8* src, u32 size, FrameInfo& fi, u8* lit, u64 litCap) {
 }
 
 // serial stand-in for k_exec: same checks in the same order, byte-serial copies; no checksum verification
-u32 sim_exec(const u8* src, u32 size, const FrameInfo& fi, u8* dst, u64 cap, const u8* litScratch, const SeqRec* recs, bool* needXxh, u32* trailerOff) {
-  u32 pos = fi.body_off, blk = 0; u64 op = 0, litRun = 0, recRun = 0; bool litEntropy = false; u32 err = 0;
+u32 sim_exec(const u8* src, u32 size, const FrameInfo& fi, u8* dst, u64 cap, const u8* litScratch, const SeqRec* recs, bool* needXxh, u32* trailerOff, u32* nextOff, u32* decoded) {
+  u32 pos = fi.body_off, blk = 0; u64 op = 0, litRun = 0, recRun = 0; bool litEntropy = false, dry = false; u32 err = 0;
   while (true) {
     BlockHdr bh;
     err = read_block_hdr(src + pos, size - pos, bh);
@@ -95,7 +95,7 @@ u32 sim_exec(const u8* src, u32 size, const FrameInfo& fi, u8* dst, u64 cap, con
       if (needs && !litEntropy) { err = ZE_dictionary_corrupted; break; }
       if (e) { err = e; break; }
       const u8* lit = nullptr; u32 rleByte = 0; bool isRle = false;
-      if (lh.type >= 2) { if (fi.huf_err_block == blk) { err = fi.huf_err_code; break; } litEntropy = true; lit = litScratch + litRun; litRun += lh.litSize; }
+      if (lh.type >= 2) { if (fi.huf_err_block == blk) { if (fi.huf_err_code != HUF_DRY) { err = fi.huf_err_code; break; } dry = true; } litEntropy = true; lit = litScratch + litRun; litRun += lh.litSize; }
       else if (lh.type == 0) lit = bp + lh.lhSize;
       else { isRle = true; rleByte = bp[lh.lhSize]; }
       const u32 litSize = lh.litSize;
@@ -107,14 +107,15 @@ u32 sim_exec(const u8* src, u32 size, const FrameInfo& fi, u8* dst, u64 cap, con
       u64 litPos = 0;
       if (nbSeq) {
         const SeqRec* r = recs + recRun;
-        for (; r->x != 0; r++) {
+        for (; (r->x | r->y) != 0; r++) {
+          if (r->x == 0) { if (op + r->y > cap) { err = ZE_dstSize_tooSmall; break; } continue; }   // split sequence ahead: whole-sequence check
           u32 ll = r->y & 0xFFFF, ml = r->y >> 16, off = r->x;
           if (op + ll + ml > cap) { err = ZE_dstSize_tooSmall; break; }
           if (litPos + ll > litSize) { err = ZE_corruption_detected; break; }
           if ((u64)off > op + ll) { err = ZE_corruption_detected; break; }
-          for (u32 i = 0; i < ll; i++) dst[op + i] = isRle ? (u8)rleByte : lit[litPos + i];
+          if (!dry) for (u32 i = 0; i < ll; i++) dst[op + i] = isRle ? (u8)rleByte : lit[litPos + i];
           op += ll; litPos += ll;
-          for (u32 i = 0; i < ml; i++) dst[op + i] = dst[op + i - off];
+          if (!dry) for (u32 i = 0; i < ml; i++) dst[op + i] = dst[op + i - off];
           op += ml;
         }
         if (err) break;
@@ -122,7 +123,7 @@ u32 sim_exec(const u8* src, u32 size, const FrameInfo& fi, u8* dst, u64 cap, con
         if (fi.seq_err_block == blk) { err = fi.seq_err_code; break; }
       }
       u64 lastLL = litSize - litPos;
-      if (lastLL > cap - op) { err = ZE_dstSize_tooSmall; break; }
+      if (lastLL > cap - op || dry) { err = ZE_dstSize_tooSmall; break; }
       for (u64 i = 0; i < lastLL; i++) dst[op + i] = isRle ? (u8)rleByte : lit[litPos + i];
       op += lastLL;
     }
@@ -134,47 +135,62 @@ u32 sim_exec(const u8* src, u32 size, const FrameInfo& fi, u8* dst, u64 cap, con
     if ((fi.flags & FI_FCS_KNOWN) && op != fi.fcs) err = ZE_corruption_detected;
     else if (fi.flags & FI_CHECKSUM) { if (size - pos < 4) err = ZE_checksum_wrong; else { *trailerOff = pos; pos += 4; *needXxh = true; } }
   }
-  u32 tailErr = 0;
+  u32 tailErr = 0; *decoded = (u32)op;
   if (!err) while (true) {
     u32 rem = size - pos;
     if (rem < 5) { if (rem) tailErr = ZE_srcSize_wrong; break; }
     u32 magic = ld32(src + pos);
-    if (magic == MAGIC) { tailErr = ZE_GENERIC; break; }
+    if (magic == MAGIC) { *nextOff = pos; break; }
     if ((magic & 0xFFFFFFF0u) != MAGIC_SKIP) { tailErr = ZE_prefix_unknown; break; }
     if (rem < 8) { tailErr = ZE_srcSize_wrong; break; }
     u32 skip = ld32(src + pos + 4) + 8u;
     if (rem < skip) { tailErr = ZE_srcSize_wrong; break; }
     pos += skip;
   }
-  return err ? zerr(err) : (tailErr ? zerr(tailErr) : (u32)op);
+  return err ? zerr(err) : (tailErr ? zerr(tailErr) : fi.out_base + (u32)op);
 }
 
 }  // namespace
 
-extern "C" uint32_t hostsim_decompress(uint8_t* dst, uint32_t cap, const uint8_t* src_in, uint32_t size, uint32_t* trailer_off, int* need_xxh) {
+// One pass per data frame of the item, as the host loop around the kernels does (api.cu, decode_more_passes).
+// xxh: XXH64 implementation to stand in for k_xxh (the test passes the oracle's); null = checksums are not verified
+// and trailer_off / need_xxh describe the LAST data frame, *last_base where its output starts within dst.
+typedef uint64_t (*xxh_fn)(const void*, size_t, uint64_t);
+extern "C" uint32_t hostsim_decompress2(uint8_t* dst_in, uint32_t capAll, const uint8_t* src_in, uint32_t size, uint32_t* trailer_off, int* need_xxh, uint32_t* last_base, xxh_fn xxh) {
   // the device reads whole aligned words around the streams: give the copy slack on both sides
   std::vector<u8> padded(size + 32, 0);
   u8* src = padded.data() + 16;
   memcpy(src, src_in, size);
-  FrameInfo fi; u32 r = 0;
-  *need_xxh = 0; *trailer_off = 0;
-  if (!parse_item(src, size, fi, &r)) return r;
-  std::vector<u8> lit((size_t)cap + 64);
-  std::vector<SeqRec> recs(seq_capacity(cap) + 40);
-  sim_huf(src, size, fi, lit.data(), (u64)cap + 40);
-  static thread_local Sim* sim = nullptr; if (!sim) sim = new Sim();
-  SeqTableSet T;
-  T.space[KIND_LL] = sim->ll.data(); T.space[KIND_ML] = sim->ml.data(); T.space[KIND_OF] = sim->of.data(); T.stride = 1;
-  T.defs[KIND_LL] = sim->defLL; T.defs[KIND_OF] = sim->defOF; T.defs[KIND_ML] = sim->defML;
-  SeqFrameOut res;
-  s16 normBuf[53]; u16 nextBuf[53]; alignas(16) u32 ringBuf[ZB_RING_WORDS];
-  seq_decode_frame(src, size, fi.body_off, T, recs.data(), seq_capacity(cap), res, sim->llInfo, sim->mlInfo, normBuf, nextBuf, ringBuf);
-  if (res.err_block != 0xFFFFFFFFu) { fi.seq_err_block = res.err_block; fi.seq_err_code = res.err_code; fi.seq_err_index = res.err_index; }
-  bool nx; u32 tr;
+  *need_xxh = 0; *trailer_off = 0; *last_base = 0;
   static u8 dummy[8];
-  u32 out = sim_exec(src, size, fi, dst ? dst : dummy, cap, lit.data(), recs.data(), &nx, &tr);
-  *need_xxh = nx; *trailer_off = tr;
-  return out;
+  u32 start = 0, outBase = 0, out = 0;
+  while (true) {
+    FrameInfo fi; u32 r = 0;
+    if (!parse_item(src, size, fi, &r, start, outBase)) return r;
+    const u32 cap = capAll - fi.out_base; u8* dst = dst_in ? dst_in + fi.out_base : dummy;
+    std::vector<u8> lit((size_t)cap + 64);
+    std::vector<SeqRec> recs(seq_capacity(cap) + 40);
+    sim_huf(src, size, fi, lit.data(), (u64)cap + 40);
+    static thread_local Sim* sim = nullptr; if (!sim) sim = new Sim();
+    SeqTableSet T;
+    T.space[KIND_LL] = sim->ll.data(); T.space[KIND_ML] = sim->ml.data(); T.space[KIND_OF] = sim->of.data(); T.stride = 1;
+    T.defs[KIND_LL] = sim->defLL; T.defs[KIND_OF] = sim->defOF; T.defs[KIND_ML] = sim->defML;
+    SeqFrameOut res;
+    s16 normBuf[53]; u16 nextBuf[53]; alignas(16) u32 ringBuf[ZB_RING_WORDS];
+    seq_decode_frame(src, size, fi.body_off, fi.window, T, recs.data(), seq_capacity(cap), res, sim->llInfo, sim->mlInfo, normBuf, nextBuf, ringBuf);
+    if (res.err_block != 0xFFFFFFFFu) { fi.seq_err_block = res.err_block; fi.seq_err_code = res.err_code; fi.seq_err_index = res.err_index; }
+    bool nx; u32 tr, nextOff = 0, produced = 0;
+    out = sim_exec(src, size, fi, dst, cap, lit.data(), recs.data(), &nx, &tr, &nextOff, &produced);
+    *need_xxh = nx; *trailer_off = tr; *last_base = fi.out_base;
+    // k_xxh runs whenever the frame itself decoded (even if what follows it in the item is malformed) and overrides the result
+    if (nx && xxh && dst_in && (u32)xxh(dst, produced, 0) != ld32(src + tr)) return zerr(ZE_checksum_wrong);
+    if (is_err(out) || !nextOff) return out;
+    start = nextOff; outBase = out;
+  }
+}
+extern "C" uint32_t hostsim_decompress(uint8_t* dst, uint32_t cap, const uint8_t* src_in, uint32_t size, uint32_t* trailer_off, int* need_xxh) {
+  uint32_t lastBase;
+  return hostsim_decompress2(dst, cap, src_in, size, trailer_off, need_xxh, &lastBase, nullptr);
 }
 
 // debug surface: literals + records of the first frame of an item (no execution)
@@ -193,7 +209,7 @@ extern "C" uint32_t hostsim_stages(const uint8_t* src_in, uint32_t size, uint32_
   T.defs[KIND_LL] = sim->defLL; T.defs[KIND_OF] = sim->defOF; T.defs[KIND_ML] = sim->defML;
   SeqFrameOut res;
   s16 normBuf[53]; u16 nextBuf[53]; alignas(16) u32 ringBuf[ZB_RING_WORDS];
-  seq_decode_frame(src, size, fi.body_off, T, recs.data(), seq_capacity(cap), res, sim->llInfo, sim->mlInfo, normBuf, nextBuf, ringBuf);
+  seq_decode_frame(src, size, fi.body_off, fi.window, T, recs.data(), seq_capacity(cap), res, sim->llInfo, sim->mlInfo, normBuf, nextBuf, ringBuf);
   memcpy(lit_out, lit.data(), cap);
   u32 n = (u32)std::min<size_t>(max_recs, recs.size());
   memcpy(rec_out, recs.data(), (size_t)n * 8);

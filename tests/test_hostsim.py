@@ -22,22 +22,25 @@ def test_valid_frames_match_oracle(hostsim, oracle):
             assert ro == rh and oo == oh, (n, cap, hex(ro), hex(rh))
 
 
-def test_fuzzed_frames_same_verdict(hostsim, oracle):
+def test_fuzzed_frames_same_result_code(hostsim, oracle):
     rng = random.Random(77)
     frames = helpers.make_frames(202, 120)
-    verdict_mismatch = 0
     for frame, data in frames:
         if len(frame) < 12:
             continue
-        for _ in range(6):
+        for _ in range(10):
             b = helpers.mutate(rng, frame)
-            cap = len(data) + rng.choice([0, 0, 5])
-            ro, oo, over = oracle.decompress(b, cap)
+            cap = max(0, len(data) + rng.choice([0, 0, 0, 5, -1, -100, 1000]))
+            ro, oo, _ = oracle.decompress(b, cap)
             rh, oh = hostsim.decompress(b, cap, oracle)
-            eo, eh = helpers.is_err(ro), helpers.is_err(rh)
-            if eo != eh:
-                # documented deviation: the reference accepts a final sequence whose bits were read
-                # past the stream start; the GPU path reports corruption_detected
-                assert over and eh and not eo, (hex(ro), hex(rh))
-            elif not eo:
-                assert ro == rh and oo == oh
+            # same result code (error codes included) and bytes: the stages reproduce the reference's order of checks
+            # and what its 4-byte bit container yields when a sequence reads below the stream start
+            assert ro == rh and oo == oh, (b.hex()[:80], cap, hex(ro), hex(rh))
+
+
+def test_items_with_several_data_frames(hostsim, oracle):
+    """One pass per data frame (the loop api.cu runs around the kernels) against the reference's multi-frame loop."""
+    for blob, cap in helpers.multi_frame_items():
+        ro, oo, _ = oracle.decompress(blob, cap)
+        rh, oh = hostsim.decompress(blob, cap, oracle)
+        assert ro == rh and oo == oh, (len(blob), cap, hex(ro), hex(rh))

@@ -6,8 +6,7 @@
 //
 // Data movement.  A batch is cut into sub-batches that fit the device arenas; a sub-batch is cut into slices that
 // are dealt round-robin to NSTREAMS streams, so the H2D copy of one slice, the kernels of another and the D2H
-// copy of a third overlap — and so do the latency-bound entropy kernels of one slice with the copy-bound execute
-// kernel of another.  When the caller's buffers are already laid out back to back (the layout a managed host gets
+// copy of a third overlap.  When the caller's buffers are already laid out back to back (the layout a managed host gets
 // from one pinned array plus offsets) they are DMA'd directly; otherwise items are gathered/scattered through the
 // context's pinned staging.
 #include <cuda_runtime.h>
@@ -34,15 +33,16 @@ constexpr size_t SLICE_BYTES = 48u << 20;   // uncompressed bytes per slice (sev
 struct Device {
   int id = 0;
   cudaStream_t stream[NSTREAMS] = {};
-  cudaEvent_t forkEv = nullptr, joinEv[NSTREAMS] = {};
   // device memory
   u8 *d_src = nullptr, *d_dst = nullptr;       // staging for the host-pointer API
   u64 *d_srcOff = nullptr, *d_dstOff = nullptr; u32 *d_srcSize = nullptr, *d_dstCap = nullptr, *d_result = nullptr;
   FrameInfo* d_info = nullptr; u8* d_lit = nullptr; SeqRec* d_seq = nullptr;
+  u32* d_more = nullptr;                        // per-stream counters of items with another data frame to decode (DecodeArgs::more)
   EncodeScratch enc;                            // encoder arenas (encode_kernels.cuh)
   // pinned host memory
   u8 *h_src = nullptr, *h_dst = nullptr;
   u64 *h_srcOff = nullptr, *h_dstOff = nullptr; u32 *h_srcSize = nullptr, *h_dstCap = nullptr, *h_result = nullptr;
+  u32* h_more = nullptr;
 };
 
 }  // namespace
@@ -70,14 +70,13 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 int alloc_device(zstdb200_ctx* ctx, Device& d) {
   CK(cudaSetDevice(d.id));
   for (auto& s : d.stream) CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-  CK(cudaEventCreateWithFlags(&d.forkEv, cudaEventDisableTiming));
-  for (auto& e : d.joinEv) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   const size_t items = ctx->maxItems;
   CK(cudaMalloc(&d.d_src, ctx->srcCap + 256));
   CK(cudaMalloc(&d.d_dst, ctx->dstSpan + 256));
   CK(cudaMalloc(&d.d_srcOff, items * 8)); CK(cudaMalloc(&d.d_dstOff, items * 8));
   CK(cudaMalloc(&d.d_srcSize, items * 4)); CK(cudaMalloc(&d.d_dstCap, items * 4)); CK(cudaMalloc(&d.d_result, items * 4));
   CK(cudaMalloc(&d.d_info, items * sizeof(FrameInfo)));
+  CK(cudaMalloc(&d.d_more, NSTREAMS * 4)); CK(cudaMallocHost(&d.h_more, NSTREAMS * 4));
   CK(cudaMalloc(&d.d_lit, decode_lit_arena_bytes(ctx->dstSpan, items)));
   CK(cudaMalloc(&d.d_seq, decode_seq_arena_bytes(ctx->dstSpan, items)));
   CK(cudaMallocHost(&d.h_src, ctx->srcCap + 256)); CK(cudaMallocHost(&d.h_dst, ctx->dstSpan + 256));
@@ -93,13 +92,11 @@ void free_device(Device& d) {
   cudaSetDevice(d.id);
   for (auto& s : d.stream) if (s) cudaStreamSynchronize(s);
   cudaFree(d.d_src); cudaFree(d.d_dst); cudaFree(d.d_srcOff); cudaFree(d.d_dstOff); cudaFree(d.d_srcSize); cudaFree(d.d_dstCap);
-  cudaFree(d.d_result); cudaFree(d.d_info); cudaFree(d.d_lit); cudaFree(d.d_seq);
+  cudaFree(d.d_result); cudaFree(d.d_info); cudaFree(d.d_lit); cudaFree(d.d_seq); cudaFree(d.d_more); cudaFreeHost(d.h_more);
   encode_free(d.enc);
   cudaFreeHost(d.h_src); cudaFreeHost(d.h_dst); cudaFreeHost(d.h_srcOff); cudaFreeHost(d.h_dstOff); cudaFreeHost(d.h_srcSize);
   cudaFreeHost(d.h_dstCap); cudaFreeHost(d.h_result);
   for (auto& s : d.stream) if (s) cudaStreamDestroy(s);
-  if (d.forkEv) cudaEventDestroy(d.forkEv);
-  for (auto& e : d.joinEv) if (e) cudaEventDestroy(e);
 }
 
 struct Range { size_t lo, hi; };
@@ -122,6 +119,21 @@ std::vector<Range> make_subbatches(size_t n, size_t maxIn, size_t maxOut, size_t
 }
 
 enum class Op { Decompress, Compress };
+
+// Items that hold more than one data frame (DecompressMultiFrame, ZStdDecompress.cs:2096-2160): after the first pass
+// the execute stage has counted them in *more; every further pass decodes the next data frame of each of them.
+// Synchronises `st` once per pass (the count has to reach the host).  `a` covers the same items as the first pass.
+cudaError_t decode_more_passes(Device& d, DecodeArgs a, u32 slot, cudaStream_t st, int* launches) {
+  cudaError_t e;
+  while (true) {
+    a.pass++; a.more = d.d_more + slot;
+    if ((e = cudaMemsetAsync(a.more, 0, 4, st)) != cudaSuccess) return e;
+    if ((e = decode_launch(a, st, launches)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(d.h_more + slot, a.more, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    if (d.h_more[slot] == 0) return cudaSuccess;
+  }
+}
 
 struct Job {
   Op op; int level, checksum;
@@ -173,6 +185,8 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     }
   }
   cudaError_t e;
+  if (j.op == Op::Decompress)
+    for (int k = 0; k < NSTREAMS; k++) { e = cudaMemsetAsync(d.d_more + k, 0, 4, d.stream[k]); if (e) return fail("memset", e); d.h_more[k] = 0; }
   for (size_t s = 0; s < slices.size(); s++) {
     const size_t a = slices[s].lo, b = slices[s].hi, cnt = b - a;
     cudaStream_t st = d.stream[s % NSTREAMS];
@@ -191,8 +205,9 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     int nl = 0;
     if (j.op == Op::Decompress) {
       DecodeArgs ar{d.d_src, d.d_srcOff + a, d.d_srcSize + a, d.d_dst, d.d_dstOff + a, d.d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
-                    d.d_info + a, d.d_lit, d.d_seq};
+                    d.d_info + a, d.d_lit, d.d_seq, 0, d.d_more + (s % NSTREAMS)};
       e = decode_launch(ar, st, &nl);
+      if (!e) e = cudaMemcpyAsync(d.h_more + (s % NSTREAMS), d.d_more + (s % NSTREAMS), 4, cudaMemcpyDeviceToHost, st);   // cumulative per stream
     } else {
       EncodeArgs ar{d.d_src, d.d_srcOff + a, d.d_srcSize + a, d.d_dst, d.d_dstOff + a, d.d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
                     j.level, j.checksum, (u32)(s % NSTREAMS)};
@@ -208,6 +223,18 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     }
   }
   for (auto& st : d.stream) { e = cudaStreamSynchronize(st); if (e) return fail("stream sync", e); }
+  if (j.op == Op::Decompress && (d.h_more[0] | d.h_more[1] | d.h_more[2] | d.h_more[3])) {
+    // rare path: some items hold several data frames.  Everything is still resident: decode the remaining frames
+    // pass by pass over the whole sub-batch, then fetch results and output again.
+    cudaStream_t st = d.stream[0]; int nl = 0;
+    DecodeArgs ar{d.d_src, d.d_srcOff, d.d_srcSize, d.d_dst, d.d_dstOff, d.d_dstCap, d.d_result, (u32)m, 0, d.d_info, d.d_lit, d.d_seq, 0, nullptr};
+    e = decode_more_passes(d, ar, 0, st, &nl); *launches += nl;
+    if (e) return fail("multi-frame passes", e);
+    e = cudaMemcpyAsync(d.h_result, d.d_result, m * 4, cudaMemcpyDeviceToHost, st); if (e) return fail("D2H result", e);
+    const size_t outLo = d.h_dstOff[0], outHi = d.h_dstOff[m - 1] + d.h_dstCap[m - 1];
+    if (outHi > outLo) { e = cudaMemcpyAsync(dstDirect ? dstBase + outLo : d.h_dst + outLo, d.d_dst + outLo, outHi - outLo, cudaMemcpyDeviceToHost, st); if (e) return fail("D2H dst", e); }
+    e = cudaStreamSynchronize(st); if (e) return fail("stream sync", e);
+  }
   for (size_t k = 0; k < m; k++) {
     const size_t i = lo + k; const u32 r = d.h_result[k];
     j.result[i] = r;
@@ -336,28 +363,17 @@ uint32_t zstdb200_decompress(zstdb200_ctx* ctx, void* dst, uint32_t dstCapacity,
   return r;
 }
 
-// Device-resident decode: the batch is cut into slices dealt to the context's streams (forked from and joined
-// back into `stream`) so that the entropy kernels of one slice overlap the execute kernel of another.
-static int decode_device_sliced(zstdb200_ctx* ctx, Device& d, const DecodeArgs& a, cudaStream_t user, cudaEvent_t* marks) {
+// Device-resident decode: one launch sequence over the whole batch on the caller's stream (slicing a resident batch
+// over several streams was measured slower: whole-batch kernels fill the GPU better).  The count of items that
+// hold a further data frame has to reach the host, so this entry point synchronises the stream once per pass.
+static int decode_device(zstdb200_ctx* ctx, Device& d, const DecodeArgs& a, cudaStream_t user, cudaEvent_t* marks) {
   int nl = 0;
-  static const bool noSlice = getenv("ZSTDB200_NO_SLICE") != nullptr;   // profiling aid: whole-batch kernels
-  if (marks || a.n < (1u << 30) || noSlice) {   // slicing the device-resident path does not pay: whole-batch kernels fill the GPU better
-   // timed runs and small batches: one launch sequence on the caller's stream
-    CK(decode_launch(a, user, &nl, marks));
-    ctx->launches += nl;
-    return 0;
-  }
-  const u32 per = std::max<u32>(1024, (a.n + 4 * NSTREAMS - 1) / (4 * NSTREAMS));
-  CK(cudaEventRecord(d.forkEv, user));
-  for (auto& s : d.stream) CK(cudaStreamWaitEvent(s, d.forkEv, 0));
-  u32 k = 0;
-  for (u32 lo = 0; lo < a.n; lo += per, k++) {
-    DecodeArgs b = a;
-    b.src_off += lo; b.src_size += lo; b.dst_off += lo; b.dst_cap += lo; b.result += lo; b.info += lo;
-    b.n = std::min(per, a.n - lo); b.item_base = a.item_base + lo;
-    CK(decode_launch(b, d.stream[k % NSTREAMS], &nl));
-  }
-  for (int s = 0; s < NSTREAMS; s++) { CK(cudaEventRecord(d.joinEv[s], d.stream[s])); CK(cudaStreamWaitEvent(user, d.joinEv[s], 0)); }
+  DecodeArgs b = a; b.pass = 0; b.more = d.d_more;
+  CK(cudaMemsetAsync(b.more, 0, 4, user));
+  CK(decode_launch(b, user, &nl, marks));
+  CK(cudaMemcpyAsync(d.h_more, b.more, 4, cudaMemcpyDeviceToHost, user));
+  CK(cudaStreamSynchronize(user));
+  if (d.h_more[0]) CK(decode_more_passes(d, b, 0, user, &nl));
   ctx->launches += nl;
   return 0;
 }
@@ -371,8 +387,8 @@ int zstdb200_decompress_batch_device(zstdb200_ctx* ctx, int device_index, const 
   if (n > ctx->maxItems) { ctx->err = "n exceeds zstdb200_max_items"; return 1; }
   Device& d = ctx->dev[device_index];
   CK(cudaSetDevice(d.id));
-  DecodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, 0, d.d_info, d.d_lit, d.d_seq};
-  return decode_device_sliced(ctx, d, a, stream ? (cudaStream_t)stream : d.stream[0], nullptr);
+  DecodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, 0, d.d_info, d.d_lit, d.d_seq, 0, nullptr};
+  return decode_device(ctx, d, a, stream ? (cudaStream_t)stream : d.stream[0], nullptr);
 }
 
 // Same work as one launch sequence with CUDA events between the kernels: per-kernel device times for the
@@ -389,8 +405,8 @@ int zstdb200_decompress_batch_device_timed(zstdb200_ctx* ctx, int device_index, 
   cudaStream_t st = stream ? (cudaStream_t)stream : d.stream[0];
   cudaEvent_t ev[DECODE_KERNELS + 1];
   for (auto& e : ev) CK(cudaEventCreate(&e));
-  DecodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, 0, d.d_info, d.d_lit, d.d_seq};
-  if (decode_device_sliced(ctx, d, a, st, ev)) return 1;
+  DecodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, 0, d.d_info, d.d_lit, d.d_seq, 0, nullptr};
+  if (decode_device(ctx, d, a, st, ev)) return 1;
   CK(cudaStreamSynchronize(st));
   for (int k = 0; k < DECODE_KERNELS && k < max_kernels; k++) CK(cudaEventElapsedTime(&kernel_ms[k], ev[k], ev[k + 1]));
   for (auto& e : ev) cudaEventDestroy(e);

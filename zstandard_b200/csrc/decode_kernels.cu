@@ -15,9 +15,14 @@ namespace zb {
 // -----------------------------------------------------------------------------------------------
 // scratch addressing shared by the stages (see DESIGN.md "HBM layout")
 // -----------------------------------------------------------------------------------------------
-__device__ __forceinline__ u8* lit_region(const DecodeArgs& a, u32 f) { return a.lit_arena + (a.dst_off[f] & ~15ull) + 64ull * (a.item_base + f); }
+// A data frame of item f writes at dst_off[f] + out_base and may use dst_cap[f] - out_base bytes (out_base > 0 only
+// for the second and later data frames of one item); its scratch regions follow from that position, so they stay
+// inside the item's share of the arenas.
+__device__ __forceinline__ u64 frame_dst_off(const DecodeArgs& a, u32 f, const FrameInfo& fi) { return a.dst_off[f] + fi.out_base; }
+__device__ __forceinline__ u32 frame_cap(const DecodeArgs& a, u32 f, const FrameInfo& fi) { return a.dst_cap[f] - fi.out_base; }
+__device__ __forceinline__ u8* lit_region(const DecodeArgs& a, u32 f, const FrameInfo& fi) { return a.lit_arena + (frame_dst_off(a, f, fi) & ~15ull) + 64ull * (a.item_base + f); }
 __device__ __forceinline__ u64 lit_capacity(u32 cap) { return (u64)cap + 40; }
-__device__ __forceinline__ SeqRec* seq_region(const DecodeArgs& a, u32 f) { return a.seq_arena + 2 * (a.dst_off[f] / 3) + 32ull * (a.item_base + f); }
+__device__ __forceinline__ SeqRec* seq_region(const DecodeArgs& a, u32 f, const FrameInfo& fi) { return a.seq_arena + 2 * (frame_dst_off(a, f, fi) / 3) + 32ull * (a.item_base + f); }
 
 // =================================================================================================
 // k_parse
@@ -25,8 +30,14 @@ __device__ __forceinline__ SeqRec* seq_region(const DecodeArgs& a, u32 f) { retu
 __global__ void __launch_bounds__(128) k_parse(DecodeArgs a) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
-  FrameInfo fi; u32 r = 0;
-  bool go = parse_item(a.src_base + a.src_off[i], a.src_size[i], fi, &r);
+  FrameInfo fi; u32 r = 0; u32 start = 0, outBase = 0;
+  if (a.pass) {
+    // later passes only touch items whose previous data frame decoded cleanly and is followed by another one
+    const FrameInfo prev = a.info[i];
+    if ((prev.flags & FI_DONE) || prev.next_off == 0 || is_err(a.result[i])) { a.info[i].flags = FI_DONE; return; }
+    start = prev.next_off; outBase = prev.out_base + prev.decoded;
+  }
+  bool go = parse_item(a.src_base + a.src_off[i], a.src_size[i], fi, &r, start, outBase);
   a.info[i] = fi;
   if (!go) a.result[i] = r;
 }
@@ -51,7 +62,7 @@ __global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
   if (active) { fi = a.info[f]; if (fi.flags & FI_DONE) active = false; }
   if (!active) return;   // whole 4-lane group leaves together; group syncs below use gmask
   const u8* src = a.src_base + a.src_off[f]; const u32 size = a.src_size[f];
-  u8* lit = lit_region(a, f); const u64 litCap = lit_capacity(a.dst_cap[f]);
+  u8* lit = lit_region(a, f, fi); const u64 litCap = lit_capacity(frame_cap(a, f, fi));
   u16* dt = sm.table[slot]; HufBuildWk& wk = sm.wk[slot];
   u32 pos = fi.body_off, blk = 0; u64 litRun = 0;
   u32 tableLog = 0; bool haveTable = false;
@@ -67,10 +78,10 @@ __global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
       if (read_lit_hdr(bp, bsz, lh, &needs)) break;
       if (lh.type >= 2) {
         if (lh.type == 3 && !haveTable) break;                                     // dictionary_corrupted, reported by k_exec
-        bool ok = true; u32 code = ZE_corruption_detected;
+        bool ok = true;
         const u8* body = bp + lh.lhSize; u32 bodySize = lh.litCSize;
-        if (litRun + lh.litSize + 3 > litCap) { ok = false; code = ZE_dstSize_tooSmall; }
-        if (ok && lh.type == 2) {
+        const bool dry = litRun + lh.litSize + 3 > litCap;                         // cannot be stored: validate only (HUF_DRY)
+        if (lh.type == 2) {
           if (!lh.single && (lh.litSize == 0 || bodySize == 0)) ok = false;       // HufDecompress.cs:1211-1212
           u32 hdr = 0, nbSym = 0, tl = 0;
           if (ok) {
@@ -94,16 +105,18 @@ __global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
         if (ok) {
           bool good = true;
           if (lh.single) {
-            if (sub == 0) good = huf_decode_stream(body, bodySize, lit + litRun, lh.litSize, dt, tableLog, &sm.ring[lane][0]);   // HufDecompress.cs:247-264
+            if (sub == 0) good = dry ? huf_check_stream(body, bodySize, lh.litSize, dt, tableLog)
+                                     : huf_decode_stream(body, bodySize, lit + litRun, lh.litSize, dt, tableLog, &sm.ring[lane][0]);   // HufDecompress.cs:247-264
           } else {
             HufStream st;
             good = huf_split4(body, bodySize, lh.litSize, sub, st);
-            if (good) good = huf_decode_stream(st.src, st.len, lit + litRun + st.outOfs, st.count, dt, tableLog, &sm.ring[lane][0]);
+            if (good) good = dry ? huf_check_stream(st.src, st.len, st.count, dt, tableLog)
+                                 : huf_decode_stream(st.src, st.len, lit + litRun + st.outOfs, st.count, dt, tableLog, &sm.ring[lane][0]);
           }
           unsigned okmask = __ballot_sync(gmask, good);
           if ((okmask & gmask) != gmask) ok = false;
         }
-        if (!ok) { errBlock = blk; errCode = code; break; }
+        if (!ok || dry) { errBlock = blk; errCode = ok ? HUF_DRY : ZE_corruption_detected; break; }
         litRun += lh.litSize;
       }
     }
@@ -150,7 +163,7 @@ __global__ void __launch_bounds__(32) k_seq(DecodeArgs a) {
   T.space[KIND_LL] = &sm.ll[0][lane]; T.space[KIND_ML] = &sm.ml[0][lane]; T.space[KIND_OF] = &sm.of[0][lane]; T.stride = 32;
   T.defs[KIND_LL] = sm.defLL; T.defs[KIND_OF] = sm.defOF; T.defs[KIND_ML] = sm.defML;
   SeqFrameOut res;
-  seq_decode_frame(a.src_base + a.src_off[f], a.src_size[f], fi.body_off, T, seq_region(a, f), seq_capacity(a.dst_cap[f]), res, sm.llInfo, sm.mlInfo,
+  seq_decode_frame(a.src_base + a.src_off[f], a.src_size[f], fi.body_off, fi.window, T, seq_region(a, f, fi), seq_capacity(frame_cap(a, f, fi)), res, sm.llInfo, sm.mlInfo,
                    Strided<s16>{&sm.norm[0][lane], 32}, Strided<u16>{&sm.next[0][lane], 32}, &sm.ring[lane][0]);
   if (res.err_block != 0xFFFFFFFFu) {
     a.info[f].seq_err_block = res.err_block; a.info[f].seq_err_code = res.err_code; a.info[f].seq_err_index = res.err_index;
@@ -309,11 +322,11 @@ __global__ void __launch_bounds__(EXEC_THREADS, 8) k_exec(DecodeArgs a) {
   FrameInfo fi = a.info[f];
   if (fi.flags & FI_DONE) return;
   const u8* src = a.src_base + a.src_off[f]; const u32 size = a.src_size[f];
-  u8* dst = a.dst_base + a.dst_off[f]; const u64 cap = a.dst_cap[f];
-  const u8* litScratch = lit_region(a, f);
-  const SeqRec* recs = seq_region(a, f);
+  u8* dst = a.dst_base + frame_dst_off(a, f, fi); const u64 cap = frame_cap(a, f, fi);
+  const u8* litScratch = lit_region(a, f, fi);
+  const SeqRec* recs = seq_region(a, f, fi);
   u32 pos = fi.body_off, blk = 0; u64 op = 0, litRun = 0, recRun = 0;
-  bool litEntropy = false; u32 err = 0;
+  bool litEntropy = false, dry = false; u32 err = 0;
   while (true) {
     BlockHdr bh;
     err = read_block_hdr(src + pos, size - pos, bh);
@@ -334,7 +347,10 @@ __global__ void __launch_bounds__(EXEC_THREADS, 8) k_exec(DecodeArgs a) {
       if (e) { err = e; break; }
       const u8* lit; u32 rleByte = 0; bool isRle = false;
       if (lh.type >= 2) {
-        if (fi.huf_err_block == blk) { err = fi.huf_err_code; break; }             // :742 (all Huffman failures -> corruption_detected)
+        if (fi.huf_err_block == blk) {
+          if (fi.huf_err_code != HUF_DRY) { err = fi.huf_err_code; break; }        // :742 (all Huffman failures -> corruption_detected)
+          dry = true;                                                              // literals were not stored: checks only, the block must fail
+        }
         litEntropy = true; lit = litScratch + litRun; litRun += lh.litSize;
       } else if (lh.type == 0) lit = bp + lh.lhSize;
       else { lit = nullptr; isRle = true; rleByte = bp[lh.lhSize]; }
@@ -349,15 +365,16 @@ __global__ void __launch_bounds__(EXEC_THREADS, 8) k_exec(DecodeArgs a) {
         const SeqRec* r = recs + recRun; bool done = false;
         while (!done) {
           const SeqRec rec = r[lane];
-          const unsigned term = __ballot_sync(FULLMASK, rec.x == 0);
+          const unsigned term = __ballot_sync(FULLMASK, (rec.x | rec.y) == 0);
           const u32 cnt = term ? (u32)__ffs(term) - 1 : 32; done = term != 0;
-          const bool valid = lane < cnt;
-          const u32 ll = valid ? (rec.y & 0xFFFF) : 0, ml = valid ? (rec.y >> 16) : 0, off = rec.x;
+          const bool valid = lane < cnt, piece = valid && rec.x != 0;     // x == 0, y != 0 announces a split sequence (SeqRec)
+          const u32 ll = piece ? (rec.y & 0xFFFF) : 0, ml = piece ? (rec.y >> 16) : 0, off = rec.x;
+          const u32 whole = (valid && !piece) ? rec.y : 0;
           const u32 tot = ll + ml;
           const u32 incl = warp_incl_scan(tot, lane), lincl = warp_incl_scan(ll, lane);
           const u32 excl = incl - tot, mrel = excl + ll;   // group-relative output positions of literals / match
           // checks in the reference's order (:1278, :1279, :1290-1294)
-          const bool e1 = valid && (op + incl > cap);
+          const bool e1 = valid && (op + incl + whole > cap);
           const bool e2 = valid && (litPos + lincl > litSize);
           const bool e3 = valid && ((u64)off > op + mrel);
           const unsigned bad = __ballot_sync(FULLMASK, e1 | e2 | e3);
@@ -369,7 +386,7 @@ __global__ void __launch_bounds__(EXEC_THREADS, 8) k_exec(DecodeArgs a) {
           }
           u8* const g = dst + op;
           // ---- literals: short runs flattened over the lanes, long runs by the whole warp ----
-          {
+          if (!dry) {
             const bool bigL = ll >= 128;
             unsigned bigMask = __ballot_sync(FULLMASK, bigL);
             const u32 ls = bigL ? 0 : ll;
@@ -388,7 +405,7 @@ __global__ void __launch_bounds__(EXEC_THREADS, 8) k_exec(DecodeArgs a) {
           // ---- matches, in dependency rounds ----
           const bool hasM = ml > 0;
           const unsigned matchMask = __ballot_sync(FULLMASK, hasM);
-          if (matchMask) {
+          if (matchMask && !dry) {
             unsigned depMask = 0;
             {
               const i64 slo = (i64)mrel - (i64)off;                         // source range, group-relative
@@ -431,7 +448,7 @@ __global__ void __launch_bounds__(EXEC_THREADS, 8) k_exec(DecodeArgs a) {
       }
       // last literals (:1599-1605)
       const u64 lastLL = litSize - litPos;
-      if (lastLL > cap - op) { err = ZE_dstSize_tooSmall; break; }
+      if (lastLL > cap - op || dry) { err = ZE_dstSize_tooSmall; break; }
       if (isRle) warp_fill(dst + op, (u8)rleByte, (u32)lastLL, lane); else warp_copy(dst + op, lit + litPos, (u32)lastLL, lane);
       op += lastLL;
       __syncwarp();
@@ -447,13 +464,13 @@ __global__ void __launch_bounds__(EXEC_THREADS, 8) k_exec(DecodeArgs a) {
       if (size - pos < 4) err = ZE_checksum_wrong; else { trailer = pos; pos += 4; needXxh = true; }
     }
   }
-  u32 tailErr = 0;
+  u32 tailErr = 0, nextOff = 0;
   if (!err) {
     while (true) {
       u32 rem = size - pos;
       if (rem < 5) { if (rem) tailErr = ZE_srcSize_wrong; break; }
       u32 magic = ld32(src + pos);
-      if (magic == MAGIC) { tailErr = ZE_GENERIC; break; }                         // second data frame in one item: see DESIGN.md (host splits)
+      if (magic == MAGIC) { nextOff = pos; break; }                                // another data frame: next pass (:2111-2153)
       if ((magic & 0xFFFFFFF0u) != MAGIC_SKIP) { tailErr = ZE_prefix_unknown; break; }
       if (rem < 8) { tailErr = ZE_srcSize_wrong; break; }
       u32 skip = ld32(src + pos + 4) + 8u;
@@ -462,10 +479,11 @@ __global__ void __launch_bounds__(EXEC_THREADS, 8) k_exec(DecodeArgs a) {
     }
   }
   if (lane == 0) {
-    u32 res = err ? zerr(err) : (tailErr ? zerr(tailErr) : (u32)op);
-    a.result[f] = res;
-    a.info[f].trailer_off = trailer; a.info[f].decoded = (u32)op;
+    u32 res = err ? zerr(err) : (tailErr ? zerr(tailErr) : fi.out_base + (u32)op);
+    a.result[f] = res;                                                             // provisional while next_off != 0
+    a.info[f].trailer_off = trailer; a.info[f].decoded = (u32)op; a.info[f].next_off = nextOff;
     a.info[f].flags = fi.flags | (needXxh ? FI_NEED_XXH : 0);
+    if (nextOff && a.more) atomicAdd(a.more, 1u);
   }
 }
 
@@ -479,7 +497,7 @@ __global__ void __launch_bounds__(128) k_xxh(DecodeArgs a) {
   if (f >= a.n) return;
   FrameInfo fi = a.info[f];
   if (!(fi.flags & FI_NEED_XXH)) return;
-  const u8* dst = a.dst_base + a.dst_off[f];
+  const u8* dst = a.dst_base + frame_dst_off(a, f, fi);
   u64 h = xxh64_group(dst, fi.decoded, sub, gmask, lane & ~3u);
   if (sub == 0) {
     const u8* src = a.src_base + a.src_off[f];

@@ -17,6 +17,11 @@ struct DecodeArgs {
   FrameInfo* info;     // n records
   u8* lit_arena;       // decode_lit_arena_bytes()
   SeqRec* seq_arena;   // decode_seq_arena_bytes()
+  // Items that hold several data frames (ZStdDecompress.cs:2096-2160) are decoded one data frame per pass: the
+  // execute stage counts in *more the items that found another data frame behind the one it finished; the host
+  // re-launches the pipeline with pass + 1 until the count stays 0.  Later passes skip every other item.
+  u32 pass;            // 0 = first data frame of every item
+  u32* more;           // device counter, zeroed by the host before each pass (may be null: multi-frame items end after frame 1)
 };
 
 size_t decode_lit_arena_bytes(u64 max_dst_bytes, u64 max_items);

@@ -42,6 +42,9 @@ static const u32 MaxLL = 35, MaxML = 52, MaxOff = 31, LLFSELog = 9, MLFSELog = 9
 static const u32 HUF_LOG_MAX = 12;
 
 // ---- per-item record produced by the parse kernel and refined by later stages ----
+// huf_err_code value: the block's Huffman streams are well formed but its literals do not fit the frame's literal
+// scratch (the output cannot fit either): the execute stage replays the block's checks without copying.
+#define HUF_DRY 0xFFFFu
 enum : u32 { FI_CHECKSUM = 1, FI_FCS_KNOWN = 2, FI_DONE = 4 /* result[] already final, later stages skip the item */,
               FI_NEED_XXH = 8 /* set by the execute stage: verify the content checksum */ };
 struct FrameInfo {
@@ -54,7 +57,10 @@ struct FrameInfo {
   u32 seq_err_block, seq_err_code, seq_err_index;   // seq_err_index: sequences decoded before the failure; 0xFFFFFFFF = header error
   // set by the execute stage for the checksum stage
   u32 trailer_off;   // offset of the 4-byte checksum within the item
-  u32 decoded;       // bytes produced
+  u32 decoded;       // bytes produced by this data frame
+  // items holding several data frames (DecompressMultiFrame, ZStdDecompress.cs:2096-2160) take one pass per frame
+  u32 out_base;      // bytes produced by the item's earlier data frames: this frame writes at dst + out_base
+  u32 next_off;      // offset within the item of the next data frame's magic (0 = none), set by the execute stage
 };
 
 // array view with a stride (bank-interleaved per-lane arrays in shared memory)

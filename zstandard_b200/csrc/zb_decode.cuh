@@ -12,9 +12,12 @@
 namespace zb {
 
 // 8-byte sequence record consumed by the execute stage.
-//   x = offset (>= 1 for a match; 0 marks the end of a block's records)
+//   x = offset (>= 1 for a match)
 //   y = litLength | matchLength << 16       (both < 65536; longer ones are split into several records,
 //                                            a literals-only piece has matchLength 0 and offset 1)
+//   x == 0, y == 0 : end of a block's records
+//   x == 0, y != 0 : announces a split sequence: y = its litLength + matchLength, so that the execute stage can
+//                    make the reference's whole-sequence capacity check (:1278) before any check of the pieces
 struct SeqRec { u32 x, y; };
 
 // Capacity rule shared with the host side: records for a frame whose output capacity is `cap` bytes.
@@ -36,6 +39,7 @@ struct SeqFrameOut {
 // slow path of the record writer: lengths that do not fit 16 bits are split (ZStdDecompress.cs allows
 // litLength <= 131071 and matchLength <= 131074)
 ZB_HD void seq_emit_long(SeqRec* out, u64& n, u64 cap, u32 off, u32 ll, u32 ml) {
+  if (n < cap) { out[n].x = 0; out[n].y = ll + ml; } n++;
   while (ll > 65535) { if (n < cap) { out[n].x = 1; out[n].y = 65535; } n++; ll -= 65535; }
   while (ml > 65535) { if (n < cap) { out[n].x = off; out[n].y = ll | (65535u << 16); } n++; ll = 0; ml -= 65535; }
   if (n < cap) { out[n].x = off; out[n].y = ll | (ml << 16); }
@@ -62,13 +66,62 @@ ZB_HD u32 rep_resolve(u32& rep0, u32& rep1, u32& rep2, u32 ofBits, u32 ofv, u32 
   return offset;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Over-read emulation.  The reference reads its backward bitstream through a 4-byte container
+// (BitStream.cs:322-489, size_t = UInt32).  A sequence whose value bits reach below the stream start is not
+// rejected on the spot: the reads return whatever the container shifts produce (shift counts are taken mod 32),
+// the sequence is executed, and only the next loop test (:1582) sees the overflow — never, if it was the block's
+// last sequence.  To give the same verdicts and bytes, the careful loop recomputes such a sequence's values with
+// the container arithmetic below.  The container state at a sequence's start follows from the unread-bit count P
+// alone, because the loop test has just reloaded: bitsConsumed is normalised to < 8 unless the container already
+// sits on the stream's first bytes.
+// ---------------------------------------------------------------------------------------------------
+struct RefBits {
+  const u8* s; u32 n;   // the stream
+  i32 k;                // container = bytes [k, k+4) of the stream
+  u32 bc, C;            // bitsConsumed, bitContainer
+};
+ZB_HD void refbits_load(RefBits& b) {
+  if (b.n >= 4) { b.C = ld32(b.s + b.k); return; }
+  b.C = b.s[0]; if (b.n >= 2) b.C |= (u32)b.s[1] << 8; if (b.n >= 3) b.C |= (u32)b.s[2] << 16;       // BitStream.cs:343-367
+}
+ZB_HD void refbits_at(RefBits& b, const u8* s, u32 n, i32 P) {                  // state right after a reload, P >= 0
+  b.s = s; b.n = n;
+  const i32 bcn = (8 - (P & 7)) & 7, above = P - 32 + bcn;                        // bits above a normalised container
+  if (n >= 4 && above >= 0) { b.k = above >> 3; b.bc = (u32)bcn; } else { b.k = 0; b.bc = (u32)(32 - P); }
+  refbits_load(b);
+}
+ZB_HD u32 refbits_read_fast(RefBits& b, u32 nb) { u32 v = (b.C << (b.bc & 31)) >> ((32 - nb) & 31); b.bc += nb; return v; }   // :445-451
+ZB_HD void refbits_reload(RefBits& b) {                                          // BitStream.cs:458-489
+  if (b.bc > 32 || b.k == 0) return;
+  u32 nb = b.bc >> 3;
+  if (b.k >= 4 || (i32)nb <= b.k) { b.k -= (i32)nb; b.bc -= nb * 8; } else { b.bc -= (u32)b.k * 8; b.k = 0; }
+  refbits_load(b);
+}
+// value bits of one sequence in the reference's read order and reload schedule (DecodeSequence :1487-1545, MEM_32bits)
+ZB_HD void seq_values_ref32(const u8* s, u32 n, i32 P, bool longOffsets, u32 ofBits, u32 mlBits, u32 llBits, u32& ofv, u32& mlv, u32& llv) {
+  RefBits b; refbits_at(b, s, n, P);
+  ofv = 0;
+  if (ofBits) {
+    if (longOffsets && ofBits >= 25) {                                             // :1494-1501
+      const u32 room = 32 - b.bc, extra = ofBits - (ofBits < room ? ofBits : room);
+      ofv = refbits_read_fast(b, ofBits - extra) << (extra & 31);
+      refbits_reload(b);
+      if (extra) ofv += refbits_read_fast(b, extra);
+    } else { ofv = refbits_read_fast(b, ofBits); refbits_reload(b); }              // :1504-1506
+  }
+  mlv = mlBits ? refbits_read_fast(b, mlBits) : 0;                                 // :1534
+  if (mlBits + llBits >= 20) refbits_reload(b);                                    // :1536 (25 - 5)
+  llv = llBits ? refbits_read_fast(b, llBits) : 0;                                 // :1542
+}
+
 // Walks the frame at item `src` (size bytes, first block header at body_off) and decodes every compressed
 // block's sequences.  Stops silently at structural errors that the execute stage will report itself from the
 // same headers; records entropy-level failures in `res`.
 // llInfo/mlInfo: per-symbol base | extra bits << 24 (ll_info/ml_info); norm/symbolNext: >= 53 entries of per-thread scratch each;
 // ringMem: ZB_RING_WORDS words of per-thread bitstream read-ahead (BitRing), 16-byte aligned.
 template <class NormT, class NextT>
-ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, SeqTableSet& T, SeqRec* out, u64 cap, SeqFrameOut& res,
+ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, SeqTableSet& T, SeqRec* out, u64 cap, SeqFrameOut& res,
                             const u32* llInfo, const u32* mlInfo, NormT norm, NextT symbolNext, u32* ringMem) {
   res.err_block = 0xFFFFFFFFu; res.err_code = 0; res.err_index = 0;
   u32 pos = body_off, blk = 0;
@@ -165,12 +218,12 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, SeqTableSet& 
             const u32 nLL = cell_nb(lLL), nML = cell_nb(lML), nOF = cell_nb(lOF);
             const u32 valBits = ofBits + mlBits + llBits, stBits = nLL + nML + nOF;
             u64 w = w0;
-            const u32 ofv = top_bits(w, ofBits); w <<= ofBits;
-            const u32 mlv = top_bits(w, mlBits); w <<= mlBits;
-            const u32 llv = top_bits(w, llBits); w <<= llBits;
+            u32 ofv = top_bits(w, ofBits); w <<= ofBits;
+            u32 mlv = top_bits(w, mlBits); w <<= mlBits;
+            u32 llv = top_bits(w, llBits); w <<= llBits;
             const i32 Pv = P - (i32)valBits;
-            if (Pv < 0) { bad = true; break; }     // values came from beyond the stream start (DESIGN.md "over-read")
-            if (valBits + stBits > 64) w = bc_window64(c, Pv);                     // rare: more than 64 bits in one sequence
+            if (Pv < 0) seq_values_ref32(sp + hdr, ssz - hdr, P, window > (1ull << 25), ofBits, mlBits, llBits, ofv, mlv, llv);   // over-read: the reference's container garbage
+            else if (valBits + stBits > 64) w = bc_window64(c, Pv);                // rare: more than 64 bits in one sequence
             const u32 offset = rep_resolve(rep0, rep1, rep2, ofBits, ofv, llSym);
             const u32 ml = (iML & 0xFFFFFF) + mlv, ll = (iLL & 0xFFFFFF) + llv;
             if ((ll | ml) <= 65535) { if (n < cap) { out[n].x = offset; out[n].y = ll | (ml << 16); } n++; }
@@ -264,6 +317,21 @@ ZB_HD bool huf_decode_stream(const u8* src, u32 len, u8* out, u32 count, const u
     u64 w = bc_window64(c, P);
     u32 cell = dt[(u32)(w >> sh)];
     *out++ = (u8)cell; P -= (i32)(cell >> 8); left--;
+  }
+  return P == 0;
+}
+
+// Validation without output: same verdict as huf_decode_stream.  Used when a block's literals cannot fit the
+// frame's literal scratch — the frame is then certain to fail, but whether with corruption_detected (here) or with
+// the execute stage's dstSize_tooSmall depends on whether the streams are well formed (HufDecompress.cs:350-353).
+ZB_HD bool huf_check_stream(const u8* src, u32 len, u32 count, const u16* dt, u32 tableLog) {
+  BitCursor c;
+  if (!bc_init(c, src, len)) return false;
+  i32 P = c.P;
+  const u32 sh = 64 - tableLog;
+  for (u32 left = count; left; left--) {
+    if (P < 0) return false;
+    P -= (i32)(dt[(u32)(bc_window64(c, P) >> sh)] >> 8);
   }
   return P == 0;
 }

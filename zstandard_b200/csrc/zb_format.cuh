@@ -14,14 +14,16 @@ namespace zb {
 // =====================================================================================================
 // Outcome: returns true when a data frame was found and its header is valid (fi filled, later stages run);
 // returns false when the item's result is already final (*result set).
-ZB_HD bool parse_item(const u8* src, u32 size, FrameInfo& fi, u32* result) {
+// start / out_base: where in the item to look and how many bytes its earlier data frames produced (0, 0 on the
+// first pass; the execute stage's next_off and running total on later passes of a multi-frame item).
+ZB_HD bool parse_item(const u8* src, u32 size, FrameInfo& fi, u32* result, u32 start = 0, u32 out_base = 0) {
   fi.flags = 0; fi.body_off = 0; fi.fcs = 0; fi.window = 0;
   fi.huf_err_block = 0xFFFFFFFFu; fi.huf_err_code = 0; fi.seq_err_block = 0xFFFFFFFFu; fi.seq_err_code = 0; fi.seq_err_index = 0;
-  fi.trailer_off = 0; fi.decoded = 0;
-  u32 pos = 0;
+  fi.trailer_off = 0; fi.decoded = 0; fi.out_base = out_base; fi.next_off = 0;
+  u32 pos = start;
   while (true) {
     u32 rem = size - pos;
-    if (rem < 5) { *result = rem ? zerr(ZE_srcSize_wrong) : 0; fi.flags = FI_DONE; return false; }   // :2111, :2156
+    if (rem < 5) { *result = rem ? zerr(ZE_srcSize_wrong) : out_base; fi.flags = FI_DONE; return false; }   // :2111, :2156
     u32 magic = ld32(src + pos);
     if (magic == MAGIC) break;
     if ((magic & 0xFFFFFFF0u) != MAGIC_SKIP) { *result = zerr(ZE_prefix_unknown); fi.flags = FI_DONE; return false; }
