@@ -60,8 +60,10 @@ int zstdb200_decompress_batch(zstdb200_ctx* ctx, const void* const* src, const u
  * All pointers are device pointers on device `devices[device_index]`; item i is
  * src_base[src_off[i] .. +src_size[i]) -> dst_base[dst_off[i] .. +dst_cap[i]).  Requirements: dst_off is
  * non-decreasing with dst_off[i] + dst_cap[i] <= dst_off[i+1]; dst_off[n-1] + dst_cap[n-1] <= max_batch_bytes;
- * n <= zstdb200_max_items(ctx).  Work is enqueued on `stream` (a cudaStream_t, NULL = the context's stream) and
- * the call returns without synchronising. */
+ * n <= zstdb200_max_items(ctx).  Work is enqueued on `stream` (a cudaStream_t, NULL = the context's stream).
+ * Items that hold several data frames (DecompressMultiFrame, ZStdDecompress.cs:2096-2160) take one pass of the
+ * kernels per data frame; the count of such items has to reach the host, so this call synchronises `stream`
+ * once per pass (once in total when every item holds a single data frame) before it returns. */
 int zstdb200_decompress_batch_device(zstdb200_ctx* ctx, int device_index,
                                      const void* src_base, const uint64_t* src_off, const uint32_t* src_size,
                                      void* dst_base, const uint64_t* dst_off, const uint32_t* dst_cap,
