@@ -27,8 +27,17 @@ using namespace zb;
 
 namespace {
 
-constexpr int NSTREAMS = 4;
-constexpr size_t SLICE_BYTES = 48u << 20;   // uncompressed bytes per slice (several slices per stream per GiB)
+constexpr int NSTREAMS = 8;
+static_assert(NSTREAMS <= ENC_STREAM_PARTS, "one encoder slot partition per stream");
+constexpr size_t SLICE_BYTES_DEFAULT = 32u << 20;   // uncompressed bytes per slice (several slices per stream per GiB)
+
+// tuning aids (not part of the ABI): ZSTDB200_STREAMS = streams actually used (1..NSTREAMS), ZSTDB200_SLICE_MB
+int env_int(const char* name, int dflt, int lo, int hi) {
+  const char* v = getenv(name);
+  if (!v || !*v) return dflt;
+  int x = atoi(v);
+  return x < lo ? lo : (x > hi ? hi : x);
+}
 
 struct Device {
   int id = 0;
@@ -175,6 +184,8 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     in += align_up(j.srcSize[i], 16); out += align_up(j.dstCap[i], 16);
   }
   // ---- slices ----
+  static const int nStreams = env_int("ZSTDB200_STREAMS", NSTREAMS, 1, NSTREAMS);
+  static const size_t SLICE_BYTES = (size_t)env_int("ZSTDB200_SLICE_MB", (int)(SLICE_BYTES_DEFAULT >> 20), 1, 4096) << 20;
   std::vector<Range> slices;
   {
     size_t a = 0;
@@ -189,7 +200,7 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     for (int k = 0; k < NSTREAMS; k++) { e = cudaMemsetAsync(d.d_more + k, 0, 4, d.stream[k]); if (e) return fail("memset", e); d.h_more[k] = 0; }
   for (size_t s = 0; s < slices.size(); s++) {
     const size_t a = slices[s].lo, b = slices[s].hi, cnt = b - a;
-    cudaStream_t st = d.stream[s % NSTREAMS];
+    cudaStream_t st = d.stream[s % nStreams];
     // input bytes of the slice
     const size_t inLo = d.h_srcOff[a], inHi = d.h_srcOff[b - 1] + d.h_srcSize[b - 1];
     if (srcDirect) {
@@ -205,12 +216,12 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     int nl = 0;
     if (j.op == Op::Decompress) {
       DecodeArgs ar{d.d_src, d.d_srcOff + a, d.d_srcSize + a, d.d_dst, d.d_dstOff + a, d.d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
-                    d.d_info + a, d.d_lit, d.d_seq, 0, d.d_more + (s % NSTREAMS)};
+                    d.d_info + a, d.d_lit, d.d_seq, 0, d.d_more + (s % nStreams)};
       e = decode_launch(ar, st, &nl);
-      if (!e) e = cudaMemcpyAsync(d.h_more + (s % NSTREAMS), d.d_more + (s % NSTREAMS), 4, cudaMemcpyDeviceToHost, st);   // cumulative per stream
+      if (!e) e = cudaMemcpyAsync(d.h_more + (s % nStreams), d.d_more + (s % nStreams), 4, cudaMemcpyDeviceToHost, st);   // cumulative per stream
     } else {
       EncodeArgs ar{d.d_src, d.d_srcOff + a, d.d_srcSize + a, d.d_dst, d.d_dstOff + a, d.d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
-                    j.level, j.checksum, (u32)(s % NSTREAMS)};
+                    j.level, j.checksum, (u32)(s % nStreams)};
       e = encode_launch(ar, d.enc, st, &nl);
     }
     *launches += nl;
@@ -223,7 +234,9 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     }
   }
   for (auto& st : d.stream) { e = cudaStreamSynchronize(st); if (e) return fail("stream sync", e); }
-  if (j.op == Op::Decompress && (d.h_more[0] | d.h_more[1] | d.h_more[2] | d.h_more[3])) {
+  u32 anyMore = 0;
+  for (int k = 0; k < NSTREAMS; k++) anyMore |= d.h_more[k];
+  if (j.op == Op::Decompress && anyMore) {
     // rare path: some items hold several data frames.  Everything is still resident: decode the remaining frames
     // pass by pass over the whole sub-batch, then fetch results and output again.
     cudaStream_t st = d.stream[0]; int nl = 0;
@@ -445,7 +458,7 @@ int zstdb200_compress_batch_device(zstdb200_ctx* ctx, int device_index, int leve
   if (n > ctx->maxItems) { ctx->err = "n exceeds zstdb200_max_items"; return 1; }
   Device& d = ctx->dev[device_index];
   CK(cudaSetDevice(d.id));
-  EncodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, 0, level, checksum, 0};
+  EncodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, 0, level, checksum, ENC_EXCLUSIVE};
   int nl = 0;
   CK(encode_launch(a, d.enc, stream ? (cudaStream_t)stream : d.stream[0], &nl));
   ctx->launches += nl;

@@ -233,35 +233,83 @@ __device__ __forceinline__ u32 warp_upper_bound(u32 incl, u32 x) {
   return j & 31;
 }
 
-// Flattened copy of many short runs, one output byte per lane and row, U rows in flight per pass so that the U
-// shuffle binary searches and the U loads overlap instead of serialising on their latencies.  Run of lane j
-// covers flattened indices [incl_j - len_j, incl_j); its bytes go to g + dpos_j + k and come from
-// (src ? src + spos_j + k : g + dpos_j + k - spos_j)  — i.e. spos is a match offset when src is null.
+// Flattened copy of many short runs in units of one 4-byte-aligned destination word: run of lane j writes len_j
+// bytes at g + dpos_j, i.e. touches units_j = ((g + dpos_j) % 4 + len_j + 3) / 4 aligned words (the first and the
+// last possibly in part); uincl/uexcl are the inclusive/exclusive warp prefix sums of units_j.  One unit per
+// lane and row, U rows in flight per pass so that the U shuffle binary searches and the U loads overlap instead
+// of serialising on their latencies.  Source of run j: src + spos_j.  The source word is assembled from the (at
+// most two) aligned words that hold a byte the unit needs — nothing outside [source, source + len_j) rounded to
+// words is touched.  (Used for literal runs; the same scheme for matches measured slower than flat_copy_m4.)
 template <int U>
-__device__ __forceinline__ void flat_copy(u8* g, const u8* src, bool fill, u8 fillByte, u32 total, u32 incl, u32 excl, u32 dpos, u32 spos, u32 lane) {
-  for (u32 t0 = 0; t0 < total; t0 += 32 * U) {
-    u32 t[U], j[U], dj[U], ej[U], sj[U]; u8 v[U];
+__device__ __forceinline__ void flat_copy_w(u8* g, const u8* src, u32 totalUnits, u32 uincl, u32 uexcl, u32 dpos, u32 spos, u32 len, u32 lane) {
+  for (u32 t0 = 0; t0 < totalUnits; t0 += 32 * U) {
+    u32 t[U], j[U], dj[U], ej[U], sj[U], nj[U], v[U], lo[U], hi[U];
 #pragma unroll
     for (int k = 0; k < U; k++) { t[k] = t0 + 32 * k + lane; j[k] = 0; }
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) {
 #pragma unroll
-      for (int k = 0; k < U; k++) { const u32 x = __shfl_sync(FULLMASK, incl, (j[k] + s - 1) & 31); if (x <= t[k]) j[k] += s; }
+      for (int k = 0; k < U; k++) { const u32 x = __shfl_sync(FULLMASK, uincl, (j[k] + s - 1) & 31); if (x <= t[k]) j[k] += s; }
     }
 #pragma unroll
     for (int k = 0; k < U; k++) {
       j[k] &= 31;
-      dj[k] = __shfl_sync(FULLMASK, dpos, j[k]); ej[k] = __shfl_sync(FULLMASK, excl, j[k]); sj[k] = __shfl_sync(FULLMASK, spos, j[k]);
+      dj[k] = __shfl_sync(FULLMASK, dpos, j[k]); ej[k] = __shfl_sync(FULLMASK, uexcl, j[k]);
+      sj[k] = __shfl_sync(FULLMASK, spos, j[k]); nj[k] = __shfl_sync(FULLMASK, len, j[k]);
     }
 #pragma unroll
     for (int k = 0; k < U; k++) {
-      v[k] = fillByte;
-      if (t[k] < total && !fill) { const u32 rel = t[k] - ej[k]; v[k] = src ? src[sj[k] + rel] : *(g + dj[k] + rel - (size_t)sj[k]); }   // a match source may lie before the group
+      v[k] = 0; lo[k] = 0; hi[k] = 0;
+      if (t[k] < totalUnits) {
+        u8* const d0 = g + dj[k];                                         // first byte of the run
+        const u32 word = ((u32)(uintptr_t)d0 & 3) + 0;                    // its position within its aligned word
+        const i32 rel = (i32)(4 * (t[k] - ej[k])) - (i32)word;           // run-relative position of this unit's word (-3..)
+        lo[k] = rel < 0 ? (u32)-rel : 0;                                  // bytes [lo, hi) of the word belong to the run
+        const u32 left = nj[k] - (u32)(rel + (i32)lo[k]);
+        hi[k] = lo[k] + left < 4 ? lo[k] + left : 4;
+        const u8* sp = src + sj[k] + rel;                                 // source of the word's byte 0
+        const u32* w = (const u32*)((uintptr_t)sp & ~(uintptr_t)3); const u32 sb = (u32)(uintptr_t)sp & 3;
+        const u32 a0 = (sb + lo[k] < 4) ? w[0] : 0, a1 = (sb + hi[k] > 4) ? w[1] : 0;
+        v[k] = __funnelshift_r(a0, a1, sb * 8);
+      }
     }
 #pragma unroll
-    for (int k = 0; k < U; k++) if (t[k] < total) g[dj[k] + (t[k] - ej[k])] = v[k];
+    for (int k = 0; k < U; k++) if (t[k] < totalUnits) {
+      u8* d = (u8*)(((uintptr_t)(g + dj[k]) & ~(uintptr_t)3) + 4 * (size_t)(t[k] - ej[k]));
+      if (hi[k] - lo[k] == 4) *(u32*)d = v[k];
+      else {
+        if (lo[k] == 0) d[0] = (u8)v[k];
+        if (lo[k] <= 1 && hi[k] > 1) d[1] = (u8)(v[k] >> 8);
+        if (lo[k] <= 2 && hi[k] > 2) d[2] = (u8)(v[k] >> 16);
+        if (hi[k] == 4) d[3] = (u8)(v[k] >> 24);
+      }
+    }
   }
 }
+// RLE literals: the same units, filled with one byte value
+template <int U>
+__device__ __forceinline__ void flat_fill_w(u8* g, u32 fillWord, u32 totalUnits, u32 uincl, u32 uexcl, u32 dpos, u32 len, u32 lane) {
+  for (u32 t0 = 0; t0 < totalUnits; t0 += 32 * U) {
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      const u32 t = t0 + 32 * k + lane; u32 j = 0;
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) { const u32 x = __shfl_sync(FULLMASK, uincl, (j + s - 1) & 31); if (x <= t) j += s; }
+      j &= 31;
+      const u32 dj = __shfl_sync(FULLMASK, dpos, j), ej = __shfl_sync(FULLMASK, uexcl, j), nj = __shfl_sync(FULLMASK, len, j);
+      if (t < totalUnits) {
+        u8* const d0 = g + dj;
+        const i32 rel = (i32)(4 * (t - ej)) - (i32)((u32)(uintptr_t)d0 & 3);
+        const u32 lo = rel < 0 ? (u32)-rel : 0, left = nj - (u32)(rel + (i32)lo), hi = lo + left < 4 ? lo + left : 4;
+        u8* d = (u8*)(((uintptr_t)d0 & ~(uintptr_t)3) + 4 * (size_t)(t - ej));
+        if (hi - lo == 4) *(u32*)d = fillWord;
+        else for (u32 b = lo; b < hi; b++) d[b] = (u8)fillWord;
+      }
+    }
+  }
+}
+// units of a run of len bytes starting at p (0 for an empty run)
+__device__ __forceinline__ u32 word_units(const u8* p, u32 len) { return len ? (((u32)(uintptr_t)p & 3) + len + 3) >> 2 : 0; }
 
 // Flattened copy of many short non-overlapping matches in units of 4 bytes: run of lane j has len_j bytes
 // (off_j >= len_j), i.e. (len_j + 3) / 4 units; unit u moves bytes [4u, min(4u + 4, len_j)) from g + mrel_j - off_j.
@@ -315,7 +363,7 @@ __device__ __forceinline__ void warp_match(u8* d, u32 off, u32 len, u32 lane) {
   for (u32 i = lane; i < len; i += 32) { d[i] = s[r]; r += stepm; if (r >= off) r -= off; }
 }
 
-__global__ void __launch_bounds__(EXEC_THREADS, 8) k_exec(DecodeArgs a) {
+__global__ void __launch_bounds__(EXEC_THREADS, 10) k_exec(DecodeArgs a) {
   const u32 lane = threadIdx.x & 31;
   const u32 f = (blockIdx.x * EXEC_THREADS + threadIdx.x) >> 5;
   if (f >= a.n) return;
@@ -365,6 +413,7 @@ __global__ void __launch_bounds__(EXEC_THREADS, 8) k_exec(DecodeArgs a) {
         const SeqRec* r = recs + recRun; bool done = false;
         while (!done) {
           const SeqRec rec = r[lane];
+          if (lane < 2) prefetch_line(r + 32 + 16 * lane);          // next group's 256 bytes (arena slack covers the over-reach)
           const unsigned term = __ballot_sync(FULLMASK, (rec.x | rec.y) == 0);
           const u32 cnt = term ? (u32)__ffs(term) - 1 : 32; done = term != 0;
           const bool valid = lane < cnt, piece = valid && rec.x != 0;     // x == 0, y != 0 announces a split sequence (SeqRec)
@@ -390,11 +439,13 @@ __global__ void __launch_bounds__(EXEC_THREADS, 8) k_exec(DecodeArgs a) {
             const bool bigL = ll >= 128;
             unsigned bigMask = __ballot_sync(FULLMASK, bigL);
             const u32 ls = bigL ? 0 : ll;
-            const u32 sincl = warp_incl_scan(ls, lane), sexcl = sincl - ls;
+            const u32 lu = word_units(g + excl, ls);
+            const u32 sincl = warp_incl_scan(lu, lane), sexcl = sincl - lu;
             const u32 Ls = __shfl_sync(FULLMASK, sincl, 31);
             const u32 lsrc = lincl - ll;                    // literal source position of this lane, relative to litPos
-            if (Ls > 32) flat_copy<2>(g, isRle ? g : lit + litPos, isRle, (u8)rleByte, Ls, sincl, sexcl, excl, lsrc, lane);
-            else if (Ls) flat_copy<1>(g, isRle ? g : lit + litPos, isRle, (u8)rleByte, Ls, sincl, sexcl, excl, lsrc, lane);
+            if (isRle) { if (Ls) flat_fill_w<1>(g, rleByte * 0x01010101u, Ls, sincl, sexcl, excl, ls, lane); }
+            else if (Ls > 32) flat_copy_w<2>(g, lit + litPos, Ls, sincl, sexcl, excl, lsrc, ls, lane);
+            else if (Ls) flat_copy_w<1>(g, lit + litPos, Ls, sincl, sexcl, excl, lsrc, ls, lane);
             while (bigMask) {
               const u32 j = (u32)__ffs(bigMask) - 1; bigMask &= bigMask - 1;
               const u32 dj = __shfl_sync(FULLMASK, excl, j), nj = __shfl_sync(FULLMASK, ll, j), lj = __shfl_sync(FULLMASK, lsrc, j);

@@ -454,8 +454,12 @@ __global__ void __launch_bounds__(128) k_enc_xxh(EncodeArgs a) {
 
 size_t encode_bound(size_t srcSize) { return srcSize + (srcSize >> 8) + 32 + 3 * ((srcSize >> 17) + 1); }
 
-static constexpr u32 kSlotsPerStream = 148 * 16;   // resident entropy-stage warps per stream partition
-static constexpr u32 kStreamSlots = 4;
+// Entropy-stage work areas ("slots", one per resident warp).  A launch that owns the context (device-pointer path)
+// takes up to kSlotsExclusive from the start of the pool; slices of a host batch that run concurrently on
+// different streams each get one of ENC_STREAM_PARTS equal partitions.
+static constexpr u32 kPoolSlots = 148 * 16 * 4;
+static constexpr u32 kSlotsExclusive = 148 * 16;
+static constexpr u32 kSlotsPerPart = kPoolSlots / ENC_STREAM_PARTS;
 
 cudaError_t encode_alloc(EncodeScratch& s, size_t maxBatchBytes, size_t maxItems) {
   s = EncodeScratch();
@@ -474,7 +478,7 @@ static cudaError_t encode_lazy_alloc(EncodeScratch& s) {
   if ((e = cudaMalloc(&s.lit, B + 64 * N + 256)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&s.seq, (B / 4 + 64 * ((B >> 17) + 1) + 128 * N + 64) * 8)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&s.meta, ((B >> 17) + N + 8) * sizeof(BlockMeta))) != cudaSuccess) return e;
-  if ((e = cudaMalloc(&s.slots, (size_t)kSlotsPerStream * kStreamSlots * slot_bytes())) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&s.slots, (size_t)kPoolSlots * slot_bytes())) != cudaSuccess) return e;
   int dev = 0; cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&s.sms, cudaDevAttrMultiProcessorCount, dev);
   cudaFuncSetAttribute(k_enc_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -497,10 +501,12 @@ cudaError_t encode_launch(const EncodeArgs& a, EncodeScratch& s, cudaStream_t st
   if (timing) { for (auto& x : ev) cudaEventCreate(&x); cudaEventRecord(ev[0], st); }
   if (dfast) k_enc_match<true><<<grid, 32, smem, st>>>(a, s, hlogL, hlogS, mls);
   else k_enc_match<false><<<grid, 32, smem, st>>>(a, s, hlogL, hlogS, mls);
-  const u32 part = a.stream_slot % kStreamSlots;
-  const u32 slots = a.n < kSlotsPerStream ? a.n : kSlotsPerStream;
+  const bool exclusive = a.stream_slot == ENC_EXCLUSIVE;
+  const u32 slot0 = exclusive ? 0 : (a.stream_slot % ENC_STREAM_PARTS) * kSlotsPerPart;
+  const u32 maxSlots = exclusive ? kSlotsExclusive : kSlotsPerPart;
+  const u32 slots = a.n < maxSlots ? a.n : maxSlots;
   if (timing) cudaEventRecord(ev[1], st);
-  k_enc_entropy<<<(slots + 3) / 4, 128, 0, st>>>(a, s, part * kSlotsPerStream, slots);
+  k_enc_entropy<<<(slots + 3) / 4, 128, 0, st>>>(a, s, slot0, slots);
   if (timing) {
     cudaEventRecord(ev[2], st); cudaEventSynchronize(ev[2]);
     float m1 = 0, m2 = 0; cudaEventElapsedTime(&m1, ev[0], ev[1]); cudaEventElapsedTime(&m2, ev[1], ev[2]);

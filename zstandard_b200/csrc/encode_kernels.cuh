@@ -9,13 +9,17 @@ namespace zb {
 // dst_base[dst_off[i] ..] (at most dst_cap[i] bytes); result[i] = frame size or an error code.
 // src_off must be non-decreasing with src_off[i] + src_size[i] <= src_off[i+1] (the match stage's scratch is
 // addressed from it) and the source buffer must be readable up to 8 bytes past its last item.
+#define ENC_STREAM_PARTS 8
+#define ENC_EXCLUSIVE 0xFFFFFFFFu
+
 struct EncodeArgs {
   const u8* src_base; const u64* src_off; const u32* src_size;
   u8* dst_base; const u64* dst_off; const u32* dst_cap;
   u32* result; u32 n;
   u32 item_base;     // index of item 0 within the scratch numbering (slices of one batch share the arenas)
   int level, checksum;
-  u32 stream_slot;   // which quarter of the entropy stage's slot arena to use (launches on different streams run concurrently)
+  u32 stream_slot;   // partition (0..ENC_STREAM_PARTS-1) of the entropy stage's slot pool for launches that run concurrently
+                     // on different streams, or ENC_EXCLUSIVE when the launch has the context to itself
 };
 
 // Per-device scratch owned by the context (allocated on the first compress call).
