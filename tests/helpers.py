@@ -187,3 +187,54 @@ def multi_frame_items(seed=11, count=40):
             mutated = bytearray(blob); mutated[blob.index(first) + len(first) - 2] ^= 0x10
             items.append((bytes(mutated), total))
     return items
+
+
+def huf12_frame(n=700, four_streams=True, seed=5, raw_prefix=0):
+    """Hand-made frame whose Huffman table has tableLog 12 — legal for the reference (HufDecompress.cs:128, ReadStats
+    EntropyCommon.cs:198-269) although no encoder emits it.  Direct 4-bit weights 11,11,11,10,9,...,2,1 for symbols
+    0..12, the 14th symbol's weight (1) is implied; literals only, no sequences.  Returns (frame, plaintext)."""
+    rng = random.Random(seed)
+    weights = [11, 11, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 1]
+    # canonical positions as the decoder lays them out: ascending weight, ascending symbol within a weight
+    start, pos = {}, 0
+    for w in range(1, 12):
+        for sym, ws in enumerate(weights):
+            if ws == w:
+                start[sym] = pos
+                pos += 1 << (w - 1)
+    assert pos == 4096
+    code = {sym: (start[sym] >> (w - 1), 13 - w) for sym, w in enumerate(weights)}      # (value, nbBits)
+    data = bytes(rng.choice([0, 0, 0, 1, 1, 2, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13]) for _ in range(n))
+
+    def stream(symbols):
+        acc, nbits = 0, 0
+        for sym in reversed(symbols):                 # the decoder reads backwards: last written is first read
+            v, nb = code[sym]
+            acc |= v << nbits
+            nbits += nb
+        acc |= 1 << nbits                             # end mark
+        return acc.to_bytes(nbits // 8 + 1, "little")
+
+    if four_streams:
+        seg = (n + 3) // 4
+        parts = [stream(data[0:seg]), stream(data[seg:2 * seg]), stream(data[2 * seg:3 * seg]), stream(data[3 * seg:])]
+        body = b"".join(len(p).to_bytes(2, "little") for p in parts[:3]) + b"".join(parts)
+    else:
+        body = stream(data)
+    nib = weights[:13] + [0]
+    hdr = bytes([127 + 13]) + bytes((nib[i] << 4) | nib[i + 1] for i in range(0, 14, 2))
+    comp = hdr + body
+    assert n < 1024 and len(comp) < 1024
+    lhc = 2 | ((1 if four_streams else 0) << 2) | (n << 4) | (len(comp) << 14)
+    block = lhc.to_bytes(3, "little") + comp + b"\x00"                                  # + "0 sequences"
+    blocks = b""
+    plain = b""
+    if raw_prefix:                                                                      # a raw block first: table built in block 1
+        pre = bytes(rng.randrange(256) for _ in range(raw_prefix))
+        blocks += ((raw_prefix << 3) | 0).to_bytes(3, "little") + pre
+        plain += pre
+    blocks += ((len(block) << 3) | (2 << 1) | 1).to_bytes(3, "little") + block
+    plain += data
+    total = len(plain)
+    frame = b"\x28\xb5\x2f\xfd" + bytes([0x60]) + (total - 256).to_bytes(2, "little") + blocks    # single segment, 2-byte FCS
+    return frame, plain

@@ -75,6 +75,26 @@ def test_edge_cases(gpu_ctx, oracle):
     del bad_sum
 
 
+def test_huffman_table_log_12(gpu_ctx, oracle):
+    """Log-12 Huffman tables (legal, never emitted by encoders) are folded into the kernels' 2^11-cell tables."""
+    items = []
+    for four in (True, False):
+        for n in (300, 700, 1001):
+            for prefix in (0, 50):
+                frame, plain = helpers.huf12_frame(n, four, seed=n + prefix, raw_prefix=prefix)
+                items += [(frame, len(plain)), (frame[:-1], len(plain)), (frame, 10)]
+    ordinary = [(f, len(d)) for f, d in helpers.make_frames(306, 20, sizes=[5000, 70000])]
+    mixed = []
+    for k, it in enumerate(items):                     # folded and ordinary tables side by side in one CTA
+        mixed += [it, ordinary[k % len(ordinary)]]
+    res, dsts = _gpu_decode(gpu_ctx, mixed)
+    for (frame, cap), r, d in zip(mixed, res, dsts):
+        ro, oo, _ = oracle.decompress(frame, cap)
+        assert int(r) == ro, (len(frame), cap, hex(ro), hex(int(r)))
+        if not helpers.is_err(ro):
+            assert d[:ro].tobytes() == oo
+
+
 def test_checksum_mismatch_is_reported(gpu_ctx, oracle):
     from tools import zstd_ref
     rng = random.Random(4)

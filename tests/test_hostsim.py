@@ -44,3 +44,19 @@ def test_items_with_several_data_frames(hostsim, oracle):
         ro, oo, _ = oracle.decompress(blob, cap)
         rh, oh = hostsim.decompress(blob, cap, oracle)
         assert ro == rh and oo == oh, (len(blob), cap, hex(ro), hex(rh))
+
+
+def test_huffman_table_log_12_is_folded_correctly(hostsim, oracle):
+    """The kernels keep 2^11 cells per Huffman table and fold a log-12 table into it (zb_format.cuh huf_fill_table)."""
+    for four in (True, False):
+        for n in (300, 700, 1001):
+            for prefix in (0, 50):
+                frame, plain = helpers.huf12_frame(n, four, seed=n + prefix, raw_prefix=prefix)
+                ro, oo, _ = oracle.decompress(frame, len(plain))
+                assert ro == len(plain) and oo == plain, "crafted frame is not valid for the oracle"
+                rh, oh = hostsim.decompress(frame, len(plain), oracle)
+                assert rh == ro and oh == plain
+                for cut in (1, 3):                    # truncations: same verdicts
+                    bad = frame[:-cut]
+                    assert hostsim.decompress(bad, len(plain), oracle)[0] == oracle.decompress(bad, len(plain))[0]
+                assert hostsim.decompress(frame, 10, oracle)[0] == oracle.decompress(frame, 10)[0]    # dry validation path

@@ -46,10 +46,13 @@ __global__ void __launch_bounds__(128) k_parse(DecodeArgs a) {
 // k_huf : one warp per CTA, 8 frames per warp, lanes 4f..4f+3 own the 4 streams of frame f
 // =================================================================================================
 struct HufSmem {
-  u16 table[8][1 << HUF_LOG_MAX];
+  __align__(16) u16 table[8][1 << HUF_TABLE_LOG];   // also lent as HufFseScratch while a frame's weights are decoded
   HufBuildWk wk[8];
-  __align__(16) u32 ring[32][ZB_RING_WORDS + 4];   // per-lane (= per-stream) bitstream read-ahead (BitRing)
+  __align__(16) u32 ring[32][ZB_RING_WORDS + 4];   // per-lane (= per-stream) bitstream read-ahead (BitRing); a folded
+                                                   // log-12 table keeps its 256-byte side table in the group's first ring
 };
+static_assert(sizeof(HufFseScratch) <= sizeof(u16) << HUF_TABLE_LOG, "FSE scratch must fit the decode table it borrows");
+static_assert((ZB_RING_WORDS + 4) * 4 >= 256, "side table must fit one lane's ring");
 
 __global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -64,6 +67,7 @@ __global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
   const u8* src = a.src_base + a.src_off[f]; const u32 size = a.src_size[f];
   u8* lit = lit_region(a, f, fi); const u64 litCap = lit_capacity(frame_cap(a, f, fi));
   u16* dt = sm.table[slot]; HufBuildWk& wk = sm.wk[slot];
+  u8* const sideMem = (u8*)&sm.ring[slot * 4][0]; const u8* side = nullptr;
   u32 pos = fi.body_off, blk = 0; u64 litRun = 0;
   u32 tableLog = 0; bool haveTable = false;
   u32 errBlock = 0xFFFFFFFFu, errCode = 0;
@@ -87,7 +91,7 @@ __global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
           if (ok) {
             u32 e = 0;
             if (sub == 0) {
-              e = huf_read_weights(body, bodySize, wk, &hdr, &tl, &nbSym);
+              e = huf_read_weights(body, bodySize, wk, *reinterpret_cast<HufFseScratch*>(dt), &hdr, &tl, &nbSym);
               if (!e && hdr >= bodySize) e = ZE_srcSize_wrong;                     // HufDecompress.cs:1193
             }
             __syncwarp(gmask);
@@ -96,22 +100,23 @@ __global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
             if (e) ok = false;
           }
           if (ok) {
-            huf_fill_table(dt, wk, tl, nbSym, sub, 4);
+            __syncwarp(gmask);                                                     // lane 0's scratch use of dt is over
+            huf_fill_table(dt, sideMem, wk, tl, nbSym, sub, 4);
             __syncwarp(gmask);
-            tableLog = tl; haveTable = true;
+            tableLog = tl; haveTable = true; side = tl > HUF_TABLE_LOG ? sideMem : nullptr;
             body += hdr; bodySize -= hdr;
           }
         }
         if (ok) {
           bool good = true;
           if (lh.single) {
-            if (sub == 0) good = dry ? huf_check_stream(body, bodySize, lh.litSize, dt, tableLog)
-                                     : huf_decode_stream(body, bodySize, lit + litRun, lh.litSize, dt, tableLog, &sm.ring[lane][0]);   // HufDecompress.cs:247-264
+            if (sub == 0) good = dry ? huf_check_stream(body, bodySize, lh.litSize, dt, tableLog, side)
+                                     : huf_decode_stream(body, bodySize, lit + litRun, lh.litSize, dt, tableLog, &sm.ring[lane][0], side);   // HufDecompress.cs:247-264
           } else {
             HufStream st;
             good = huf_split4(body, bodySize, lh.litSize, sub, st);
-            if (good) good = dry ? huf_check_stream(st.src, st.len, st.count, dt, tableLog)
-                                 : huf_decode_stream(st.src, st.len, lit + litRun + st.outOfs, st.count, dt, tableLog, &sm.ring[lane][0]);
+            if (good) good = dry ? huf_check_stream(st.src, st.len, st.count, dt, tableLog, side)
+                                 : huf_decode_stream(st.src, st.len, lit + litRun + st.outOfs, st.count, dt, tableLog, &sm.ring[lane][0], side);
           }
           unsigned okmask = __ballot_sync(gmask, good);
           if ((okmask & gmask) != gmask) ok = false;

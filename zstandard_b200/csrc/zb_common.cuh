@@ -39,7 +39,8 @@ static const u32 MAGIC = 0xFD2FB528u, MAGIC_SKIP = 0x184D2A50u;
 static const u32 BLOCKSIZE_MAX = 1u << 17;
 static const u32 LONGNBSEQ = 0x7F00;
 static const u32 MaxLL = 35, MaxML = 52, MaxOff = 31, LLFSELog = 9, MLFSELog = 9, OffFSELog = 8;
-static const u32 HUF_LOG_MAX = 12;
+static const u32 HUF_LOG_MAX = 12;        // largest table log the reference accepts (HufDecompress.cs:128)
+static const u32 HUF_TABLE_LOG = 11;      // log of the decode table the kernels keep (log-12 tables are folded, zb_format.cuh)
 
 // ---- per-item record produced by the parse kernel and refined by later stages ----
 // huf_err_code value: the block's Huffman streams are well formed but its literals do not fit the frame's literal

@@ -273,10 +273,24 @@ ZB_HD bool huf_split4(const u8* body, u32 bodySize, u32 n, u32 lane, HufStream& 
 
 // Decodes `count` symbols of one backward stream into out[0..count).  true iff the stream was consumed
 // exactly (EndOfDStream, HufDecompress.cs:350-353 / :261) — which also implies it was never over-read.
-ZB_HD bool huf_decode_stream(const u8* src, u32 len, u8* out, u32 count, const u16* dt, u32 tableLog, u32* ringMem) {
+// One symbol of a folded log-12 table (huf_fill_table): window w is left aligned
+ZB_HD u32 huf_cell12(const u16* dt, const u8* side, u64 w) {
+  const u32 i12 = (u32)(w >> 52), cell = dt[i12 >> 1];
+  return (cell >> 8) == 12 ? (12u << 8) | side[i12] : cell;
+}
+// side != nullptr <=> the table is a folded log-12 table: plain per-symbol loop (no encoder emits such tables)
+ZB_HD bool huf_decode_stream(const u8* src, u32 len, u8* out, u32 count, const u16* dt, u32 tableLog, u32* ringMem, const u8* side = nullptr) {
   BitCursor c;
   if (!bc_init(c, src, len)) return false;                                         // InitDStream errors :304-307
   i32 P = c.P;
+  if (side) {
+    for (u32 left = count; left; left--) {
+      if (P < 0) return false;
+      const u32 cell = huf_cell12(dt, side, bc_window64(c, P));
+      *out++ = (u8)cell; P -= (i32)(cell >> 8);
+    }
+    return P == 0;
+  }
   u32 left = count;
   const u32 sh = 64 - tableLog;
   // head: reach 4-byte alignment of the output
@@ -324,14 +338,15 @@ ZB_HD bool huf_decode_stream(const u8* src, u32 len, u8* out, u32 count, const u
 // Validation without output: same verdict as huf_decode_stream.  Used when a block's literals cannot fit the
 // frame's literal scratch — the frame is then certain to fail, but whether with corruption_detected (here) or with
 // the execute stage's dstSize_tooSmall depends on whether the streams are well formed (HufDecompress.cs:350-353).
-ZB_HD bool huf_check_stream(const u8* src, u32 len, u32 count, const u16* dt, u32 tableLog) {
+ZB_HD bool huf_check_stream(const u8* src, u32 len, u32 count, const u16* dt, u32 tableLog, const u8* side = nullptr) {
   BitCursor c;
   if (!bc_init(c, src, len)) return false;
   i32 P = c.P;
   const u32 sh = 64 - tableLog;
   for (u32 left = count; left; left--) {
     if (P < 0) return false;
-    P -= (i32)(dt[(u32)(bc_window64(c, P) >> sh)] >> 8);
+    const u64 w = bc_window64(c, P);
+    P -= (i32)((side ? huf_cell12(dt, side, w) : dt[(u32)(w >> sh)]) >> 8);
   }
   return P == 0;
 }

@@ -301,10 +301,13 @@ ZB_HD u32 read_seq_table(u32 mode, int kind, const u8* p, u32 srcSize, u16* cell
 // Huffman weights and single-symbol table (ReadStats EntropyCommon.cs:198-269; FSE_decompress_wksp
 // FseDecompress.cs:111-181,233-332; HUF_readDTableX2_wksp HufDecompress.cs:117-180)
 // =====================================================================================================
-// Workspace per Huffman table build, all in memory private to the building thread.
+// Workspace per Huffman table build.  weight/rank survive until the table has been filled; the FSE scratch is only
+// live while compressed weights are decoded, so callers lend the (not yet filled) decode table for it.
 struct HufBuildWk {
   u8 weight[256 + 4];
   u32 rank[16];
+};
+struct HufFseScratch {          // 1280 bytes
   s16 norm[256];
   u16 symbolNext[256];
   u32 fse[64];        // weight-FSE decode cells: newState | nbBits << 16 | symbol << 24
@@ -313,7 +316,7 @@ struct HufBuildWk {
 // FSE-compressed weights -> w[0..n).  Returns count, or 0xFFFFFFFF on error.  Mirrors the reference's
 // two-state loop: symbols alternate between the states; once a read has crossed the stream start the other
 // state's pending symbol is emitted and decoding stops (FseDecompress.cs:275-292).
-ZB_HD u32 fse_decode_weights(u8* w, u32 maxOut, const u8* src, u32 srcSize, HufBuildWk& wk) {
+ZB_HD u32 fse_decode_weights(u8* w, u32 maxOut, const u8* src, u32 srcSize, HufFseScratch& wk) {
   u32 maxSV = 255, tl, h;
   if (read_ncount(wk.norm, &maxSV, &tl, src, srcSize, &h)) return 0xFFFFFFFFu;
   if (tl > 6) return 0xFFFFFFFFu;                                                  // FseDecompress.cs:322 (maxLog 6)
@@ -360,7 +363,7 @@ ZB_HD u32 fse_decode_weights(u8* w, u32 maxOut, const u8* src, u32 srcSize, HufB
 
 // Parses the weight header at src and validates it.  On success returns 0 and sets *hdrBytes, *tableLog,
 // *nbSym with wk.weight[0..nbSym) and wk.rank[] = first cell index of each weight (ready for filling).
-ZB_HD u32 huf_read_weights(const u8* src, u32 srcSize, HufBuildWk& wk, u32* hdrBytes, u32* tableLog, u32* nbSym) {
+ZB_HD u32 huf_read_weights(const u8* src, u32 srcSize, HufBuildWk& wk, HufFseScratch& fs, u32* hdrBytes, u32* tableLog, u32* nbSym) {
   if (srcSize == 0) return ZE_srcSize_wrong;
   u32 iSize = src[0], oSize;
   if (iSize >= 128) {
@@ -370,7 +373,7 @@ ZB_HD u32 huf_read_weights(const u8* src, u32 srcSize, HufBuildWk& wk, u32* hdrB
     for (u32 n = 0; n < oSize; n += 2) { wk.weight[n] = src[1 + n / 2] >> 4; wk.weight[n + 1] = src[1 + n / 2] & 15; }
   } else {
     if (iSize + 1 > srcSize) return ZE_srcSize_wrong;
-    oSize = fse_decode_weights(wk.weight, 255, src + 1, iSize, wk);
+    oSize = fse_decode_weights(wk.weight, 255, src + 1, iSize, fs);
     if (oSize == 0xFFFFFFFFu) return ZE_corruption_detected;
   }
   for (u32 i = 0; i < 16; i++) wk.rank[i] = 0;
@@ -396,15 +399,24 @@ ZB_HD u32 huf_read_weights(const u8* src, u32 srcSize, HufBuildWk& wk, u32* hdrB
 // Huffman decode cell: byte | nbBits << 8 (HufDecompress.cs:110-115)
 // Fills table cells for symbols n = first, first+step, ... (so that several lanes can share the fill);
 // rank starts must be advanced for *all* symbols in order, hence the full loop with a write predicate.
-ZB_HD void huf_fill_table(u16* dt, const HufBuildWk& wk, u32 tableLog, u32 nbSym, u32 first, u32 step) {
+//
+// The kernels keep 2^HUF_TABLE_LOG (11) cells per table — what every real encoder produces — so that more frames
+// fit an SM's shared memory.  A log-12 table (legal for the reference, HufDecompress.cs:128) is folded: cell i stands
+// for codes 2i and 2i+1.  Codes of 2..11 bits cover whole pairs (their first cell index is even because the weight-1
+// symbols come first and their count is even, :389).  The 12-bit codes (weight 1) are the cells below count1/2:
+// those get nbBits 12 and the two symbols of a pair go to side[2i], side[2i+1] (side: 256 bytes, only for log 12).
+ZB_HD void huf_fill_table(u16* dt, u8* side, const HufBuildWk& wk, u32 tableLog, u32 nbSym, u32 first, u32 step) {
   u32 rank[16];
   for (u32 i = 0; i < 16; i++) rank[i] = wk.rank[i];
+  const bool folded = tableLog > HUF_TABLE_LOG;
   for (u32 n = 0; n < nbSym; n++) {
     u32 wv = wk.weight[n], len = (1u << wv) >> 1, start = rank[wv];
     rank[wv] = start + len;
     if ((n % step) == first) {
       u16 cell = (u16)(n | ((tableLog + 1 - wv) << 8));
-      for (u32 u = 0; u < len; u++) dt[start + u] = cell;
+      if (!folded) { for (u32 u = 0; u < len; u++) dt[start + u] = cell; }
+      else if (wv == 1) { side[start] = (u8)n; dt[start >> 1] = (u16)(12u << 8); }
+      else { for (u32 u = 0; u < len / 2; u++) dt[start / 2 + u] = cell; }
     }
   }
 }
