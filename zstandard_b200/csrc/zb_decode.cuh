@@ -18,7 +18,14 @@ namespace zb {
 //   x == 0, y == 0 : end of a block's records
 //   x == 0, y != 0 : announces a split sequence: y = its litLength + matchLength, so that the execute stage can
 //                    make the reference's whole-sequence capacity check (:1278) before any check of the pieces
-struct SeqRec { u32 x, y; };
+struct alignas(8) SeqRec { u32 x, y; };
+ZB_HD void rec_store(SeqRec* p, u32 x, u32 y) {
+#if defined(__CUDA_ARCH__)
+  *reinterpret_cast<uint2*>(p) = make_uint2(x, y);
+#else
+  p->x = x; p->y = y;
+#endif
+}
 
 // Capacity rule shared with the host side: records for a frame whose output capacity is `cap` bytes.
 // Every record with a match yields >= 3 bytes and each block adds one terminator, so a frame that fits its
@@ -38,12 +45,15 @@ struct SeqFrameOut {
 
 // slow path of the record writer: lengths that do not fit 16 bits are split (ZStdDecompress.cs allows
 // litLength <= 131071 and matchLength <= 131074)
-ZB_HD void seq_emit_long(SeqRec* out, u64& n, u64 cap, u32 off, u32 ll, u32 ml) {
-  if (n < cap) { out[n].x = 0; out[n].y = ll + ml; } n++;
-  while (ll > 65535) { if (n < cap) { out[n].x = 1; out[n].y = 65535; } n++; ll -= 65535; }
-  while (ml > 65535) { if (n < cap) { out[n].x = off; out[n].y = ll | (65535u << 16); } n++; ll = 0; ml -= 65535; }
-  if (n < cap) { out[n].x = off; out[n].y = ll | (ml << 16); }
-  n++;
+#if defined(__CUDA_ARCH__)
+__noinline__
+#endif
+ZB_HD u32 seq_emit_long(SeqRec* out, u32 n, u32 cap, u32 off, u32 ll, u32 ml) {
+  if (n < cap) rec_store(out + n, 0, ll + ml); n++;
+  while (ll > 65535) { if (n < cap) rec_store(out + n, 1, 65535); n++; ll -= 65535; }
+  while (ml > 65535) { if (n < cap) rec_store(out + n, off, ll | (65535u << 16)); n++; ll = 0; ml -= 65535; }
+  if (n < cap) rec_store(out + n, off, ll | (ml << 16));
+  return n + 1;
 }
 
 // n bits (0..32) from the top of a left-aligned 64-bit window; the double shift makes n == 0 yield 0
@@ -53,15 +63,18 @@ ZB_HD u32 top_bits(u64 w, u32 n) { return (u32)((w >> 1) >> (63 - n)); }
 // Offset value of one sequence and the repeat-offset history update (DecodeSequence :1487-1531), written
 // without data-dependent branches.  ofBits is the offset code, ofv its extra bits, llSym the literal-length code.
 ZB_HD u32 rep_resolve(u32& rep0, u32& rep1, u32& rep2, u32 ofBits, u32 ofv, u32 llSym) {
-  const u32 raw = ofBits ? of_base(ofBits) + ofv : 0;
   const bool isRep = ofBits <= 1;
-  const u32 idx = raw + (llSym == 0);                                  // 0..3 when isRep
-  const u32 pick = idx == 0 ? rep0 : (idx == 1 ? rep1 : (idx == 2 ? rep2 : rep0 - 1));
-  const u32 repv = pick + (pick == 0);                                 // 0 is not valid: forced to 1 (:1515)
-  const u32 offset = isRep ? repv : raw;
-  const bool shift1 = !isRep || idx >= 1;                              // history is untouched only when idx == 0
-  const bool shift2 = !isRep || idx >= 2;
-  const u32 n2 = shift2 ? rep1 : rep2, n1 = shift1 ? rep0 : rep1;
+  const u32 raw = (1u << (ofBits & 31)) - 3 + ofv;                     // OF_base + extra bits for codes >= 2 (:1088-1092)
+  const u32 idx = ofBits + ofv + (llSym == 0);                         // codes 0/1: repeat-offset index 0..3 (base 0 / 1, ofv = 0 for code 0)
+  u32 pick = rep0;
+  pick = idx == 1 ? rep1 : pick;
+  pick = idx == 2 ? rep2 : pick;
+  pick = idx == 3 ? rep0 - 1 : pick;
+  pick = pick == 0 ? 1 : pick;                                         // 0 is not valid: forced to 1 (:1515)
+  const u32 offset = isRep ? pick : raw;
+  const bool keep1 = isRep && idx == 0;                                // history is untouched only when idx == 0
+  const bool keep2 = isRep && idx <= 1;
+  const u32 n2 = keep2 ? rep2 : rep1, n1 = keep1 ? rep1 : rep0;
   rep2 = n2; rep1 = n1; rep0 = offset;
   return offset;
 }
@@ -121,13 +134,14 @@ ZB_HD void seq_values_ref32(const u8* s, u32 n, i32 P, bool longOffsets, u32 ofB
 // llInfo/mlInfo: per-symbol base | extra bits << 24 (ll_info/ml_info); norm/symbolNext: >= 53 entries of per-thread scratch each;
 // ringMem: ZB_RING_WORDS words of per-thread bitstream read-ahead (BitRing), 16-byte aligned.
 template <class NormT, class NextT>
-ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, SeqTableSet& T, SeqRec* out, u64 cap, SeqFrameOut& res,
+ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, SeqTableSet& T, SeqRec* out, u64 cap64, SeqFrameOut& res,
                             const u32* llInfo, const u32* mlInfo, NormT norm, NextT symbolNext, u32* ringMem) {
   res.err_block = 0xFFFFFFFFu; res.err_code = 0; res.err_index = 0;
   u32 pos = body_off, blk = 0;
   u32 rep0 = 1, rep1 = 4, rep2 = 8;                      // ZStdInternal.cs:111, ZStdDecompress.cs:2492
   bool haveRepeat = false;
-  u64 n = 0;
+  const u32 cap = (u32)cap64;                            // seq_capacity of a u32 capacity fits 32 bits
+  u32 n = 0;
   for (int k = 0; k < 3; k++) { T.cur[k] = T.space[k]; T.curStride[k] = T.stride; T.log[k] = 0; }
   while (true) {
     BlockHdr bh;
@@ -196,8 +210,8 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, S
             const u32 h2 = fshl(lo, hi, valBits);                                  // the 32 bits after the value bits
             const u32 offset = rep_resolve(rep0, rep1, rep2, ofBits, ofv, llSym);
             const u32 ml = (iML & 0xFFFFFF) + mlv, ll = (iLL & 0xFFFFFF) + llv;
-            if ((ll | ml) <= 65535) { if (n < cap) { out[n].x = offset; out[n].y = ll | (ml << 16); } n++; }
-            else seq_emit_long(out, n, cap, offset, ll, ml);
+            if ((ll | ml) <= 65535) { if (n < cap) rec_store(out + n, offset, ll | (ml << 16)); n++; }
+            else n = seq_emit_long(out, n, cap, offset, ll, ml);
             stLL = cell_base(lLL) + shr_c(h2, 32 - nLL);                           // state update LL, ML, OF (:1547-1550)
             stML = cell_base(lML) + shr_c(h2 << nLL, 32 - nML);
             stOF = cell_base(lOF) + shr_c(h2 << (nLL + nML), 32 - nOF);
@@ -226,8 +240,8 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, S
             else if (valBits + stBits > 64) w = bc_window64(c, Pv);                // rare: more than 64 bits in one sequence
             const u32 offset = rep_resolve(rep0, rep1, rep2, ofBits, ofv, llSym);
             const u32 ml = (iML & 0xFFFFFF) + mlv, ll = (iLL & 0xFFFFFF) + llv;
-            if ((ll | ml) <= 65535) { if (n < cap) { out[n].x = offset; out[n].y = ll | (ml << 16); } n++; }
-            else seq_emit_long(out, n, cap, offset, ll, ml);
+            if ((ll | ml) <= 65535) { if (n < cap) rec_store(out + n, offset, ll | (ml << 16)); n++; }
+            else n = seq_emit_long(out, n, cap, offset, ll, ml);
             decoded++;
             // past the last sequence these bits do not exist (the stream ends after its value bits)
             stLL = cell_base(lLL) + top_bits(w, nLL); w <<= nLL;
@@ -238,7 +252,7 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, S
         }
         // terminator; when the region is full the last slot is sacrificed so that the execute stage stops there
         const bool overflow = n >= cap;
-        if (overflow) { out[cap - 1].x = 0; out[cap - 1].y = 0; } else { out[n].x = 0; out[n].y = 0; }
+        rec_store(out + (overflow ? cap - 1 : n), 0, 0);
         n++;
         if (overflow) { res.err_block = blk; res.err_code = ZE_dstSize_tooSmall; res.err_index = 0; return; }
         if (bad) { res.err_block = blk; res.err_code = ZE_corruption_detected; res.err_index = decoded; return; }
