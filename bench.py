@@ -2,6 +2,7 @@
 """bench.py — headline benchmark of libzstdb200 (BASELINE.json: GB/s uncompressed, 64 KiB frames).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload decode64k|compress128k]
+                    [--corpus log|tick|random|mixed] [--chunk BYTES] [--level 1..3] [--bytes N]
 
 One process per GPU (under torchrun for N > 1: RANK/LOCAL_RANK/WORLD_SIZE from the env).  Frames are independent,
 so ranks shard the work with no data-path collective ("scaling": "weak": every rank processes --bytes of its own
@@ -14,7 +15,10 @@ A step = one pass of the hot path over one batch:
 Reported:
   value         device-resident pipeline: inputs and outputs already in HBM, CUDA events on the launching stream
   e2e           the same work through the host-buffer C-ABI call (pinned host memory -> H2D -> kernels -> D2H)
-  roofline      algorithmic bytes (bytes in + bytes out of the codec) / duration of the dominant kernel
+  roofline      algorithmic bytes (bytes in + bytes out of the codec) / duration of the dominant kernel; `traffic` = that
+                kernel's DRAM bytes per launch from the committed ncu capture of this command (profiles/traffic.json)
+The other BASELINE.json configs are the same two workloads with other shapes: --corpus mixed (configs[3]), --corpus tick
+--chunk 4096..1048576 (configs[4]); profiles/ holds the lines measured for them.
   cpu_baseline  decode: the oracle (C++ port of the reference decoder; the C# reference cannot run in this image);
                 compress: libzstd 1.5.5 (the reference has no compressor) — all host cores in both cases
 `--impl reference` times that CPU baseline alone, rank 0 only, as the reference arm.
@@ -46,8 +50,19 @@ def parse_args():
     ap.add_argument("--bytes", type=int, default=1 << 30, help="uncompressed bytes per GPU per step")
     ap.add_argument("--corpus", default="log", choices=["log", "tick", "random", "mixed"])
     ap.add_argument("--level", type=int, default=3)
+    ap.add_argument("--chunk", type=int, default=0, help="frame / chunk size in bytes (default: the workload's 64 KiB / 128 KiB)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
+
+
+def recorded_traffic(workload_key, kernel):
+    """DRAM bytes per launch of `kernel` from the ncu --set full capture of this bench command (profiles/traffic.json,
+    written by tools/ncu_traffic.py from the committed capture); None when no capture exists for this workload."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    rec = json.load(open(p)).get(workload_key, {}).get(kernel)
+    return int(rec["dram_bytes"]) if rec else None
 
 
 def measured_peak():
@@ -100,7 +115,7 @@ class ClockSampler(threading.Thread):
 def prepare(args, rank):
     from tools import corpus, zstd_ref
     import zstandard_b200 as zb
-    chunk = CHUNK[args.workload]
+    chunk = args.chunk or CHUNK[args.workload]
     raw = corpus.make(args.corpus, args.bytes, shard=rank)
     total = len(raw)
     n = (total + chunk - 1) // chunk
@@ -119,10 +134,10 @@ def prepare(args, rank):
 
 def workload_config(args, w):
     if w["kind"] == "decode64k":
-        what = (f"decode64k: batched decompression of {w['total']} B/GPU of libzstd-1.5.5 level-{args.level} {args.corpus} text held as "
+        what = (f"decode{w['chunk'] // 1024}k: batched decompression of {w['total']} B/GPU of libzstd-1.5.5 level-{args.level} {args.corpus} text held as "
                 f"{w['chunk'] // 1024} KiB independent frames with XXH64 checksums")
     else:
-        what = (f"compress128k: batched level-{args.level} compression of {w['total']} B/GPU of {args.corpus} text in "
+        what = (f"compress{w['chunk'] // 1024}k: batched level-{args.level} compression of {w['total']} B/GPU of {args.corpus} text in "
                 f"{w['chunk'] // 1024} KiB chunks, one frame each, with XXH64 checksums")
     return {"workload": what, "frames_per_gpu": w["n"], "libzstd_compressed_bytes_per_gpu": w["ref_compressed_bytes"],
             "libzstd_ratio": round(w["total"] / w["ref_compressed_bytes"], 4),
@@ -292,7 +307,9 @@ def main():
             for k, v in ctx.decompress_batch_device_timed(*dargs, stream=stream).items():
                 kms[k] = kms.get(k, 0.0) + v / reps
     else:
-        kms = {"k_encode+k_enc_xxh": ms / args.steps}
+        for _ in range(reps):
+            for k, v in ctx.compress_batch_device_timed(args.level, True, *dargs, stream=stream).items():
+                kms[k] = kms.get(k, 0.0) + v / reps
     dom = max(kms, key=kms.get)
     out_bytes_algo = total if decode else our_compressed
     algo_bytes = src_bytes + out_bytes_algo
@@ -359,7 +376,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
-                         "traffic": None, "kernel": dom, "peak_source": peak_src,
+                         "traffic": recorded_traffic(f"{args.workload}/{args.corpus}/{w['chunk']}/{total}/L{args.level}", dom), "kernel": dom, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo_bytes),
                          "pipeline_frac": round(algo_bytes * args.steps / (ms * 1e-3) / 1e9 / peak, 5)},
             "kernel_ms": {k: round(v, 4) for k, v in kms.items()},

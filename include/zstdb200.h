@@ -98,6 +98,11 @@ int zstdb200_decompress_batch_device_timed(zstdb200_ctx* ctx, int device_index,
                                            void* dst_base, const uint64_t* dst_off, const uint32_t* dst_cap,
                                            uint32_t* result, size_t n, void* stream, float* kernel_ms, int max_kernels);
 const char* zstdb200_decode_kernel_name(int k);
+int zstdb200_compress_batch_device_timed(zstdb200_ctx* ctx, int device_index, int level, int checksum,
+                                         const void* src_base, const uint64_t* src_off, const uint32_t* src_size,
+                                         void* dst_base, const uint64_t* dst_off, const uint32_t* dst_cap,
+                                         uint32_t* result, size_t n, void* stream, float* kernel_ms, int max_kernels);
+const char* zstdb200_encode_kernel_name(int k);
 
 #ifdef __cplusplus
 }

@@ -52,6 +52,9 @@ def main():
         e1.record(s)
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1))
+    kms = ctx.compress_batch_device_timed(args.level, True, t_src.data_ptr(), t_soff.data_ptr(), t_ssz.data_ptr(), t_dst.data_ptr(),
+                                          t_doff.data_ptr(), t_dcap.data_ptr(), t_res.data_ptr(), n, stream=s.cuda_stream)
+    print("kernel_ms", {k: round(v, 3) for k, v in kms.items()})
     res = t_res.cpu().numpy().view(np.uint32)
     assert (res < 0xFFFFFF88).all()
     comp = int(res.astype(np.int64).sum())

@@ -46,6 +46,10 @@ ABI = {
                                                           _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p,
                                                           _c.POINTER(_c.c_float), _c.c_int]),
     "zstdb200_decode_kernel_name": (_c.c_char_p, [_c.c_int]),
+    "zstdb200_compress_batch_device_timed": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                                        _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p,
+                                                        _c.POINTER(_c.c_float), _c.c_int]),
+    "zstdb200_encode_kernel_name": (_c.c_char_p, [_c.c_int]),
 }
 
 _lib = None
@@ -184,6 +188,22 @@ class Context:
                                                       dst_base, dst_off, dst_cap, result, n, stream)
         if rc != 0:
             raise RuntimeError("zstdb200_compress_batch_device failed: " + self.last_error())
+
+
+    def compress_batch_device_timed(self, level, checksum, src_base, src_off, src_size, dst_base, dst_off, dst_cap, result, n, stream=0,
+                                    device_index=0):
+        """-> {kernel name: ms} for one synchronised run of the device pipeline."""
+        ms = (_c.c_float * 8)()
+        rc = self._lib.zstdb200_compress_batch_device_timed(self._h, device_index, int(level), 1 if checksum else 0, src_base, src_off,
+                                                            src_size, dst_base, dst_off, dst_cap, result, n, stream, ms, 8)
+        if rc != 0:
+            raise RuntimeError("zstdb200_compress_batch_device_timed failed: " + self.last_error())
+        out = {}
+        for k in range(8):
+            name = self._lib.zstdb200_encode_kernel_name(k).decode()
+            if name:
+                out[name] = ms[k]
+        return out
 
 
 _default_ctx = None

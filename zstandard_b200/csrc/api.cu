@@ -465,6 +465,31 @@ int zstdb200_compress_batch_device(zstdb200_ctx* ctx, int device_index, int leve
   return 0;
 }
 
+// zstdb200_compress_batch_device with CUDA events between its kernels (see zstdb200_decompress_batch_device_timed).
+int zstdb200_compress_batch_device_timed(zstdb200_ctx* ctx, int device_index, int level, int checksum, const void* src_base,
+                                         const uint64_t* src_off, const uint32_t* src_size, void* dst_base, const uint64_t* dst_off,
+                                         const uint32_t* dst_cap, uint32_t* result, size_t n, void* stream, float* kernel_ms, int max_kernels) {
+  if (!ctx) return 1;
+  ctx->err.clear();
+  if (device_index < 0 || device_index >= (int)ctx->dev.size()) { ctx->err = "bad device_index"; return 1; }
+  if (level < 1 || level > 3) { ctx->err = "level must be 1..3"; return 1; }
+  if (n > ctx->maxItems) { ctx->err = "n exceeds zstdb200_max_items"; return 1; }
+  Device& d = ctx->dev[device_index];
+  CK(cudaSetDevice(d.id));
+  cudaStream_t st = stream ? (cudaStream_t)stream : d.stream[0];
+  cudaEvent_t ev[ENCODE_KERNELS + 1];
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  EncodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, 0, level, checksum, ENC_EXCLUSIVE};
+  int nl = 0;
+  CK(encode_launch(a, d.enc, st, &nl, ev));
+  ctx->launches += nl;
+  CK(cudaStreamSynchronize(st));
+  for (int k = 0; k < ENCODE_KERNELS && k < max_kernels; k++) CK(cudaEventElapsedTime(&kernel_ms[k], ev[k], ev[k + 1]));
+  for (auto& e : ev) cudaEventDestroy(e);
+  return 0;
+}
+const char* zstdb200_encode_kernel_name(int k) { return (k >= 0 && k < ENCODE_KERNELS) ? kEncodeKernelNames[k] : ""; }
+
 void* zstdb200_host_alloc(size_t bytes) { void* p = nullptr; return cudaMallocHost(&p, bytes ? bytes : 1) == cudaSuccess ? p : nullptr; }
 void zstdb200_host_free(void* p) { if (p) cudaFreeHost(p); }
 

@@ -486,7 +486,9 @@ static cudaError_t encode_lazy_alloc(EncodeScratch& s) {
   return cudaSuccess;
 }
 
-cudaError_t encode_launch(const EncodeArgs& a, EncodeScratch& s, cudaStream_t st, int* launches) {
+const char* const kEncodeKernelNames[ENCODE_KERNELS] = {"k_enc_match", "k_enc_entropy", "k_enc_xxh"};
+
+cudaError_t encode_launch(const EncodeArgs& a, EncodeScratch& s, cudaStream_t st, int* launches, cudaEvent_t* marks) {
   if (a.n == 0) return cudaSuccess;
   cudaError_t e = encode_lazy_alloc(s);
   if (e != cudaSuccess) return e;
@@ -496,25 +498,19 @@ cudaError_t encode_launch(const EncodeArgs& a, EncodeScratch& s, cudaStream_t st
   const size_t smem = ((size_t)(1u << hlogL) + (dfast ? (1u << hlogS) : 0)) * 2;
   u32 perSm = (u32)((220 * 1024) / smem); if (perSm > 16) perSm = 16;
   u32 grid = (u32)s.sms * perSm; if (grid > a.n) grid = a.n;
-  static const bool timing = getenv("ZSTDB200_ENC_TIMING") != nullptr;   // debug aid: per-kernel times on stderr
-  cudaEvent_t ev[3];
-  if (timing) { for (auto& x : ev) cudaEventCreate(&x); cudaEventRecord(ev[0], st); }
+  if (marks) cudaEventRecord(marks[0], st);
   if (dfast) k_enc_match<true><<<grid, 32, smem, st>>>(a, s, hlogL, hlogS, mls);
   else k_enc_match<false><<<grid, 32, smem, st>>>(a, s, hlogL, hlogS, mls);
   const bool exclusive = a.stream_slot == ENC_EXCLUSIVE;
   const u32 slot0 = exclusive ? 0 : (a.stream_slot % ENC_STREAM_PARTS) * kSlotsPerPart;
   const u32 maxSlots = exclusive ? kSlotsExclusive : kSlotsPerPart;
   const u32 slots = a.n < maxSlots ? a.n : maxSlots;
-  if (timing) cudaEventRecord(ev[1], st);
+  if (marks) cudaEventRecord(marks[1], st);
   k_enc_entropy<<<(slots + 3) / 4, 128, 0, st>>>(a, s, slot0, slots);
-  if (timing) {
-    cudaEventRecord(ev[2], st); cudaEventSynchronize(ev[2]);
-    float m1 = 0, m2 = 0; cudaEventElapsedTime(&m1, ev[0], ev[1]); cudaEventElapsedTime(&m2, ev[1], ev[2]);
-    fprintf(stderr, "[zstdb200] encode level %d n %u: k_enc_match %.3f ms (grid %u, smem %zu), k_enc_entropy %.3f ms (slots %u)\n", a.level, a.n, m1, grid, smem, m2, slots);
-    for (auto& x : ev) cudaEventDestroy(x);
-  }
+  if (marks) cudaEventRecord(marks[2], st);
   if (launches) *launches += 2;
   if (a.checksum) { k_enc_xxh<<<(a.n * 4 + 127) / 128, 128, 0, st>>>(a); if (launches) *launches += 1; }
+  if (marks) cudaEventRecord(marks[3], st);
   return cudaGetLastError();
 }
 

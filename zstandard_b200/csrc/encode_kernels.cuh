@@ -35,6 +35,9 @@ struct EncodeScratch {
 size_t encode_bound(size_t srcSize);
 cudaError_t encode_alloc(EncodeScratch& s, size_t maxBatchBytes, size_t maxItems);   // records sizes; memory comes lazily
 void encode_free(EncodeScratch& s);
-cudaError_t encode_launch(const EncodeArgs& a, EncodeScratch& s, cudaStream_t st, int* launches);
+// marks (optional): ENCODE_KERNELS + 1 events recorded before the first kernel and after each kernel
+#define ENCODE_KERNELS 3
+extern const char* const kEncodeKernelNames[ENCODE_KERNELS];
+cudaError_t encode_launch(const EncodeArgs& a, EncodeScratch& s, cudaStream_t st, int* launches, cudaEvent_t* marks = nullptr);
 
 }  // namespace zb
