@@ -32,7 +32,7 @@ struct Sim {
 // mirrors k_huf for one frame; returns first failing block / code through fi
 void sim_huf(const u8* src, u32 size, FrameInfo& fi, u8* lit, u64 litCap) {
   alignas(16) static thread_local u16 dt[1 << HUF_TABLE_LOG]; static thread_local HufBuildWk wk; alignas(16) u32 ringBuf[ZB_RING_WORDS];
-  static thread_local u8 sideMem[256]; const u8* side = nullptr;
+  static thread_local u8 sideMem[256], slotMem[256]; const u8* side = nullptr;
   u32 pos = fi.body_off, blk = 0; u64 litRun = 0; u32 tableLog = 0; bool haveTable = false;
   while (true) {
     BlockHdr bh;
@@ -52,12 +52,12 @@ void sim_huf(const u8* src, u32 size, FrameInfo& fi, u8* lit, u64 litCap) {
           if (!lh.single && (lh.litSize == 0 || bodySize == 0)) ok = false;
           u32 hdr = 0, nbSym = 0, tl = 0;
           if (ok) {
-            u32 e = huf_read_weights(body, bodySize, wk, *reinterpret_cast<HufFseScratch*>(dt), &hdr, &tl, &nbSym);
+            u32 e = huf_read_weights(body, bodySize, wk, *reinterpret_cast<HufFseScratch*>(dt), slotMem, &hdr, &tl, &nbSym);
             if (!e && hdr >= bodySize) e = ZE_srcSize_wrong;
             if (e) ok = false;
           }
           if (ok) {
-            for (u32 sub = 0; sub < 4; sub++) huf_fill_table(dt, sideMem, wk, tl, nbSym, sub, 4);
+            for (u32 sub = 0; sub < 4; sub++) huf_fill_table(dt, sideMem, wk, slotMem, tl, nbSym, sub, 4);
             tableLog = tl; haveTable = true; body += hdr; bodySize -= hdr; side = tl > HUF_TABLE_LOG ? sideMem : nullptr;
           }
         }

@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
   u8* lit = lit_region(a, f, fi); const u64 litCap = lit_capacity(frame_cap(a, f, fi));
   u16* dt = sm.table[slot]; HufBuildWk& wk = sm.wk[slot];
   u8* const sideMem = (u8*)&sm.ring[slot * 4][0]; const u8* side = nullptr;
+  u8* const slotMem = (u8*)&sm.ring[slot * 4 + 1][0];   // per-symbol rank within its weight: dead once the table is filled
   u32 pos = fi.body_off, blk = 0; u64 litRun = 0;
   u32 tableLog = 0; bool haveTable = false;
   u32 errBlock = 0xFFFFFFFFu, errCode = 0;
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
           if (ok) {
             u32 e = 0;
             if (sub == 0) {
-              e = huf_read_weights(body, bodySize, wk, *reinterpret_cast<HufFseScratch*>(dt), &hdr, &tl, &nbSym);
+              e = huf_read_weights(body, bodySize, wk, *reinterpret_cast<HufFseScratch*>(dt), slotMem, &hdr, &tl, &nbSym);
               if (!e && hdr >= bodySize) e = ZE_srcSize_wrong;                     // HufDecompress.cs:1193
             }
             __syncwarp(gmask);
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
           }
           if (ok) {
             __syncwarp(gmask);                                                     // lane 0's scratch use of dt is over
-            huf_fill_table(dt, sideMem, wk, tl, nbSym, sub, 4);
+            huf_fill_table(dt, sideMem, wk, slotMem, tl, nbSym, sub, 4);
             __syncwarp(gmask);
             tableLog = tl; haveTable = true; side = tl > HUF_TABLE_LOG ? sideMem : nullptr;
             body += hdr; bodySize -= hdr;

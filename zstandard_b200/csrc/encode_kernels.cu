@@ -100,11 +100,17 @@ __global__ void __launch_bounds__(32) k_enc_match(EncodeArgs a, EncodeScratch sc
         if (blk > 0) { rep1 = 0; rep2 = 0; }
         u32 anchor = bpos; const u32 ilimit = bend - 8;
         u32 p0 = bpos + (bpos == 0 ? 1 : 0);
-        while (p0 < ilimit) {
+        // fresh: p0 directly follows a match, so the "immediate repeat of the older offset" test (litLength 0,
+        // code 1 == second offset) is pending for it.  Its loads are issued together with the window's, and the
+        // window's table lookups and candidate loads run speculatively behind it: one memory round trip instead of two.
+        bool fresh = false;
+        while (p0 < ilimit || (fresh && p0 == ilimit)) {
           const u32 step = 1 + ((p0 - anchor) >> 8);                 // skim incompressible runs
           if (lane < 4) prefetch_line(src + p0 + 384 + 128 * lane);   // the source streams in from HBM: keep ~4 lines ahead in L1
           const u32 p = p0 + lane * step;
           const bool act = p < ilimit;
+          u32 r2a = 0, r2b = 1;
+          if (fresh && rep2 != 0) { r2a = ldu32(src + p0); r2b = ldu32(src + p0 - rep2); }
           const u64 v = act ? ldu64(src + p) : 0;
           const u32 hL = act ? hash64(v, hlogL, DFAST ? 8 : mls) : (0x80000000u | lane);
           const u32 eL = act ? tabL[hL] : 0;
@@ -124,6 +130,24 @@ __global__ void __launch_bounds__(32) k_enc_match(EncodeArgs a, EncodeScratch sc
           if (validL) okL = DFAST ? (ldu64(src + candL) == v) : (ldu32(src + candL) == (u32)v);
           if (DFAST && validS) okS = ldu32(src + candS) == (u32)v;
           const bool rok = act && rep1 != 0 && rep1 <= p && ldu32(src + p - rep1) == (u32)v;
+          if (fresh) {
+            fresh = false;
+            if (r2a == r2b) {                                                      // uniform over the warp
+              const u32 rlen = 4 + warp_extend(src, p0 + 4, rep2, bend, lane);
+              { const u32 t = rep2; rep2 = rep1; rep1 = t; }
+              if (lane == 0) {
+                tabL[hash64(ldu64(src + p0), hlogL, DFAST ? 8 : mls)] = (u16)p0;
+                if (DFAST) tabS[hash64(ldu64(src + p0), hlogS, mls)] = (u16)p0;
+                seqs[2 * nseq] = ((rlen - 3) & 0xFFFF) << 16;
+                seqs[2 * nseq + 1] = 1u | ((((rlen - 3) >> 16) & 1) << 30);
+              }
+              __syncwarp();
+              nseq++;
+              p0 += rlen; anchor = p0;
+              fresh = p0 <= ilimit;
+              continue;
+            }
+          }
           const unsigned fRep = __ballot_sync(FULLMASK, rok);
           const unsigned found = __ballot_sync(FULLMASK, okL | okS) | fRep;
           if (!found) {                                                // no match in the window: enter every position, move on
@@ -141,8 +165,18 @@ __global__ void __launch_bounds__(32) k_enc_match(EncodeArgs a, EncodeScratch sc
           const u32 cf = __shfl_sync(FULLMASK, kind == 1 ? candL : candS, fl);
           u32 cnd = kf == 0 ? pos - rep1 : cf;
           const u32 off = pos - cnd;
-          u32 mlen = 4 + warp_extend(src, pos + 4, off, bend, lane);
-          while (pos > anchor && cnd > 0 && src[pos - 1] == src[cnd - 1]) { pos--; cnd--; mlen++; }   // catch up
+          // forward extension and backward catch-up (:pos > anchor && cnd > 0 && equal) from one round of loads
+          u32 mlen;
+          {
+            const u32 i = pos + 4 + lane; const bool feq = i < bend && src[i] == src[i - off];
+            const u32 maxb = min(pos - anchor, cnd);
+            const bool beq = lane < maxb && src[pos - 1 - lane] == src[cnd - 1 - lane];
+            const unsigned fm = __ballot_sync(FULLMASK, feq), bm = __ballot_sync(FULLMASK, beq);
+            const u32 fwd = fm == FULLMASK ? 32 + warp_extend(src, pos + 36, off, bend, lane) : (u32)__ffs(~fm) - 1;
+            u32 bwd = bm == FULLMASK ? 32 : (u32)__ffs(~bm) - 1;
+            if (bm == FULLMASK) while (bwd < maxb && src[pos - 1 - bwd] == src[cnd - 1 - bwd]) bwd++;
+            mlen = 4 + fwd + bwd; pos -= bwd; cnd -= bwd;
+          }
  {
             // enter the window's positions up to the end of the match: nothing at or beyond the restart position may
             // go in, or it would later be found as its own candidate
@@ -167,20 +201,7 @@ __global__ void __launch_bounds__(32) k_enc_match(EncodeArgs a, EncodeScratch sc
           if (p0 <= ilimit) {
             if (lane == 0) { const u32 q = p0 - 2; tabL[hash64(ldu64(src + q), hlogL, DFAST ? 8 : mls)] = (u16)q; if (DFAST) tabS[hash64(ldu64(src + q), hlogS, mls)] = (u16)q; }
             __syncwarp();
-            // immediate repeat of the older offset (litLength 0, code 1 == second offset)
-            while (rep2 != 0 && p0 <= ilimit && ldu32(src + p0) == ldu32(src + p0 - rep2)) {
-              const u32 rlen = 4 + warp_extend(src, p0 + 4, rep2, bend, lane);
-              { const u32 t = rep2; rep2 = rep1; rep1 = t; }
-              if (lane == 0) {
-                tabL[hash64(ldu64(src + p0), hlogL, DFAST ? 8 : mls)] = (u16)p0;
-                if (DFAST) tabS[hash64(ldu64(src + p0), hlogS, mls)] = (u16)p0;
-                seqs[2 * nseq] = ((rlen - 3) & 0xFFFF) << 16;
-                seqs[2 * nseq + 1] = 1u | ((((rlen - 3) >> 16) & 1) << 30);
-              }
-              __syncwarp();
-              nseq++;
-              p0 += rlen; anchor = p0;
-            }
+            fresh = true;                                              // immediate-repeat test at the top of the next pass
           }
         }
         // last literals
@@ -218,10 +239,11 @@ __host__ __device__ inline size_t slot_bytes() { return align16((size_t)kBlockSe
 struct EntWarp {
   u32 hist[256];
   HufEnc he;
-  u32 cnt[3][64];
-  u16 state[3][514 + 2];
+  union {                        // the Huffman tree is built before any of the sequence tables exist
+    struct { u32 cnt[3][64]; u16 state[3][514 + 2]; u8 sym[512 + 16]; };
+    HufBuildScratch hb;
+  };
   FseCTable ct[3];
-  u8 sym[512 + 16];
 };
 
 __device__ __forceinline__ void wcopy(u8* dst, const u8* src, u32 n, u32 lane) {
@@ -275,8 +297,21 @@ __device__ u32 warp_enc_literals(u8* out, u32 cap, const u8* lits, u32 n, EntWar
   }
   if (largest <= (n >> 7) + 4) return raw();
   u32 maxBits = fse_optimal_log(11, n, maxSym, 1); if (maxBits > 11) maxBits = 11;
+  // sort the used symbols by (count, symbol) across the warp: rank = number of used symbols that sort before
+  // (same order as huf_sort_symbols' stable insertion sort), then lane 0 builds the tree from shared memory
+  u32 nUsed = 0;
+  for (u32 s0 = 0; s0 < 256; s0 += 32) {
+    const u32 s = s0 + lane, c = w.hist[s];
+    nUsed += __popc(__ballot_sync(FULLMASK, c != 0));
+    if (c) {
+      u32 rank = 0;
+      for (u32 t = 0; t <= maxSym; t++) { const u32 ct = w.hist[t]; rank += (ct != 0) && (ct < c || (ct == c && t < s)); }
+      w.hb.order[rank] = (u16)s;
+    }
+  }
+  __syncwarp();
   u32 ok = 0;
-  if (lane == 0) ok = huf_build(w.he, w.hist, maxSym, maxBits) ? 1 : 0;
+  if (lane == 0) ok = huf_build_sorted(w.he, w.hist, nUsed, maxBits, w.hb) ? 1 : 0;
   ok = __shfl_sync(FULLMASK, ok, 0);
   if (!ok) return raw();
   const bool single = n < 256;

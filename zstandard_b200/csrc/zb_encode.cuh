@@ -401,14 +401,22 @@ struct HufEnc { HufCode code[256]; u8 weight[256]; u32 maxSym; u32 tableLog; };
 // Builds code lengths <= maxBits for symbols with count > 0 (needs >= 2 distinct symbols).  Package-free
 // heuristic: build an optimal tree with two queues over the sorted symbols, then repair over-long codes the
 // way zstd's HUF_setMaxHeight does (pay back the Kraft debt on the longest cheap symbols).
-ZB_HD bool huf_build(HufEnc& he, const u32* count, u32 maxSym, u32 maxBits) {
-  u16 order[256]; u32 n = 0;
+// Working arrays of huf_build (4 KB): callers choose where they live (the GPU kernel lends shared memory).
+struct HufBuildScratch { u32 nodeCount[512]; u16 parent[512]; u16 order[256]; u8 depth[512]; };
+
+// Stable sort of the used symbols by count ascending (ties: symbol ascending) -> order[0..n); returns n.
+ZB_HD u32 huf_sort_symbols(u16* order, const u32* count, u32 maxSym) {
+  u32 n = 0;
   for (u32 s = 0; s <= maxSym; s++) if (count[s]) order[n++] = (u16)s;
-  if (n < 2) return false;
-  // insertion sort by count ascending (n <= 256)
   for (u32 i = 1; i < n; i++) { u16 v = order[i]; u32 c = count[v]; u32 j = i; while (j > 0 && count[order[j - 1]] > c) { order[j] = order[j - 1]; j--; } order[j] = v; }
+  return n;
+}
+
+// sc.order[0..n) holds the used symbols sorted as huf_sort_symbols does
+ZB_HD bool huf_build_sorted(HufEnc& he, const u32* count, u32 n, u32 maxBits, HufBuildScratch& sc) {
+  if (n < 2) return false;
+  u16* const order = sc.order; u32* const nodeCount = sc.nodeCount; u16* const parent = sc.parent; u8* const depth = sc.depth;
   // two-queue Huffman: nodes 0..n-1 leaves (sorted), n..2n-2 internal
-  u32 nodeCount[512]; u16 parent[512];
   for (u32 i = 0; i < n; i++) nodeCount[i] = count[order[i]];
   u32 leaf = 0, inner = n, next = n;
   while (next < 2 * n - 1) {
@@ -419,7 +427,6 @@ ZB_HD bool huf_build(HufEnc& he, const u32* count, u32 maxSym, u32 maxBits) {
     nodeCount[next] = nodeCount[pick[0]] + nodeCount[pick[1]];
     parent[pick[0]] = parent[pick[1]] = (u16)next; next++;
   }
-  u8 depth[512];
   depth[2 * n - 2] = 0;
   for (i32 i = (i32)(2 * n - 3); i >= 0; i--) depth[i] = depth[parent[i]] + 1;
   // enforce the length limit: clamp, then repay the Kraft excess (in units of 2^-maxBits) by lengthening the
@@ -467,6 +474,10 @@ ZB_HD bool huf_build(HufEnc& he, const u32* count, u32 maxSym, u32 maxBits) {
     rankStart[wv] += 1u << (wv - 1);
   }
   return true;
+}
+ZB_HD bool huf_build(HufEnc& he, const u32* count, u32 maxSym, u32 maxBits, HufBuildScratch& sc) {
+  const u32 n = huf_sort_symbols(sc.order, count, maxSym);
+  return huf_build_sorted(he, count, n, maxBits, sc);
 }
 
 // weight header: FSE-compressed weights when that is smaller, else 4-bit nibbles (needs maxSym <= 128 there)
@@ -550,9 +561,9 @@ ZB_HD u32 enc_literals(u8* out, u32 cap, const u8* lits, u32 n, u16* stateScratc
     return lh + 1;
   }
   if (largest <= (n >> 7) + 4) return raw();   // too flat to be worth it
-  HufEnc he;
+  HufEnc he; HufBuildScratch hsc;
   u32 maxBits = fse_optimal_log(11, n, maxSym, 1); if (maxBits > 11) maxBits = 11;
-  if (!huf_build(he, count, maxSym, maxBits)) return raw();
+  if (!huf_build(he, count, maxSym, maxBits, hsc)) return raw();
   const bool single = n < 256;
   const u32 lhSize = 3 + (n >= 1024) + (n >= 16384);
   if (lhSize + 8 > cap) return 0;

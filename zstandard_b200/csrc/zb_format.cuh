@@ -362,8 +362,9 @@ ZB_HD u32 fse_decode_weights(u8* w, u32 maxOut, const u8* src, u32 srcSize, HufF
 }
 
 // Parses the weight header at src and validates it.  On success returns 0 and sets *hdrBytes, *tableLog,
-// *nbSym with wk.weight[0..nbSym) and wk.rank[] = first cell index of each weight (ready for filling).
-ZB_HD u32 huf_read_weights(const u8* src, u32 srcSize, HufBuildWk& wk, HufFseScratch& fs, u32* hdrBytes, u32* tableLog, u32* nbSym) {
+// *nbSym with wk.weight[0..nbSym), wk.rank[] = first cell index of each weight and slot[n] = how many earlier
+// symbols share symbol n's weight — so that any lane can place any symbol's cells without a running count.
+ZB_HD u32 huf_read_weights(const u8* src, u32 srcSize, HufBuildWk& wk, HufFseScratch& fs, u8* slot, u32* hdrBytes, u32* tableLog, u32* nbSym) {
   if (srcSize == 0) return ZE_srcSize_wrong;
   u32 iSize = src[0], oSize;
   if (iSize >= 128) {
@@ -381,6 +382,7 @@ ZB_HD u32 huf_read_weights(const u8* src, u32 srcSize, HufBuildWk& wk, HufFseScr
   for (u32 n = 0; n < oSize; n++) {
     u32 wv = wk.weight[n];
     if (wv >= HUF_LOG_MAX) return ZE_corruption_detected;
+    slot[n] = (u8)wk.rank[wv];
     wk.rank[wv]++; total += (1u << wv) >> 1;
   }
   if (total == 0) return ZE_corruption_detected;
@@ -388,7 +390,7 @@ ZB_HD u32 huf_read_weights(const u8* src, u32 srcSize, HufBuildWk& wk, HufFseScr
   if (tl > HUF_LOG_MAX) return ZE_corruption_detected;
   u32 rest = (1u << tl) - total, last = highbit(rest) + 1;
   if ((1u << highbit(rest)) != rest) return ZE_corruption_detected;
-  wk.weight[oSize] = (u8)last; wk.rank[last]++;
+  wk.weight[oSize] = (u8)last; slot[oSize] = (u8)wk.rank[last]; wk.rank[last]++;
   if (wk.rank[1] < 2 || (wk.rank[1] & 1)) return ZE_corruption_detected;
   u32 next = 0;
   for (u32 n = 1; n < tl + 1; n++) { u32 cur = next; next += wk.rank[n] << (n - 1); wk.rank[n] = cur; }
@@ -405,19 +407,25 @@ ZB_HD u32 huf_read_weights(const u8* src, u32 srcSize, HufBuildWk& wk, HufFseScr
 // for codes 2i and 2i+1.  Codes of 2..11 bits cover whole pairs (their first cell index is even because the weight-1
 // symbols come first and their count is even, :389).  The 12-bit codes (weight 1) are the cells below count1/2:
 // those get nbBits 12 and the two symbols of a pair go to side[2i], side[2i+1] (side: 256 bytes, only for log 12).
-ZB_HD void huf_fill_table(u16* dt, u8* side, const HufBuildWk& wk, u32 tableLog, u32 nbSym, u32 first, u32 step) {
-  u32 rank[16];
-  for (u32 i = 0; i < 16; i++) rank[i] = wk.rank[i];
+// dt must be 16-byte aligned: runs of 8 or more cells (power-of-two lengths at multiples of their length) are
+// written as 16-byte vectors.
+ZB_HD void huf_fill_cells(u16* dt, u32 start, u32 len, u16 cell) {
+  if (len >= 8) {
+    const u32 c2 = cell * 0x10001u;
+    u32* p = (u32*)(dt + start);
+    for (u32 u = 0; u < len / 2; u += 4) { p[u] = c2; p[u + 1] = c2; p[u + 2] = c2; p[u + 3] = c2; }
+  } else for (u32 u = 0; u < len; u++) dt[start + u] = cell;
+}
+ZB_HD void huf_fill_table(u16* dt, u8* side, const HufBuildWk& wk, const u8* slot, u32 tableLog, u32 nbSym, u32 first, u32 step) {
   const bool folded = tableLog > HUF_TABLE_LOG;
-  for (u32 n = 0; n < nbSym; n++) {
-    u32 wv = wk.weight[n], len = (1u << wv) >> 1, start = rank[wv];
-    rank[wv] = start + len;
-    if ((n % step) == first) {
-      u16 cell = (u16)(n | ((tableLog + 1 - wv) << 8));
-      if (!folded) { for (u32 u = 0; u < len; u++) dt[start + u] = cell; }
-      else if (wv == 1) { side[start] = (u8)n; dt[start >> 1] = (u16)(12u << 8); }
-      else { for (u32 u = 0; u < len / 2; u++) dt[start / 2 + u] = cell; }
-    }
+  for (u32 n = first; n < nbSym; n += step) {
+    const u32 wv = wk.weight[n];
+    if (!wv) continue;
+    const u32 len = 1u << (wv - 1), start = wk.rank[wv] + slot[n] * len;
+    const u16 cell = (u16)(n | ((tableLog + 1 - wv) << 8));
+    if (!folded) huf_fill_cells(dt, start, len, cell);
+    else if (wv == 1) { side[start] = (u8)n; dt[start >> 1] = (u16)(12u << 8); }
+    else huf_fill_cells(dt, start / 2, len / 2, cell);
   }
 }
 
