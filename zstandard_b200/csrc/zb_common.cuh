@@ -139,8 +139,8 @@ ZB_HD bool bc_init(BitCursor& c, const u8* src, u32 n) {
 }
 
 // 64 stream bits ending at P, left aligned: bit 63 of the result is stream bit P-1.  Bits below stream bit 0
-// are zero.  Requires P >= 0 for meaningful data; for P < 64 a byte-safe path is used so that nothing below
-// `words` or before the stream is ever dereferenced.
+// are zero.  Requires P >= 0 for meaningful data; for P < 64 only the aligned words that hold unread stream bits
+// are dereferenced (nothing below `words`, nothing past the word of the last unread bit).
 ZB_HD u64 bc_window64(const BitCursor& c, i32 P) {
   if (P >= 64) {
     i32 g = c.gofs + P - 64;          // bit offset (>= 0) of the window's lowest bit
@@ -151,11 +151,11 @@ ZB_HD u64 bc_window64(const BitCursor& c, i32 P) {
     return ((u64)hi << 32) | lo;
   }
   if (P <= 0) return 0;
-  // tail: gather the ceil(P/8) remaining bytes
-  const u8* b = (const u8*)c.words + (c.gofs >> 3);
-  u64 v = 0; i32 nb = (P + 7) >> 3;
-  for (i32 i = 0; i < nb; i++) v |= (u64)b[i] << (8 * i);
-  return v << (64 - P);   // bits at and above P (end mark, padding) fall off the top
+  // tail: stream bits [0, P) sit in words[0..2] from bit gofs up; only words that hold one of them are loaded
+  const u32 top = (u32)c.gofs + (u32)P;                       // 1 .. 87
+  const u32 w0 = c.words[0], w1 = top > 32 ? c.words[1] : 0, w2 = top > 64 ? c.words[2] : 0;
+  const u32 lo = fshr(w0, w1, (u32)c.gofs), hi = fshr(w1, w2, (u32)c.gofs);
+  return (((u64)hi << 32) | lo) << (64 - P);                  // bits at and above P (end mark, padding) fall off the top
 }
 
 // ---- per-thread read-ahead of a backward bitstream through shared memory ---------------------------
