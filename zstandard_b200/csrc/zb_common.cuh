@@ -223,9 +223,20 @@ ZB_HD void ring_window(const BitRing& r, i32 P, u32& lo, u32& hi) {
 }
 // Call once per step after the cursor moved to Pn (by fewer than 128 bits): keeps the ring ZB_RING_AHEAD chunks
 // ahead of the window and closes this step's commit group.
+// Branch-free on the device (the refill is a predicated cp.async): branches are what the one-warp-per-scheduler
+// entropy loops pay most for.
 ZB_HD void ring_advance(BitRing& r, i32 Pn) {
   const i32 wc = (r.gofs + Pn - 64) >> 7;
+#if defined(__CUDA_ARCH__)
+  const i32 chunk = r.lowChunk - 1;
+  const u32 move = r.lowChunk > wc - ZB_RING_AHEAD, fetch = move && chunk >= 0;   // chunks below 0 lie before the stream
+  const u32 saddr = (u32)__cvta_generic_to_shared(r.ring) + ((((u32)chunk) & 15) << 4);
+  const u8* src = r.base16 + (i64)chunk * 16;
+  asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p cp.async.ca.shared.global [%0], [%1], 16; }" ::"r"(saddr), "l"(src), "r"(fetch) : "memory");
+  r.lowChunk -= (i32)move;
+#else
   if (r.lowChunk > wc - ZB_RING_AHEAD) { r.lowChunk -= 1; ring_request(r, r.lowChunk); }
+#endif
   ring_commit();
 }
 

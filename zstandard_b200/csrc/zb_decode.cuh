@@ -201,17 +201,19 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, S
             const u32 iLL = llInfo[llSym], iML = mlInfo[mlSym];
             const u32 llBits = iLL >> 24, mlBits = iML >> 24;
             const u32 valBits = ofBits + mlBits + llBits;
-            if (valBits >= 32) break;
             const u32 lLL = yLL & 0x3FF, lOF = yOF & 0x3FF, lML = yML & 0x3FF;
             const u32 nLL = cell_nb(lLL), nML = cell_nb(lML), nOF = cell_nb(lOF);
             const u32 ofv = shr_c(hi, 32 - ofBits);                                // read order: offset, matchLength, litLength
             const u32 mlv = shr_c(hi << ofBits, 32 - mlBits);                      // (:1504, :1534, :1542)
             const u32 llv = shr_c(hi << (ofBits + mlBits), 32 - llBits);
+            const u32 ml = (iML & 0xFFFFFF) + mlv, ll = (iLL & 0xFFFFFF) + llv;
+            // the one rare exit of the loop: >= 32 value bits (the 32-bit extraction above is then wrong) or a length that
+            // needs a split record — nothing has been committed yet, the careful loop redoes this sequence
+            if (valBits >= 32 || (ll | ml) > 65535) break;
             const u32 h2 = fshl(lo, hi, valBits);                                  // the 32 bits after the value bits
             const u32 offset = rep_resolve(rep0, rep1, rep2, ofBits, ofv, llSym);
-            const u32 ml = (iML & 0xFFFFFF) + mlv, ll = (iLL & 0xFFFFFF) + llv;
-            if ((ll | ml) <= 65535) { if (n < cap) rec_store(out + n, offset, ll | (ml << 16)); n++; }
-            else n = seq_emit_long(out, n, cap, offset, ll, ml);
+            if (n < cap) rec_store(out + n, offset, ll | (ml << 16));
+            n++;
             stLL = cell_base(lLL) + shr_c(h2, 32 - nLL);                           // state update LL, ML, OF (:1547-1550)
             stML = cell_base(lML) + shr_c(h2 << nLL, 32 - nML);
             stOF = cell_base(lOF) + shr_c(h2 << (nLL + nML), 32 - nOF);
