@@ -316,7 +316,7 @@ extern "C" uint32_t hostsim_compress_warp(uint8_t* dst, uint32_t cap, const uint
   std::vector<u8> padded(size + 64, 0);
   u8* src = padded.data() + 16;
   if (size) memcpy(src, src_in, size);
-  WarpMatcher m; m.src = src; m.size = size; m.dfast = level >= 3; m.hlogL = 13; m.hlogS = 12; m.mls = level <= 1 ? 6 : 5;
+  WarpMatcher m; m.src = src; m.size = size; m.dfast = level >= 3; m.hlogL = getenv("HS_HLOGL") ? atoi(getenv("HS_HLOGL")) : enc_hlog_long(level); m.hlogS = getenv("HS_HLOGS") ? atoi(getenv("HS_HLOGS")) : enc_hlog_short(level); m.mls = level <= 1 ? 6 : 5;
   m.tab.assign((1u << m.hlogL) + (1u << m.hlogS), 0);
   const u32 seqCap = BLOCKSIZE_MAX / 4 + 64;
   std::vector<u8> codes(3 * seqCap), sym(4096); std::vector<u16> ct(3 * 514 + 16);

@@ -529,9 +529,16 @@ cudaError_t encode_launch(const EncodeArgs& a, EncodeScratch& s, cudaStream_t st
   if (e != cudaSuccess) return e;
   // match stage: table sizes per level (u16 entries); as many resident warps as shared memory allows
   const bool dfast = a.level >= 3;
-  const u32 hlogL = 13, hlogS = 12, mls = a.level <= 1 ? 6 : 5;   // u16 entries: 16 KB (levels 1-2) / 24 KB (level 3) per warp
+  static const int envLog = getenv("ZSTDB200_ENC_HLOG") ? atoi(getenv("ZSTDB200_ENC_HLOG")) : 0;       // tuning aids
+  static const int envPerSm = getenv("ZSTDB200_ENC_PERSM") ? atoi(getenv("ZSTDB200_ENC_PERSM")) : 0;
+  // Table sizes (u16 entries) trade ratio against resident warps, and this kernel's throughput is its warp count:
+  // level 1: 2^12 (8 KB, 24 warps/SM), level 2: 2^13 (16 KB, 12 warps/SM), level 3: 2^12 long + 2^12 short (16 KB).
+  // Measured with the lock-step emulation (tests/hostsim): tick records stay within -2.2 % of libzstd at 128 KiB
+  // chunks, log text gains ratio with the smaller tables.
+  const u32 hlogL = envLog ? (u32)envLog : enc_hlog_long(a.level), hlogS = envLog ? (u32)envLog - 1 : enc_hlog_short(a.level), mls = a.level <= 1 ? 6 : 5;
   const size_t smem = ((size_t)(1u << hlogL) + (dfast ? (1u << hlogS) : 0)) * 2;
-  u32 perSm = (u32)((220 * 1024) / smem); if (perSm > 16) perSm = 16;
+  const u32 capSm = envPerSm ? (u32)envPerSm : 32;
+  u32 perSm = (u32)((220 * 1024) / (smem + 1024)); if (perSm > capSm) perSm = capSm;
   u32 grid = (u32)s.sms * perSm; if (grid > a.n) grid = a.n;
   if (marks) cudaEventRecord(marks[0], st);
   if (dfast) k_enc_match<true><<<grid, 32, smem, st>>>(a, s, hlogL, hlogS, mls);
