@@ -375,7 +375,7 @@ __device__ u32 warp_enc_sequences(u8* out, u32 cap, const SeqStore& st, u8* code
     atomicAdd(&w.cnt[KIND_LL][lc], 1u); atomicAdd(&w.cnt[KIND_OF][oc], 1u); atomicAdd(&w.cnt[KIND_ML][mc], 1u);
   }
   __syncwarp();
-  u32 total = 0;
+  u32 total = 0, o2w = 0;
   if (lane == 0) {
     bool good = true; u32 used, o2 = op;
     u8* modeByte = out + o2++;
@@ -385,11 +385,37 @@ __device__ u32 warp_enc_sequences(u8* out, u32 cap, const SeqStore& st, u8* code
     if (mLL == 0xFF) good = false; else o2 += used;
     if (good) { mOF = enc_seq_table_counts(w.ct[1], w.state[1], w.sym, w.cnt[KIND_OF], ofc[nbSeq - 1], nbSeq, kOF, level, out + o2, cap - o2, &used); if (mOF == 0xFF) good = false; else o2 += used; }
     if (good) { mML = enc_seq_table_counts(w.ct[2], w.state[2], w.sym, w.cnt[KIND_ML], mlc[nbSeq - 1], nbSeq, kML, level, out + o2, cap - o2, &used); if (mML == 0xFF) good = false; else o2 += used; }
-    if (good) {
-      *modeByte = (u8)((mLL << 6) | (mOF << 4) | (mML << 2));
-      u8* e = enc_seq_bitstream(out + o2, out + cap, st, llc, ofc, mlc, w.ct[0], w.ct[1], w.ct[2]);
-      if (e) total = (u32)(e - out);
+    if (good) { *modeByte = (u8)((mLL << 6) | (mOF << 4) | (mML << 2)); o2w = o2; }
+  }
+  o2w = __shfl_sync(FULLMASK, o2w, 0);
+  if (o2w) {
+    // The bitstream is one serial chain (lane 0), but its inputs need not come from HBM one dependent load at a
+    // time: the warp stages the sequences and their codes through shared memory, kStage at a time, last to first
+    // (hist and he are free once the literals are coded).
+    constexpr u32 kStage = 128;
+    static_assert(sizeof(w.hist) >= kStage * 8 && sizeof(w.he) >= kStage * 4, "staging buffers");
+    u32* const sq = w.hist; u32* const sc = reinterpret_cast<u32*>(&w.he);
+    SeqBits b; bool first = true;
+    for (u32 hi = nbSeq; hi > 0;) {
+      const u32 lo = hi > kStage ? hi - kStage : 0, cnt = hi - lo;
+      __syncwarp();
+      for (u32 i = lane; i < cnt; i += 32) {
+        const uint2 s2 = *reinterpret_cast<const uint2*>(st.seqs + 2 * (size_t)(lo + i));
+        sq[2 * i] = s2.x; sq[2 * i + 1] = s2.y;
+        sc[i] = (u32)llc[lo + i] | ((u32)ofc[lo + i] << 8) | ((u32)mlc[lo + i] << 16);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        for (i32 i = (i32)cnt - 1; i >= 0; i--) {
+          const u32 a = sq[2 * i], bb = sq[2 * i + 1], c = sc[i];
+          const u32 ll = (a & 0xFFFF) | ((bb >> 31) << 16), mlm3 = (a >> 16) | (((bb >> 30) & 1) << 16), ob = bb & 0x3FFFFFFFu;   // seq_get
+          if (first) { seqbits_first(b, out + o2w, out + cap, w.ct[0], w.ct[1], w.ct[2], ll, ob, mlm3, c & 0xFF, (c >> 8) & 0xFF, c >> 16); first = false; }
+          else seqbits_next(b, w.ct[0], w.ct[1], w.ct[2], ll, ob, mlm3, c & 0xFF, (c >> 8) & 0xFF, c >> 16);
+        }
+      }
+      hi = lo;
     }
+    if (lane == 0) { u8* e = seqbits_finish(b, w.ct[0], w.ct[1], w.ct[2]); if (e) total = (u32)(e - out); }
   }
   total = __shfl_sync(FULLMASK, total, 0);
   __syncwarp();

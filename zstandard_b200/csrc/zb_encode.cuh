@@ -222,16 +222,36 @@ ZB_HD void match_dfast(SeqStore& st, u32* hashLong, u32 hlogL, u32* hashSmall, u
 // ------------------------------------------------------------------------------------------------
 // forward bit writer (the decoder reads it backwards: BitStream.cs:322-497).  Bits are appended LSB first.
 // ------------------------------------------------------------------------------------------------
+// Forward bit writer that stores whole aligned 32-bit words: p is 4-byte aligned, acc holds the nb pending bits
+// (when the stream starts off alignment, the bytes already in memory before it ride along as the first pending
+// bits and are stored back unchanged).  Contract: at most 32 bits are added between two bw_flush calls.
 struct BitWriter { u8* p; u8* end; u64 acc; u32 nb; bool ovf; };
-ZB_HD void bw_init(BitWriter& w, u8* p, u8* end) { w.p = p; w.end = end; w.acc = 0; w.nb = 0; w.ovf = false; }
+ZB_HD u32 bw_load32(const u8* p) { return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24); }
+ZB_HD void bw_init(BitWriter& w, u8* p, u8* end) {
+  const u32 a = (u32)((uintptr_t)p & 3);
+  w.p = p - a; w.end = end; w.nb = 8 * a; w.ovf = false;
+  w.acc = a ? (bw_load32(w.p) & ((1u << (8 * a)) - 1)) : 0;
+}
 ZB_HD void bw_add(BitWriter& w, u32 v, u32 n) { w.acc |= (u64)(v & ((n >= 32) ? 0xFFFFFFFFu : ((1u << n) - 1))) << w.nb; w.nb += n; }
-ZB_HD void bw_flush(BitWriter& w) {   // keeps < 8 bits pending
-  while (w.nb >= 8) { if (w.p < w.end) *w.p++ = (u8)w.acc; else w.ovf = true; w.acc >>= 8; w.nb -= 8; }
+ZB_HD void bw_flush(BitWriter& w) {   // keeps < 32 bits pending
+  if (w.nb >= 32) {
+    const u32 v = (u32)w.acc;
+    if (w.p + 4 <= w.end) {
+#if defined(__CUDA_ARCH__)
+      *reinterpret_cast<u32*>(w.p) = v;
+#else
+      w.p[0] = (u8)v; w.p[1] = (u8)(v >> 8); w.p[2] = (u8)(v >> 16); w.p[3] = (u8)(v >> 24);
+#endif
+    } else { for (u32 k = 0; k < 4; k++) { if (w.p + k < w.end) w.p[k] = (u8)(v >> (8 * k)); else w.ovf = true; } }
+    w.p += 4; w.acc >>= 32; w.nb -= 32;
+  }
 }
 // end mark: a 1 bit, then zero padding (InitDStream locates it through the highest set bit of the last byte)
 ZB_HD u8* bw_close(BitWriter& w) {
   bw_add(w, 1, 1); bw_flush(w);
-  if (w.nb) { if (w.p < w.end) *w.p++ = (u8)w.acc; else w.ovf = true; w.nb = 0; }
+  const u32 bytes = (w.nb + 7) >> 3;
+  for (u32 k = 0; k < bytes; k++) { if (w.p + k < w.end) w.p[k] = (u8)(w.acc >> (8 * k)); else w.ovf = true; }
+  w.p += bytes; w.nb = 0;
   return w.ovf ? nullptr : w.p;
 }
 
@@ -489,7 +509,7 @@ ZB_HD u32 huf_write_header(u8* out, u32 cap, const HufEnc& he, u16* stateScratch
   const u32 nw = he.maxSym;   // weights of symbols 0..maxSym-1; the last one is implied
   if (nw == 0) return 0;
   // try FSE
-  u32 fseSize = 0; u8 fseBuf[160];
+  u32 fseSize = 0; alignas(4) u8 fseBuf[160];
   if (nw > 1) {
     u32 cnt[13]; for (u32 i = 0; i < 13; i++) cnt[i] = 0;
     u32 maxW = 0; for (u32 s = 0; s < nw; s++) { cnt[he.weight[s]]++; if (he.weight[s] > maxW) maxW = he.weight[s]; }
@@ -535,8 +555,7 @@ ZB_HD u32 huf_write_header(u8* out, u32 cap, const HufEnc& he, u16* stateScratch
 // one stream: symbols are written last-to-first so that the backward reader yields them in order
 ZB_HD u32 huf_encode_stream(u8* out, u32 cap, const u8* src, u32 n, const HufEnc& he) {
   BitWriter w; bw_init(w, out, out + cap);
-  for (i32 i = (i32)n - 1; i >= 0; i--) { const HufCode c = he.code[src[i]]; bw_add(w, c.val, c.nbBits); if (w.nb > 40) bw_flush(w); }
-  bw_flush(w);
+  for (i32 i = (i32)n - 1; i >= 0; i--) { const HufCode c = he.code[src[i]]; bw_add(w, c.val, c.nbBits); bw_flush(w); }
   u8* e = bw_close(w);
   return e ? (u32)(e - out) : 0;
 }
@@ -668,29 +687,40 @@ ZB_HD u32 enc_seq_count_header(u8* out, u32 nbSeq) {
 // bitstream: sequences last to first; per sequence the decoder reads offset, matchLength, litLength extra
 // bits, then the LL, ML, OF state bits (:1504-1550) — so we write them in the opposite order.
 // Returns the end of the stream or nullptr when out of room.
+// The encoder's running state, so that callers can feed the sequences in pieces (the GPU kernel stages them
+// through shared memory a chunk at a time).
+struct SeqBits { BitWriter w; u32 sLL, sOF, sML; };
+ZB_HD void seqbits_first(SeqBits& b, u8* out, u8* end, const FseCTable& ctLL, const FseCTable& ctOF, const FseCTable& ctML,
+                         u32 ll, u32 ob, u32 mlm3, u32 lc, u32 oc, u32 mc) {   // the last sequence of the block
+  bw_init(b.w, out, end);
+  fse_init_state(ctML, b.sML, mc); fse_init_state(ctOF, b.sOF, oc); fse_init_state(ctLL, b.sLL, lc);
+  bw_add(b.w, ll - kLLbase[lc], kLLbits[lc]);
+  bw_add(b.w, mlm3 + 3 - kMLbase[mc], kMLbits[mc]); bw_flush(b.w);
+  bw_add(b.w, ob - (1u << oc), oc); bw_flush(b.w);
+}
+ZB_HD void seqbits_next(SeqBits& b, const FseCTable& ctLL, const FseCTable& ctOF, const FseCTable& ctML,
+                        u32 ll, u32 ob, u32 mlm3, u32 lc, u32 oc, u32 mc) {    // the others, last to first
+  fse_encode(b.w, ctOF, b.sOF, oc); fse_encode(b.w, ctML, b.sML, mc); bw_flush(b.w);
+  fse_encode(b.w, ctLL, b.sLL, lc);
+  bw_add(b.w, ll - kLLbase[lc], kLLbits[lc]); bw_flush(b.w);
+  bw_add(b.w, mlm3 + 3 - kMLbase[mc], kMLbits[mc]); bw_flush(b.w);
+  bw_add(b.w, ob - (1u << oc), oc); bw_flush(b.w);
+}
+ZB_HD u8* seqbits_finish(SeqBits& b, const FseCTable& ctLL, const FseCTable& ctOF, const FseCTable& ctML) {
+  fse_flush_state(b.w, ctML, b.sML); fse_flush_state(b.w, ctOF, b.sOF); fse_flush_state(b.w, ctLL, b.sLL);
+  return bw_close(b.w);
+}
 ZB_HD u8* enc_seq_bitstream(u8* out, u8* end, const SeqStore& st, const u8* llc, const u8* ofc, const u8* mlc,
                             const FseCTable& ctLL, const FseCTable& ctOF, const FseCTable& ctML) {
   const u32 nbSeq = st.n;
-  BitWriter w; bw_init(w, out, end);
-  u32 sLL, sOF, sML;
-  {
-    const u32 i = nbSeq - 1; u32 ll, ob, mlm3; seq_get(st, i, ll, ob, mlm3);
-    fse_init_state(ctML, sML, mlc[i]); fse_init_state(ctOF, sOF, ofc[i]); fse_init_state(ctLL, sLL, llc[i]);
-    bw_add(w, ll - kLLbase[llc[i]], kLLbits[llc[i]]);
-    bw_add(w, mlm3 + 3 - kMLbase[mlc[i]], kMLbits[mlc[i]]); bw_flush(w);
-    bw_add(w, ob - (1u << ofc[i]), ofc[i]); bw_flush(w);
-  }
+  SeqBits b;
+  { const u32 i = nbSeq - 1; u32 ll, ob, mlm3; seq_get(st, i, ll, ob, mlm3);
+    seqbits_first(b, out, end, ctLL, ctOF, ctML, ll, ob, mlm3, llc[i], ofc[i], mlc[i]); }
   for (i32 n = (i32)nbSeq - 2; n >= 0; n--) {
     u32 ll, ob, mlm3; seq_get(st, (u32)n, ll, ob, mlm3);
-    const u32 lc = llc[n], oc = ofc[n], mc = mlc[n];
-    fse_encode(w, ctOF, sOF, oc); fse_encode(w, ctML, sML, mc); bw_flush(w);
-    fse_encode(w, ctLL, sLL, lc);
-    bw_add(w, ll - kLLbase[lc], kLLbits[lc]); bw_flush(w);
-    bw_add(w, mlm3 + 3 - kMLbase[mc], kMLbits[mc]); bw_flush(w);
-    bw_add(w, ob - (1u << oc), oc); bw_flush(w);
+    seqbits_next(b, ctLL, ctOF, ctML, ll, ob, mlm3, llc[n], ofc[n], mlc[n]);
   }
-  fse_flush_state(w, ctML, sML); fse_flush_state(w, ctOF, sOF); fse_flush_state(w, ctLL, sLL);
-  return bw_close(w);
+  return seqbits_finish(b, ctLL, ctOF, ctML);
 }
 
 ZB_HD SeqKind seq_kind(int kind) {
