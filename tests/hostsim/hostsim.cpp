@@ -240,8 +240,8 @@ struct WarpMatcher {
   std::vector<u32> seqs; std::vector<u8> lits;
   static u32 h64(u64 v, u32 hlog, u32 mls) {
     if (mls >= 8) return (u32)((v * 0xCF1BBCDCB7A56463ull) >> (64 - hlog));
-    if (mls == 6) return (u32)(((v << 16) * 0xCF1BBCDCBF9Bull) >> (64 - hlog));
-    return (u32)(((v << 24) * 0xCF1BBCDCBBull) >> (64 - hlog));
+    const u32 lo = (u32)v, hi = (u32)(v >> 32);                 // 5 / 6 bytes: two 32-bit multiplies (as k_enc_match)
+    return (lo * 2654435761u + (hi & (mls == 6 ? 0xFFFFu : 0xFFu)) * 2246822519u) >> (32 - hlog);
   }
   static bool candFrom(u32 p, u32 e, u32& c) { u32 d = (p - e) & 0xFFFF; if (!d) d = 0x10000; c = p - d; return d <= p; }
   u32 extend(u32 a, u32 off, u32 end) { u32 n = 0; while (a + n < end && src[a + n] == src[a + n - off]) n++; return n; }
@@ -294,7 +294,7 @@ struct WarpMatcher {
       nlits += ll; nseq++;
       anchor = pos + mlen; p0 = anchor;
       if (p0 <= ilimit) {
-        const u32 q = p0 - 2; tabL[h64(ld64(src + q), hlogL, dfast ? 8 : mls)] = (u16)q; if (dfast) tabS[h64(ld64(src + q), hlogS, mls)] = (u16)q;
+
         while (rep2 != 0 && p0 <= ilimit && ld32(src + p0) == ld32(src + p0 - rep2)) {
           const u32 rlen = 4 + extend(p0 + 4, rep2, bend);
           std::swap(rep1, rep2);
