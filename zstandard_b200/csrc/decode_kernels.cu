@@ -376,10 +376,10 @@ __global__ void __launch_bounds__(EXEC_THREADS, 10) k_exec(DecodeArgs a) {
   FrameInfo fi = a.info[f];
   if (fi.flags & FI_DONE) return;
   const u8* src = a.src_base + a.src_off[f]; const u32 size = a.src_size[f];
-  u8* dst = a.dst_base + frame_dst_off(a, f, fi); const u64 cap = frame_cap(a, f, fi);
+  u8* dst = a.dst_base + frame_dst_off(a, f, fi); const u32 cap = frame_cap(a, f, fi);
   const u8* litScratch = lit_region(a, f, fi);
   const SeqRec* recs = seq_region(a, f, fi);
-  u32 pos = fi.body_off, blk = 0; u64 op = 0, litRun = 0, recRun = 0;
+  u32 pos = fi.body_off, blk = 0, op = 0, litRun = 0, recRun = 0;   // op <= cap < 2^32 throughout: checks are written against cap - op
   bool litEntropy = false, dry = false; u32 err = 0;
   while (true) {
     BlockHdr bh;
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(EXEC_THREADS, 10) k_exec(DecodeArgs a) {
       e = read_seq_count(sp, ssz, &nbSeq, &modes, &hdr);
       if (e) { err = e; break; }
       if (fi.seq_err_block == blk && fi.seq_err_index == 0xFFFFFFFFu) { err = fi.seq_err_code; break; }
-      u64 litPos = 0;
+      u32 litPos = 0;
       if (nbSeq) {
         const SeqRec* r = recs + recRun; bool done = false;
         while (!done) {
@@ -429,9 +429,9 @@ __global__ void __launch_bounds__(EXEC_THREADS, 10) k_exec(DecodeArgs a) {
           const u32 incl = warp_incl_scan(tot, lane), lincl = warp_incl_scan(ll, lane);
           const u32 excl = incl - tot, mrel = excl + ll;   // group-relative output positions of literals / match
           // checks in the reference's order (:1278, :1279, :1290-1294)
-          const bool e1 = valid && (op + incl + whole > cap);
+          const bool e1 = valid && (incl + whole > cap - op);
           const bool e2 = valid && (litPos + lincl > litSize);
-          const bool e3 = valid && ((u64)off > op + mrel);
+          const bool e3 = valid && off > mrel && off - mrel > op;
           const unsigned bad = __ballot_sync(FULLMASK, e1 | e2 | e3);
           if (bad) {
             const u32 first = (u32)__ffs(bad) - 1;
@@ -500,13 +500,13 @@ __global__ void __launch_bounds__(EXEC_THREADS, 10) k_exec(DecodeArgs a) {
           r += cnt + (done ? 1 : 0);
         }
         if (err) break;
-        recRun = (u64)(r - recs);
+        recRun = (u32)(r - recs);
         if (fi.seq_err_block == blk) { err = fi.seq_err_code; break; }             // :1594 after the decodable prefix
       }
       // last literals (:1599-1605)
-      const u64 lastLL = litSize - litPos;
+      const u32 lastLL = litSize - litPos;
       if (lastLL > cap - op || dry) { err = ZE_dstSize_tooSmall; break; }
-      if (isRle) warp_fill(dst + op, (u8)rleByte, (u32)lastLL, lane); else warp_copy(dst + op, lit + litPos, (u32)lastLL, lane);
+      if (isRle) warp_fill(dst + op, (u8)rleByte, lastLL, lane); else warp_copy(dst + op, lit + litPos, lastLL, lane);
       op += lastLL;
       __syncwarp();
     }
