@@ -43,6 +43,7 @@ int env_int(const char* name, int dflt, int lo, int hi) {
 struct Device {
   int id = 0;
   cudaStream_t stream[NSTREAMS] = {};
+  cudaEvent_t descEv = nullptr;                 // descriptors of the current sub-batch are on the device
   // device memory
   u8 *d_src = nullptr, *d_dst = nullptr;       // staging for the host-pointer API
   u64 *d_srcOff = nullptr, *d_dstOff = nullptr; u32 *d_srcSize = nullptr, *d_dstCap = nullptr, *d_result = nullptr;
@@ -80,6 +81,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 int alloc_device(zstdb200_ctx* ctx, Device& d) {
   CK(cudaSetDevice(d.id));
   for (auto& s : d.stream) CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&d.descEv, cudaEventDisableTiming));
   const size_t items = ctx->maxItems;
   CK(cudaMalloc(&d.d_src, ctx->srcCap + 256));
   CK(cudaMalloc(&d.d_dst, ctx->dstSpan + 256));
@@ -107,6 +109,7 @@ void free_device(Device& d) {
   cudaFreeHost(d.h_src); cudaFreeHost(d.h_dst); cudaFreeHost(d.h_srcOff); cudaFreeHost(d.h_dstOff); cudaFreeHost(d.h_srcSize);
   cudaFreeHost(d.h_dstCap); cudaFreeHost(d.h_result);
   for (auto& s : d.stream) if (s) cudaStreamDestroy(s);
+  if (d.descEv) cudaEventDestroy(d.descEv);
 }
 
 struct Range { size_t lo, hi; };
@@ -199,8 +202,18 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     }
   }
   cudaError_t e;
-  if (j.op == Op::Decompress)
-    for (int k = 0; k < NSTREAMS; k++) { e = cudaMemsetAsync(d.d_more + k, 0, 4, d.stream[k]); if (e) return fail("memset", e); d.h_more[k] = 0; }
+  // Small copies cost the copy engines about as much as a megabyte each, and they queue between the slices'
+  // payload copies: descriptors go up once per sub-batch, results and counters come back once at its end.
+  {
+    cudaStream_t s0 = d.stream[0];
+    e = cudaMemsetAsync(d.d_more, 0, NSTREAMS * 4, s0); if (e) return fail("memset", e);
+    e = cudaMemcpyAsync(d.d_srcOff, d.h_srcOff, m * 8, cudaMemcpyHostToDevice, s0); if (e) return fail("H2D desc", e);
+    e = cudaMemcpyAsync(d.d_dstOff, d.h_dstOff, m * 8, cudaMemcpyHostToDevice, s0); if (e) return fail("H2D desc", e);
+    e = cudaMemcpyAsync(d.d_srcSize, d.h_srcSize, m * 4, cudaMemcpyHostToDevice, s0); if (e) return fail("H2D desc", e);
+    e = cudaMemcpyAsync(d.d_dstCap, d.h_dstCap, m * 4, cudaMemcpyHostToDevice, s0); if (e) return fail("H2D desc", e);
+    e = cudaEventRecord(d.descEv, s0); if (e) return fail("event", e);
+    for (int k = 1; k < NSTREAMS; k++) { e = cudaStreamWaitEvent(d.stream[k], d.descEv, 0); if (e) return fail("event wait", e); }
+  }
   for (size_t s = 0; s < slices.size(); s++) {
     const size_t a = slices[s].lo, b = slices[s].hi, cnt = b - a;
     cudaStream_t st = d.stream[s % nStreams];
@@ -212,16 +225,11 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
       for (size_t k = a; k < b; k++) if (d.h_srcSize[k]) memcpy(d.h_src + d.h_srcOff[k], j.src[lo + k], d.h_srcSize[k]);
       if (inHi > inLo) { e = cudaMemcpyAsync(d.d_src + inLo, d.h_src + inLo, inHi - inLo, cudaMemcpyHostToDevice, st); if (e) return fail("H2D src", e); }
     }
-    e = cudaMemcpyAsync(d.d_srcOff + a, d.h_srcOff + a, cnt * 8, cudaMemcpyHostToDevice, st); if (e) return fail("H2D desc", e);
-    e = cudaMemcpyAsync(d.d_dstOff + a, d.h_dstOff + a, cnt * 8, cudaMemcpyHostToDevice, st); if (e) return fail("H2D desc", e);
-    e = cudaMemcpyAsync(d.d_srcSize + a, d.h_srcSize + a, cnt * 4, cudaMemcpyHostToDevice, st); if (e) return fail("H2D desc", e);
-    e = cudaMemcpyAsync(d.d_dstCap + a, d.h_dstCap + a, cnt * 4, cudaMemcpyHostToDevice, st); if (e) return fail("H2D desc", e);
     int nl = 0;
     if (j.op == Op::Decompress) {
       DecodeArgs ar{d.d_src, d.d_srcOff + a, d.d_srcSize + a, d.d_dst, d.d_dstOff + a, d.d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
                     d.d_info + a, d.d_lit, d.d_seq, 0, d.d_more + (s % nStreams)};
       e = decode_launch(ar, st, &nl);
-      if (!e) e = cudaMemcpyAsync(d.h_more + (s % nStreams), d.d_more + (s % nStreams), 4, cudaMemcpyDeviceToHost, st);   // cumulative per stream
     } else {
       EncodeArgs ar{d.d_src, d.d_srcOff + a, d.d_srcSize + a, d.d_dst, d.d_dstOff + a, d.d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
                     j.level, j.checksum, (u32)(s % nStreams)};
@@ -229,7 +237,6 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     }
     *launches += nl;
     if (e) return fail("kernel launch", e);
-    e = cudaMemcpyAsync(d.h_result + a, d.d_result + a, cnt * 4, cudaMemcpyDeviceToHost, st); if (e) return fail("D2H result", e);
     const size_t outLo = d.h_dstOff[a], outHi = d.h_dstOff[b - 1] + d.h_dstCap[b - 1];
     if (outHi > outLo) {
       u8* hostDst = dstDirect ? dstBase + outLo : d.h_dst + outLo;
@@ -237,6 +244,9 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     }
   }
   for (auto& st : d.stream) { e = cudaStreamSynchronize(st); if (e) return fail("stream sync", e); }
+  e = cudaMemcpyAsync(d.h_result, d.d_result, m * 4, cudaMemcpyDeviceToHost, d.stream[0]); if (e) return fail("D2H result", e);
+  e = cudaMemcpyAsync(d.h_more, d.d_more, NSTREAMS * 4, cudaMemcpyDeviceToHost, d.stream[0]); if (e) return fail("D2H counters", e);
+  e = cudaStreamSynchronize(d.stream[0]); if (e) return fail("stream sync", e);
   u32 anyMore = 0;
   for (int k = 0; k < NSTREAMS; k++) anyMore |= d.h_more[k];
   if (j.op == Op::Decompress && anyMore) {
