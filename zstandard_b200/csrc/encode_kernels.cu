@@ -5,8 +5,10 @@
 //                                        hashes resolved with __match_any_sync, candidates verified in parallel, the
 //                                        first hit wins (greedy parse), match length by warp ballot; sequence store
 //                                        and literals go to HBM scratch
-//   k_enc_entropy      : thread / frame  Huffman + FSE table construction, bitstream encode, block + frame assembly
-//                                        (zb_encode.cuh) from the stored sequences
+//   k_enc_entropy      : warp / frame    literals: histogram, Huffman code (symbols sorted across the warp), 4 streams on
+//                                        4 lanes; sequences: codes + histograms in parallel, FSE tables (lane 0), the
+//                                        three FSE state chains on three lanes and the bitstream packed by all lanes
+//                                        through a warp prefix sum of field widths; block + frame assembly
 //   k_enc_xxh          : 4 lanes / frame XXH64 content checksum appended to the frame (xxh_device.cuh)
 //
 // Frames are independent, so there is no inter-warp communication.  HBM scratch of the match stage is addressed
@@ -233,7 +235,7 @@ __host__ __device__ inline size_t slot_bytes() { return align16((size_t)kBlockSe
 // Same decisions and same bytes as enc_literals / enc_sequences / encode_frame_with in zb_encode.cuh (the
 // serial replay), with the data-parallel parts spread over the lanes: histograms (shared-memory atomics),
 // the four Huffman streams (one lane each, into scratch, then concatenated), code computation, block copies.
-// Table construction (Huffman tree, FSE normalisation) and the FSE bitstream stay on lane 0.
+// Table construction (Huffman tree, FSE normalisation) stays on lane 0.
 struct EntWarp {
   u32 hist[256];
   HufEnc he;
@@ -256,6 +258,12 @@ __device__ __forceinline__ void wcopy(u8* dst, const u8* src, u32 n, u32 lane) {
   }
   for (u32 i = lane; i < n; i += 32) dst[i] = src[i];
 }
+__device__ __forceinline__ u32 warp_scan_incl(u32 v, u32 lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(FULLMASK, v, d); if (lane >= (u32)d) v += t; }
+  return v;
+}
+struct EntLut { u32 ll[36], ml[53]; };   // per code: base | extra-bit count << 24 (ll_info / ml_info), shared by the CTA's warps
 __device__ __forceinline__ u32 wmax(u32 v) {
 #pragma unroll
   for (int d = 16; d >= 1; d >>= 1) { const u32 t = __shfl_xor_sync(FULLMASK, v, d); v = t > v ? t : v; }
@@ -356,7 +364,7 @@ __device__ u32 warp_enc_literals(u8* out, u32 cap, const u8* lits, u32 n, EntWar
 }
 
 // sequences section; returns bytes written, 0 on failure (mirror of enc_sequences)
-__device__ u32 warp_enc_sequences(u8* out, u32 cap, const SeqStore& st, u8* codes, EntWarp& w, int level, u32 lane) {
+__device__ u32 warp_enc_sequences(u8* out, u32 cap, const SeqStore& st, u8* codes, EntWarp& w, const EntLut& lut, int level, u32 lane) {
   const u32 nbSeq = st.n;
   if (cap < 4) return 0;
   u32 op = 0;
@@ -387,33 +395,99 @@ __device__ u32 warp_enc_sequences(u8* out, u32 cap, const SeqStore& st, u8* code
   }
   o2w = __shfl_sync(FULLMASK, o2w, 0);
   if (o2w) {
-    // The bitstream is one serial chain (lane 0), but its inputs need not come from HBM one dependent load at a
-    // time: the warp stages the sequences and their codes through shared memory, kStage at a time, last to first
-    // (hist and he are free once the literals are coded).
-    constexpr u32 kStage = 128;
-    static_assert(sizeof(w.hist) >= kStage * 8 && sizeof(w.he) >= kStage * 4, "staging buffers");
-    u32* const sq = w.hist; u32* const sc = reinterpret_cast<u32*>(&w.he);
-    SeqBits b; bool first = true;
-    for (u32 hi = nbSeq; hi > 0;) {
-      const u32 lo = hi > kStage ? hi - kStage : 0, cnt = hi - lo;
+    // ---- bitstream (mirror of enc_seq_bitstream: same bits, found in parallel) ----
+    // The three FSE state chains are serial, but independent of each other and of the bit positions: lanes 0-2 walk
+    // them for a chunk of kChunk sequences (last to first) and leave each sequence's state bits in shared memory.
+    // All lanes then size their sequences' six fields, a warp prefix sum gives every field its bit offset, and the
+    // fields are OR-ed into a shared-memory bit buffer that is flushed to the frame in whole aligned words.
+    constexpr u32 kChunk = 64, kBufWords = 184;   // a sequence is <= 88 bits: 64 * 88 + 31 carried bits < 184 * 32
+    static_assert(sizeof(w.hist) >= kChunk * 16 && sizeof(w.he) >= (kChunk + kBufWords) * 4, "chunk buffers");
+    u32* const sq = w.hist;                                     // [2 * kChunk] the chunk's sequences, write order
+    u32* const sbLL = w.hist + 2 * kChunk; u32* const sbML = w.hist + 3 * kChunk;
+    u32* const sbOF = reinterpret_cast<u32*>(&w.he);           // code, later state bits | nbBits << 16 | code << 24
+    u32* const bitbuf = sbOF + kChunk;
+    u8* const s0 = out + o2w;
+    u32* const gbase = reinterpret_cast<u32*>((uintptr_t)s0 & ~(uintptr_t)3);
+    u32 G = 8 * (u32)((uintptr_t)s0 & 3);                       // stream bit position relative to gbase
+    const u32 capBits = 8 * (u32)((out + cap) - reinterpret_cast<u8*>(gbase));
+    u32 carry = 0;
+    if (G) { if (lane == 0) carry = gbase[0] & ((1u << G) - 1); carry = __shfl_sync(FULLMASK, carry, 0); }   // bytes before the stream ride along
+    const FseCTable& myCt = w.ct[lane == 0 ? 0 : (lane == 1 ? 2 : 1)];   // lane 0: LL, 1: ML, 2: OF
+    u32* const mySb = lane == 0 ? sbLL : (lane == 1 ? sbML : sbOF);
+    u32 state = 0; bool fits = true;
+    for (u32 hi = nbSeq; hi > 0 && fits;) {
+      const u32 lo = hi > kChunk ? hi - kChunk : 0, cnt = hi - lo;
       __syncwarp();
-      for (u32 i = lane; i < cnt; i += 32) {
-        const uint2 s2 = *reinterpret_cast<const uint2*>(st.seqs + 2 * (size_t)(lo + i));
-        sq[2 * i] = s2.x; sq[2 * i + 1] = s2.y;
-        sc[i] = (u32)llc[lo + i] | ((u32)ofc[lo + i] << 8) | ((u32)mlc[lo + i] << 16);
+      for (u32 t = lane; t < cnt; t += 32) {                   // t-th sequence written = sequence hi - 1 - t
+        const u32 n = hi - 1 - t;
+        const uint2 s2 = *reinterpret_cast<const uint2*>(st.seqs + 2 * (size_t)n);
+        sq[2 * t] = s2.x; sq[2 * t + 1] = s2.y;
+        sbLL[t] = llc[n]; sbML[t] = mlc[n]; sbOF[t] = ofc[n];
       }
+      for (u32 i = lane; i < kBufWords; i += 32) bitbuf[i] = i == 0 ? carry : 0;
       __syncwarp();
-      if (lane == 0) {
-        for (i32 i = (i32)cnt - 1; i >= 0; i--) {
-          const u32 a = sq[2 * i], bb = sq[2 * i + 1], c = sc[i];
-          const u32 ll = (a & 0xFFFF) | ((bb >> 31) << 16), mlm3 = (a >> 16) | (((bb >> 30) & 1) << 16), ob = bb & 0x3FFFFFFFu;   // seq_get
-          if (first) { seqbits_first(b, out + o2w, out + cap, w.ct[0], w.ct[1], w.ct[2], ll, ob, mlm3, c & 0xFF, (c >> 8) & 0xFF, c >> 16); first = false; }
-          else seqbits_next(b, w.ct[0], w.ct[1], w.ct[2], ll, ob, mlm3, c & 0xFF, (c >> 8) & 0xFF, c >> 16);
+      if (lane < 3) {
+        for (u32 t = 0; t < cnt; t++) {
+          const u32 code = mySb[t];
+          if (hi == nbSeq && t == 0) { fse_init_state(myCt, state, code); mySb[t] = code << 24; }   // the first symbol costs no bits
+          else {
+            const u32 nb = (state + myCt.deltaNbBits[code]) >> 16;                                  // fse_encode
+            mySb[t] = (state & ((1u << nb) - 1)) | (nb << 16) | (code << 24);
+            state = myCt.stateTable[(i32)(state >> nb) + myCt.deltaFindState[code]];
+          }
         }
       }
+      __syncwarp();
+      u32 run = G & 31;
+      for (u32 t0 = 0; t0 < cnt; t0 += 32) {
+        const u32 t = t0 + lane; const bool valid = t < cnt;
+        u32 fv[6], fn[6], len = 0;
+        if (valid) {
+          const u32 a = sq[2 * t], bb = sq[2 * t + 1], eLL = sbLL[t], eML = sbML[t], eOF = sbOF[t];
+          const u32 ll = (a & 0xFFFF) | ((bb >> 31) << 16), mlm3 = (a >> 16) | (((bb >> 30) & 1) << 16), ob = bb & 0x3FFFFFFFu;   // seq_get
+          const u32 lc = eLL >> 24, mc = eML >> 24, oc = eOF >> 24;
+          const u32 iLL = lut.ll[lc], iML = lut.ml[mc];
+          fv[0] = eOF & 0xFFFF; fn[0] = (eOF >> 16) & 0xFF;    // write order: OF, ML, LL state bits, then litLength,
+          fv[1] = eML & 0xFFFF; fn[1] = (eML >> 16) & 0xFF;    // matchLength and offset extra bits
+          fv[2] = eLL & 0xFFFF; fn[2] = (eLL >> 16) & 0xFF;
+          fv[3] = ll - (iLL & 0xFFFFFF); fn[3] = iLL >> 24;
+          fv[4] = mlm3 + 3 - (iML & 0xFFFFFF); fn[4] = iML >> 24;
+          fv[5] = ob - (1u << oc); fn[5] = oc;
+#pragma unroll
+          for (int k = 0; k < 6; k++) len += fn[k];
+        }
+        const u32 incl = warp_scan_incl(len, lane);
+        u32 pos = run + incl - len;
+        if (valid) {
+#pragma unroll
+          for (int k = 0; k < 6; k++) {
+            if (fn[k]) {
+              const u32 wi = pos >> 5, sh = pos & 31;
+              atomicOr(&bitbuf[wi], fv[k] << sh);
+              if (sh + fn[k] > 32) atomicOr(&bitbuf[wi + 1], fv[k] >> (32 - sh));
+              pos += fn[k];
+            }
+          }
+        }
+        run += __shfl_sync(FULLMASK, incl, 31);
+      }
+      __syncwarp();
+      const u32 words = run >> 5, wordBase = G >> 5;
+      if ((G & ~31u) + run + 1 > capBits) { fits = false; break; }   // (+ the end mark) out of room: the caller stores the block raw
+      for (u32 i = lane; i < words; i += 32) gbase[wordBase + i] = bitbuf[i];
+      carry = bitbuf[words];                                        // the incomplete word, if any, leads the next chunk
+      G = (G & ~31u) + run;
       hi = lo;
     }
-    if (lane == 0) { u8* e = seqbits_finish(b, w.ct[0], w.ct[1], w.ct[2]); if (e) total = (u32)(e - out); }
+    // state flush (ML, OF, LL) and end mark by lane 0, continuing from the carried bits
+    const u32 sLL = __shfl_sync(FULLMASK, state, 0), sML = __shfl_sync(FULLMASK, state, 1), sOF = __shfl_sync(FULLMASK, state, 2);
+    __syncwarp();
+    if (fits && lane == 0) {
+      BitWriter bw; bw.p = reinterpret_cast<u8*>(gbase + (G >> 5)); bw.end = out + cap; bw.acc = carry; bw.nb = G & 31; bw.ovf = false;
+      fse_flush_state(bw, w.ct[2], sML); fse_flush_state(bw, w.ct[1], sOF); fse_flush_state(bw, w.ct[0], sLL);
+      u8* e = bw_close(bw);
+      if (e) total = (u32)(e - out);
+    }
   }
   total = __shfl_sync(FULLMASK, total, 0);
   __syncwarp();
@@ -422,6 +496,10 @@ __device__ u32 warp_enc_sequences(u8* out, u32 cap, const SeqStore& st, u8* code
 
 __global__ void __launch_bounds__(128) k_enc_entropy(EncodeArgs a, EncodeScratch sc, u32 slot0, u32 nwarps) {
   __shared__ EntWarp sm[4];
+  __shared__ EntLut lut;
+  if (threadIdx.x < 36) lut.ll[threadIdx.x] = ll_info(threadIdx.x);
+  if (threadIdx.x < 53) lut.ml[threadIdx.x] = ml_info(threadIdx.x);
+  __syncthreads();
   const u32 lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const u32 wid = blockIdx.x * 4 + wib;
   if (wid >= nwarps) return;
@@ -472,7 +550,7 @@ __global__ void __launch_bounds__(128) k_enc_entropy(EncodeArgs a, EncodeScratch
           u8* body = dst + op + 3;
           const u32 l = warp_enc_literals(body, room, st.lits, st.nlits, w, tmp, lane);
           if (l) {
-            const u32 sq = warp_enc_sequences(body + l, room - l, st, codes, w, a.level, lane);
+            const u32 sq = warp_enc_sequences(body + l, room - l, st, codes, w, lut, a.level, lane);
             if (sq && l + sq < bsize) { csize = l + sq; compressed = true; }
           }
         }
