@@ -30,7 +30,8 @@ namespace {
 constexpr int NSTREAMS = 8;
 static_assert(NSTREAMS <= ENC_STREAM_PARTS, "one encoder slot partition per stream");
 constexpr size_t SLICE_BYTES_DEFAULT = 32u << 20;   // uncompressed bytes per slice (several slices per stream per GiB)
-constexpr size_t MIN_SLICE_ITEMS = 1024;             // and at least this many frames
+constexpr size_t MIN_SLICE_ITEMS_DECODE = 1024;      // and at least this many frames (decode kernels: one frame-time per launch)
+constexpr size_t MIN_SLICE_ITEMS_ENCODE = 512;       // the match kernel fills the GPU with 2-4 thousand frames: start early
 
 // tuning aids (not part of the ABI): ZSTDB200_STREAMS = streams actually used (1..NSTREAMS), ZSTDB200_SLICE_MB
 int env_int(const char* name, int dflt, int lo, int hi) {
@@ -197,6 +198,7 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
       size_t b = a, bytes = 0;
       // a slice is >= SLICE_BYTES and >= MIN_SLICE_ITEMS frames: the kernels take one frame-time however few frames
       // they are given, so slices of a few large frames would serialise on that latency
+      const size_t MIN_SLICE_ITEMS = j.op == Op::Decompress ? MIN_SLICE_ITEMS_DECODE : MIN_SLICE_ITEMS_ENCODE;
       while (b < m && (b - a < MIN_SLICE_ITEMS || bytes + std::max(d.h_dstCap[b], d.h_srcSize[b]) <= SLICE_BYTES)) { bytes += std::max(d.h_dstCap[b], d.h_srcSize[b]); b++; }
       slices.push_back({a, b}); a = b;
     }
