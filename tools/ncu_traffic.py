@@ -32,10 +32,12 @@ def main():
     for r in rows[2:]:
         if len(r) <= max(rd_i, wr_i):
             continue
-        name = r[name_i].split("(")[0].split("::")[-1].split("<")[0]
+        name = r[name_i].split("(")[0].split("::")[-1].split("<")[0].replace("void ", "").strip()
         rd = float(r[rd_i].replace(",", "")) * scale(units[rd_i])
         wr = float(r[wr_i].replace(",", "")) * scale(units[wr_i])
         ms = float(r[t_i].replace(",", "")) * scale(units[t_i])
+        if rd != rd or wr != wr:      # ncu could not collect the counters for this launch
+            continue
         rec[name] = {"dram_bytes": int(rd + wr), "dram_read": int(rd), "dram_write": int(wr), "ncu_ms": round(ms, 4)}   # last launch wins
     path = os.path.join(ROOT, "profiles", "traffic.json")
     allrec = json.load(open(path)) if os.path.exists(path) else {}

@@ -198,7 +198,8 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
       size_t b = a, bytes = 0;
       // a slice is >= SLICE_BYTES and >= MIN_SLICE_ITEMS frames: the kernels take one frame-time however few frames
       // they are given, so slices of a few large frames would serialise on that latency
-      const size_t MIN_SLICE_ITEMS = j.op == Op::Decompress ? MIN_SLICE_ITEMS_DECODE : MIN_SLICE_ITEMS_ENCODE;
+      static const int envMin = env_int("ZSTDB200_MIN_SLICE_ITEMS", 0, 0, 1 << 30);
+      const size_t MIN_SLICE_ITEMS = envMin ? (size_t)envMin : (j.op == Op::Decompress ? MIN_SLICE_ITEMS_DECODE : MIN_SLICE_ITEMS_ENCODE);
       while (b < m && (b - a < MIN_SLICE_ITEMS || bytes + std::max(d.h_dstCap[b], d.h_srcSize[b]) <= SLICE_BYTES)) { bytes += std::max(d.h_dstCap[b], d.h_srcSize[b]); b++; }
       slices.push_back({a, b}); a = b;
     }
