@@ -235,8 +235,8 @@ __device__ __forceinline__ u32 warp_incl_scan(u32 v, u32 lane) {
 __device__ __forceinline__ u32 warp_upper_bound(u32 incl, u32 x) {
   u32 j = 0;
 #pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) { u32 v = __shfl_sync(FULLMASK, incl, (j + s - 1) & 31); if (v <= x) j += s; }
-  return j & 31;
+  for (int s = 16; s >= 1; s >>= 1) { u32 v = __shfl_sync(FULLMASK, incl, j + s - 1); if (v <= x) j += s; }
+  return j;   // j + s - 1 <= 30 inside the loop and j <= 31 here: no lane index ever wraps
 }
 
 // Flattened copy of many short runs in units of one 4-byte-aligned destination word: run of lane j writes len_j
@@ -255,11 +255,10 @@ __device__ __forceinline__ void flat_copy_w(u8* g, const u8* src, u32 totalUnits
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) {
 #pragma unroll
-      for (int k = 0; k < U; k++) { const u32 x = __shfl_sync(FULLMASK, uincl, (j[k] + s - 1) & 31); if (x <= t[k]) j[k] += s; }
+      for (int k = 0; k < U; k++) { const u32 x = __shfl_sync(FULLMASK, uincl, j[k] + s - 1); if (x <= t[k]) j[k] += s; }
     }
 #pragma unroll
     for (int k = 0; k < U; k++) {
-      j[k] &= 31;
       dj[k] = __shfl_sync(FULLMASK, dpos, j[k]); ej[k] = __shfl_sync(FULLMASK, uexcl, j[k]);
       sj[k] = __shfl_sync(FULLMASK, spos, j[k]); nj[k] = __shfl_sync(FULLMASK, len, j[k]);
     }
@@ -300,8 +299,7 @@ __device__ __forceinline__ void flat_fill_w(u8* g, u32 fillWord, u32 totalUnits,
     for (int k = 0; k < U; k++) {
       const u32 t = t0 + 32 * k + lane; u32 j = 0;
 #pragma unroll
-      for (int s = 16; s >= 1; s >>= 1) { const u32 x = __shfl_sync(FULLMASK, uincl, (j + s - 1) & 31); if (x <= t) j += s; }
-      j &= 31;
+      for (int s = 16; s >= 1; s >>= 1) { const u32 x = __shfl_sync(FULLMASK, uincl, j + s - 1); if (x <= t) j += s; }
       const u32 dj = __shfl_sync(FULLMASK, dpos, j), ej = __shfl_sync(FULLMASK, uexcl, j), nj = __shfl_sync(FULLMASK, len, j);
       if (t < totalUnits) {
         u8* const d0 = g + dj;
@@ -329,11 +327,10 @@ __device__ __forceinline__ void flat_copy_m4(u8* g, u32 totalUnits, u32 uincl, u
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) {
 #pragma unroll
-      for (int k = 0; k < U; k++) { const u32 x = __shfl_sync(FULLMASK, uincl, (j[k] + s - 1) & 31); if (x <= t[k]) j[k] += s; }
+      for (int k = 0; k < U; k++) { const u32 x = __shfl_sync(FULLMASK, uincl, j[k] + s - 1); if (x <= t[k]) j[k] += s; }
     }
 #pragma unroll
     for (int k = 0; k < U; k++) {
-      j[k] &= 31;
       dj[k] = __shfl_sync(FULLMASK, mrel, j[k]); ej[k] = __shfl_sync(FULLMASK, uexcl, j[k]);
       oj[k] = __shfl_sync(FULLMASK, off, j[k]); nj[k] = __shfl_sync(FULLMASK, len, j[k]);
     }
