@@ -89,3 +89,44 @@ def test_destination_too_small_is_per_item(gpu_ctx):
     res, dsts = _compress(gpu_ctx, [a, b, a], 3, True, caps=[6000, 50, 6000])
     assert not helpers.is_err(int(res[0])) and not helpers.is_err(int(res[2]))
     assert int(res[1]) == helpers.err(70)
+
+
+def test_device_pointer_api_and_kernel_times(gpu_ctx):
+    """zstdb200_compress_batch_device(_timed): device-resident chunks in, frames out; every frame decodes back."""
+    import torch
+    from tools import corpus, zstd_ref
+    import zstandard_b200 as zb
+    chunk, n = 32768, 96
+    raw = corpus.make("mixed", chunk * n)
+    bound = (zb.ZStdCompress.CompressBound(chunk) + 15) // 16 * 16
+    dev = torch.device("cuda:0")
+    t_src = torch.zeros(chunk * n + 64, dtype=torch.uint8, device=dev)
+    t_src[:chunk * n] = torch.from_numpy(raw).to(dev)
+    t_dst = torch.zeros(n * bound + 64, dtype=torch.uint8, device=dev)
+    t_soff = torch.arange(n, dtype=torch.int64, device=dev) * chunk
+    t_doff = torch.arange(n, dtype=torch.int64, device=dev) * bound
+    t_ssz = torch.full((n,), chunk, dtype=torch.int32, device=dev)
+    t_cap = torch.full((n,), bound, dtype=torch.int32, device=dev)
+    t_res = torch.zeros(n, dtype=torch.int32, device=dev)
+    st = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    for level in (1, 2, 3):
+        ms = gpu_ctx.compress_batch_device_timed(level, True, t_src.data_ptr(), t_soff.data_ptr(), t_ssz.data_ptr(), t_dst.data_ptr(),
+                                                 t_doff.data_ptr(), t_cap.data_ptr(), t_res.data_ptr(), n, stream=st.cuda_stream)
+        assert set(ms) == {"k_enc_match", "k_enc_entropy", "k_enc_xxh"} and all(v >= 0 for v in ms.values())
+        res = t_res.cpu().numpy().view(np.uint32)
+        out = t_dst.cpu().numpy()
+        for k in range(n):
+            assert not helpers.is_err(int(res[k]))
+            assert zstd_ref.decompress(out[k * bound:k * bound + int(res[k])].tobytes(), chunk) == raw[k * chunk:(k + 1) * chunk].tobytes()
+
+
+def test_bad_arguments_are_batch_level_errors(gpu_ctx):
+    import zstandard_b200 as zb
+    src = np.frombuffer(b"x" * 100, dtype=np.uint8)
+    dst = np.zeros(200, dtype=np.uint8)
+    with pytest.raises(RuntimeError):
+        gpu_ctx.compress_batch([src], [dst], level=7)          # only levels 1..3 exist
+    assert len(gpu_ctx.compress_batch([], [])) == 0           # an empty batch is not an error
+    assert len(gpu_ctx.decompress_batch([], [])) == 0
+    assert zb.ZStdCompress.CompressBound(0) > 0
