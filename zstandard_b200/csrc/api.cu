@@ -199,8 +199,12 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
       // a slice is >= SLICE_BYTES and >= MIN_SLICE_ITEMS frames: the kernels take one frame-time however few frames
       // they are given, so slices of a few large frames would serialise on that latency
       static const int envMin = env_int("ZSTDB200_MIN_SLICE_ITEMS", 0, 0, 1 << 30);
-      const size_t MIN_SLICE_ITEMS = envMin ? (size_t)envMin : (j.op == Op::Decompress ? MIN_SLICE_ITEMS_DECODE : MIN_SLICE_ITEMS_ENCODE);
-      while (b < m && (b - a < MIN_SLICE_ITEMS || bytes + std::max(d.h_dstCap[b], d.h_srcSize[b]) <= SLICE_BYTES)) { bytes += std::max(d.h_dstCap[b], d.h_srcSize[b]); b++; }
+      const size_t minItems = envMin ? (size_t)envMin : (j.op == Op::Decompress ? MIN_SLICE_ITEMS_DECODE : MIN_SLICE_ITEMS_ENCODE);
+      // The first slices are smaller: output can only start to leave once a slice's kernels are done (one frame-time
+      // however small the slice), and the D2H engine then has to be fed without a gap while the big slices finish.
+      const size_t k = slices.size(), shrink = j.op == Op::Decompress ? (k < 2 ? 4 : (k < 4 ? 2 : 1)) : 1;
+      const size_t wantItems = std::max<size_t>(1, minItems / shrink), wantBytes = SLICE_BYTES / shrink;
+      while (b < m && (b - a < wantItems || bytes + std::max(d.h_dstCap[b], d.h_srcSize[b]) <= wantBytes)) { bytes += std::max(d.h_dstCap[b], d.h_srcSize[b]); b++; }
       slices.push_back({a, b}); a = b;
     }
   }
@@ -217,6 +221,9 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     e = cudaEventRecord(d.descEv, s0); if (e) return fail("event", e);
     for (int k = 1; k < NSTREAMS; k++) { e = cudaStreamWaitEvent(d.stream[k], d.descEv, 0); if (e) return fail("event wait", e); }
   }
+  static const bool trace = getenv("ZSTDB200_TRACE") != nullptr;   // per-slice timeline on stderr (tuning aid)
+  std::vector<cudaEvent_t> tev;
+  if (trace) { tev.resize(1 + 3 * slices.size()); for (auto& x : tev) cudaEventCreate(&x); cudaEventRecord(tev[0], d.stream[0]); }
   for (size_t s = 0; s < slices.size(); s++) {
     const size_t a = slices[s].lo, b = slices[s].hi, cnt = b - a;
     cudaStream_t st = d.stream[s % nStreams];
@@ -228,6 +235,7 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
       for (size_t k = a; k < b; k++) if (d.h_srcSize[k]) memcpy(d.h_src + d.h_srcOff[k], j.src[lo + k], d.h_srcSize[k]);
       if (inHi > inLo) { e = cudaMemcpyAsync(d.d_src + inLo, d.h_src + inLo, inHi - inLo, cudaMemcpyHostToDevice, st); if (e) return fail("H2D src", e); }
     }
+    if (trace) cudaEventRecord(tev[1 + 3 * s], st);
     int nl = 0;
     if (j.op == Op::Decompress) {
       DecodeArgs ar{d.d_src, d.d_srcOff + a, d.d_srcSize + a, d.d_dst, d.d_dstOff + a, d.d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
@@ -240,13 +248,23 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     }
     *launches += nl;
     if (e) return fail("kernel launch", e);
+    if (trace) cudaEventRecord(tev[2 + 3 * s], st);
     const size_t outLo = d.h_dstOff[a], outHi = d.h_dstOff[b - 1] + d.h_dstCap[b - 1];
     if (outHi > outLo) {
       u8* hostDst = dstDirect ? dstBase + outLo : d.h_dst + outLo;
       e = cudaMemcpyAsync(hostDst, d.d_dst + outLo, outHi - outLo, cudaMemcpyDeviceToHost, st); if (e) return fail("D2H dst", e);
     }
+    if (trace) cudaEventRecord(tev[3 + 3 * s], st);
   }
   for (auto& st : d.stream) { e = cudaStreamSynchronize(st); if (e) return fail("stream sync", e); }
+  if (trace) {
+    for (size_t s = 0; s < slices.size(); s++) {
+      float t1 = 0, t2 = 0, t3 = 0;
+      cudaEventElapsedTime(&t1, tev[0], tev[1 + 3 * s]); cudaEventElapsedTime(&t2, tev[0], tev[2 + 3 * s]); cudaEventElapsedTime(&t3, tev[0], tev[3 + 3 * s]);
+      fprintf(stderr, "[zstdb200] slice %2zu items %6zu: h2d done %7.3f  kernels done %7.3f  d2h done %7.3f ms\n", s, slices[s].hi - slices[s].lo, t1, t2, t3);
+    }
+    for (auto& x : tev) cudaEventDestroy(x);
+  }
   e = cudaMemcpyAsync(d.h_result, d.d_result, m * 4, cudaMemcpyDeviceToHost, d.stream[0]); if (e) return fail("D2H result", e);
   e = cudaMemcpyAsync(d.h_more, d.d_more, NSTREAMS * 4, cudaMemcpyDeviceToHost, d.stream[0]); if (e) return fail("D2H counters", e);
   e = cudaStreamSynchronize(d.stream[0]); if (e) return fail("stream sync", e);
