@@ -215,18 +215,6 @@ __global__ void __launch_bounds__(32) k_enc_match(EncodeArgs a, EncodeScratch sc
   }
 }
 
-// sequences left by k_enc_match
-struct StoredMatcher {
-  u8* lits0; u32* seqs0; const BlockMeta* meta;
-  __host__ __device__ bool operator()(SeqStore& st, u32 blk, const u8*, u32 bsize, bool isRle) {
-    if (isRle || bsize < 64) return false;
-    st.seqs = seqs0 + 2 * (size_t)blk * kBlockSeqCap; st.n = meta[blk].nseq; st.cap = kBlockSeqCap;
-    st.lits = lits0 + (size_t)blk * BLOCKSIZE_MAX; st.nlits = meta[blk].nlits;
-    return true;
-  }
-  __host__ __device__ void done(bool) {}
-};
-
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 static constexpr u32 kStreamTmp = 48 * 1024;   // worst case of one Huffman stream: 32 Ki symbols x 11 bits
 __host__ __device__ inline size_t slot_bytes() { return align16((size_t)kBlockSeqCap * 3) + 4 * (size_t)kStreamTmp; }

@@ -760,7 +760,8 @@ ZB_HD u32 enc_sequences(u8* out, u32 cap, const SeqStore& st, u8* codes, u16* ct
 //
 // `blockSeqs(st, blockIndex, bstart, bsize)` supplies the block's sequence store: either by running a match
 // finder right here (SerialMatcher: the thread-per-frame replay used by tests/hostsim) or by pointing at what
-// the warp-parallel match kernel left in HBM (StoredMatcher, encode_kernels.cu).
+// an emulation of the warp-parallel match kernel (WarpMatcher, tests/hostsim).  k_enc_entropy mirrors this function
+// warp-wide on what k_enc_match left in HBM (encode_kernels.cu).
 // Block bodies are written straight into dst and replaced by a raw copy when they do not pay.
 template <class BlockSeqs>
 ZB_HD u32 encode_frame_with(const u8* src, u32 size, u8* dst, u32 cap, int level, int checksum, u8* codes, u16* ctables, u8* symScratch,
