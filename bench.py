@@ -102,7 +102,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.005)
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
@@ -292,8 +292,6 @@ def main():
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
     launches = ctx.kernel_launches - l0
-    sampler.stop_flag = True
-    sampler.join()
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -344,6 +342,8 @@ def main():
     for _ in range(args.steps):
         step_e2e()
     e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True      # clocks are sampled through both timed regions (device-resident and host-buffer)
+    sampler.join()
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
