@@ -608,11 +608,14 @@ u32 decodeSeqHeaders(DCtx& d, int* nbSeqPtr, const u8* src, u32 srcSize) {
   u32 LLt = src[ip] >> 6, OFt = (src[ip] >> 4) & 3, MLt = (src[ip] >> 2) & 3; ip++;
   const DefaultTables& df = defaults();
   u32 h = buildSeqTable(d.LLspace, d.LL, LLt, MaxLL, LLFSELog, src + ip, (u32)(iend - ip), LL_base, LL_bits, &df.LL, d.fseEntropy);
-  if (is_err(h)) return ERR(E_corruption_detected); ip += h;
+  if (is_err(h)) return ERR(E_corruption_detected);
+  ip += h;
   h = buildSeqTable(d.OFspace, d.OF, OFt, MaxOff, OffFSELog, src + ip, (u32)(iend - ip), OF_base, OF_bits, &df.OF, d.fseEntropy);
-  if (is_err(h)) return ERR(E_corruption_detected); ip += h;
+  if (is_err(h)) return ERR(E_corruption_detected);
+  ip += h;
   h = buildSeqTable(d.MLspace, d.ML, MLt, MaxML, MLFSELog, src + ip, (u32)(iend - ip), ML_base, ML_bits, &df.ML, d.fseEntropy);
-  if (is_err(h)) return ERR(E_corruption_detected); ip += h;
+  if (is_err(h)) return ERR(E_corruption_detected);
+  ip += h;
   return (u32)ip;
 }
 

@@ -21,9 +21,12 @@ struct Sim {
   u32 llInfo[36], mlInfo[53];
   Sim() : ll(512), ml(512), of(256) {
     u16 sn[53]; s16 norm[53];
-    for (int i = 0; i < 36; i++) norm[i] = kLLnorm[i]; build_seq_table(defLL, 1, norm, 35, 6, sn);
-    for (int i = 0; i < 29; i++) norm[i] = kOFnorm[i]; build_seq_table(defOF, 1, norm, 28, 5, sn);
-    for (int i = 0; i < 53; i++) norm[i] = kMLnorm[i]; build_seq_table(defML, 1, norm, 52, 6, sn);
+    for (int i = 0; i < 36; i++) norm[i] = kLLnorm[i];
+    build_seq_table(defLL, 1, norm, 35, 6, sn);
+    for (int i = 0; i < 29; i++) norm[i] = kOFnorm[i];
+    build_seq_table(defOF, 1, norm, 28, 5, sn);
+    for (int i = 0; i < 53; i++) norm[i] = kMLnorm[i];
+    build_seq_table(defML, 1, norm, 52, 6, sn);
     for (u32 i = 0; i < 36; i++) llInfo[i] = ll_info(i);
     for (u32 i = 0; i < 53; i++) mlInfo[i] = ml_info(i);
   }

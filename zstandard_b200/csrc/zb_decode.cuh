@@ -49,7 +49,8 @@ struct SeqFrameOut {
 __noinline__
 #endif
 ZB_HD u32 seq_emit_long(SeqRec* out, u32 n, u32 cap, u32 off, u32 ll, u32 ml) {
-  if (n < cap) rec_store(out + n, 0, ll + ml); n++;
+  if (n < cap) rec_store(out + n, 0, ll + ml);
+  n++;
   while (ll > 65535) { if (n < cap) rec_store(out + n, 1, 65535); n++; ll -= 65535; }
   while (ml > 65535) { if (n < cap) rec_store(out + n, off, ll | (65535u << 16)); n++; ll = 0; ml -= 65535; }
   if (n < cap) rec_store(out + n, off, ll | (ml << 16));

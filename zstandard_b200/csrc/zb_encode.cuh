@@ -424,7 +424,7 @@ struct HufEnc { HufCode code[256]; u8 weight[256]; u32 maxSym; u32 tableLog; };
 // Working arrays of huf_build (4 KB): callers choose where they live (the GPU kernel lends shared memory).
 // hash-table logs of the warp-parallel match finder (k_enc_match and its lock-step emulation in tests/hostsim)
 ZB_HD u32 enc_hlog_long(int level) { return level == 2 ? 13 : (level >= 3 ? 11 : 12); }
-ZB_HD u32 enc_hlog_short(int level) { return 12; }
+ZB_HD u32 enc_hlog_short(int /*level*/) { return 12; }
 
 struct HufBuildScratch { u32 nodeCount[512]; u16 parent[512]; u16 order[256]; u8 depth[512]; };
 
