@@ -235,3 +235,32 @@ def test_full_size_round_trip_properties(gpu_ctx, kind, chunk):
     want = np.array([d.size for d in dsts], dtype=np.uint32)
     assert (res == want).all(), [hex(int(r)) for r in res[res != want][:5]]
     assert (out == raw).all()
+
+
+def test_one_context_over_two_devices(oracle):
+    """one context fans a batch out over its devices by bytes, no collective; results are those of a
+    single device.  Skipped on single-GPU boxes."""
+    import torch
+    import zstandard_b200 as zb
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ctx = zb.Context(devices=[0, 1], max_batch_bytes=64 << 20)
+    try:
+        frames = helpers.make_frames(307, 150)
+        items = [(f, len(d)) for f, d in frames] + [(b"\xff" * 50, 10)]
+        res, dsts = _gpu_decode(ctx, items)
+        for (frame, cap), r, d in zip(items, res, dsts):
+            ro, oo, _ = oracle.decompress(frame, cap)
+            assert int(r) == ro
+            if not helpers.is_err(ro):
+                assert d[:ro].tobytes() == oo
+        payloads = [d for _, d in frames if len(d)]
+        outs = [np.zeros(zb.ZStdCompress.CompressBound(len(p)), dtype=np.uint8) for p in payloads]
+        cres = ctx.compress_batch(payloads, outs, level=3, checksum=True)
+        for p, r, o in zip(payloads, cres, outs):
+            assert not helpers.is_err(int(r))
+            ro, oo, _ = oracle.decompress(o[:int(r)].tobytes(), len(p))
+            assert ro == len(p) and oo == p
+        assert ctx.device_count == 2
+    finally:
+        ctx.close()

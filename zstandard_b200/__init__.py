@@ -133,6 +133,10 @@ class Context:
         return self._lib.zstdb200_kernel_launches(self._h)
 
     @property
+    def device_count(self):
+        return self._lib.zstdb200_device_count(self._h)
+
+    @property
     def max_items(self):
         return self._lib.zstdb200_max_items(self._h)
 

@@ -306,8 +306,18 @@ int run_host_batch(zstdb200_ctx* ctx, const Job& j, size_t n) {
   if (nd > 1 && subs.size() < nd) {
     std::vector<Range> cut;
     for (auto& r : subs) {
+      // equal shares of bytes (in + out), not of items: a raw-block frame costs a copy, a text frame a full decode
       const size_t parts = std::min(nd, r.hi - r.lo);
-      for (size_t p = 0; p < parts; p++) cut.push_back({r.lo + (r.hi - r.lo) * p / parts, r.lo + (r.hi - r.lo) * (p + 1) / parts});
+      uint64_t total = 0;
+      for (size_t i = r.lo; i < r.hi; i++) total += (uint64_t)j.srcSize[i] + j.dstCap[i] + 1;
+      size_t lo = r.lo; uint64_t acc = 0;
+      for (size_t p = 0; p < parts; p++) {
+        size_t hi = lo;
+        const uint64_t want = total * (p + 1) / parts;
+        while (hi < r.hi && (acc < want || hi == lo) && (r.hi - hi) > (parts - 1 - p)) { acc += (uint64_t)j.srcSize[hi] + j.dstCap[hi] + 1; hi++; }
+        if (p + 1 == parts) hi = r.hi;
+        cut.push_back({lo, hi}); lo = hi;
+      }
     }
     subs.swap(cut);
   }
