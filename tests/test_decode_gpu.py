@@ -264,3 +264,30 @@ def test_one_context_over_two_devices(oracle):
         assert ctx.device_count == 2
     finally:
         ctx.close()
+
+
+def test_batches_larger_than_the_context_arena_are_cut_into_sub_batches():
+    """A small context (4 MiB of arena) takes a 24 MiB batch in several sub-batches; an item that cannot fit at all is
+    a batch-level error (`zstdb200_last_error`), not a crash."""
+    import zstandard_b200 as zb
+    from tools import corpus, zstd_ref
+    ctx = zb.Context(max_batch_bytes=4 << 20)
+    try:
+        total, chunk = 24 << 20, 65536
+        raw = corpus.make("mixed", total)
+        blob, off = zstd_ref.compress_chunks(raw, chunk, level=3, checksum=True)
+        n = len(off) - 1
+        srcs = [blob[int(off[i]):int(off[i + 1])] for i in range(n)]
+        out = np.zeros(total, dtype=np.uint8)
+        dsts = [out[i * chunk:(i + 1) * chunk] for i in range(n)]
+        res = ctx.decompress_batch(srcs, dsts)
+        assert (res == chunk).all() and (out == raw).all()
+        chunks = [raw[i * chunk:(i + 1) * chunk] for i in range(n)]
+        outs = [np.zeros(zb.ZStdCompress.CompressBound(chunk), dtype=np.uint8) for _ in range(n)]
+        cres = ctx.compress_batch(chunks, outs, level=1, checksum=True)
+        for k in range(0, n, 11):
+            assert zstd_ref.decompress(outs[k][:int(cres[k])].tobytes(), chunk) == chunks[k].tobytes()
+        with pytest.raises(RuntimeError):
+            ctx.decompress_batch([srcs[0]], [np.zeros(8 << 20, dtype=np.uint8)])
+    finally:
+        ctx.close()
