@@ -291,3 +291,28 @@ def test_batches_larger_than_the_context_arena_are_cut_into_sub_batches():
             ctx.decompress_batch([srcs[0]], [np.zeros(8 << 20, dtype=np.uint8)])
     finally:
         ctx.close()
+
+
+def test_multi_megabyte_frames_with_large_windows(gpu_ctx, oracle):
+    """multi-block frames with windows far beyond one block (libzstd level 19 on 8 MiB: 8 MiB window,
+    repeat-mode tables, cross-block repeat offsets) decode bit-exact; the encoder's multi-block frames are accepted
+    by libzstd and by the oracle."""
+    import zstandard_b200 as zb
+    from tools import corpus, zstd_ref
+    items = []
+    for kind, n, lvl in (("log", 8 << 20, 19), ("tick", 6 << 20, 12), ("mixed", 5 << 20, 3), ("log", 3 << 20, 1)):
+        raw = corpus.make(kind, n).tobytes()
+        items.append((zstd_ref.compress(raw, lvl, checksum=True), raw))
+    dsts = [np.zeros(len(r), dtype=np.uint8) for _, r in items]
+    res = gpu_ctx.decompress_batch([f for f, _ in items], dsts)
+    for (f, raw), r, d in zip(items, res, dsts):
+        assert int(r) == len(raw) and d.tobytes() == raw
+    ro, oo, _ = oracle.decompress(items[0][0], len(items[0][1]))
+    assert ro == len(items[0][1]) and oo == items[0][1]
+    outs = [np.zeros(zb.ZStdCompress.CompressBound(len(r)), dtype=np.uint8) for _, r in items]
+    cres = gpu_ctx.compress_batch([r for _, r in items], outs, level=3)
+    for (f, raw), r, o in zip(items, cres, outs):
+        frame = o[:int(r)].tobytes()
+        assert zstd_ref.decompress(frame, len(raw)) == raw
+    ro, oo, _ = oracle.decompress(outs[3][:int(cres[3])].tobytes(), len(items[3][1]))
+    assert ro == len(items[3][1]) and oo == items[3][1]
