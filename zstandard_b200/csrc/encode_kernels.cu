@@ -224,7 +224,7 @@ __host__ __device__ inline size_t slot_bytes() { return align16((size_t)kBlockSe
 // serial replay), with the data-parallel parts spread over the lanes: histograms (shared-memory atomics),
 // the four Huffman streams (one lane each, into scratch, then concatenated), code computation, block copies.
 // Table construction (Huffman tree, FSE normalisation) stays on lane 0.
-struct EntWarp {
+struct __align__(16) EntWarp {
   u32 hist[256];
   HufEnc he;
   union {                        // the Huffman tree is built before any of the sequence tables exist
@@ -293,15 +293,25 @@ __device__ u32 warp_enc_literals(u8* out, u32 cap, const u8* lits, u32 n, EntWar
   u32 maxBits = fse_optimal_log(11, n, maxSym, 1); if (maxBits > 11) maxBits = 11;
   // sort the used symbols by (count, symbol) across the warp: rank = number of used symbols that sort before
   // (same order as huf_sort_symbols' stable insertion sort), then lane 0 builds the tree from shared memory
+  // keys count << 8 | symbol are distinct and order exactly as the insertion sort does; unused symbols get the
+  // largest key.  Every lane ranks its 8 symbols against all 256 keys, read four at a time.
+  u32* const keys = reinterpret_cast<u32*>(&w.he);              // 1 KB, free until the code is built
+  u32 myKey[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { const u32 s = 32 * k + lane, c = w.hist[s]; myKey[k] = c ? (c << 8) | s : 0xFFFFFFFFu; keys[s] = myKey[k]; }
+  __syncwarp();
+  u32 rank[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (u32 t = 0; t < 256; t += 4) {
+    const uint4 q = *reinterpret_cast<const uint4*>(keys + t);
+#pragma unroll
+    for (int k = 0; k < 8; k++) rank[k] += (q.x < myKey[k]) + (q.y < myKey[k]) + (q.z < myKey[k]) + (q.w < myKey[k]);
+  }
   u32 nUsed = 0;
-  for (u32 s0 = 0; s0 < 256; s0 += 32) {
-    const u32 s = s0 + lane, c = w.hist[s];
-    nUsed += __popc(__ballot_sync(FULLMASK, c != 0));
-    if (c) {
-      u32 rank = 0;
-      for (u32 t = 0; t <= maxSym; t++) { const u32 ct = w.hist[t]; rank += (ct != 0) && (ct < c || (ct == c && t < s)); }
-      w.hb.order[rank] = (u16)s;
-    }
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const bool used = myKey[k] != 0xFFFFFFFFu;
+    nUsed += __popc(__ballot_sync(FULLMASK, used));
+    if (used) w.hb.order[rank[k]] = (u16)(32 * k + lane);
   }
   __syncwarp();
   u32 ok = 0;
