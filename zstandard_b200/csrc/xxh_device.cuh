@@ -28,14 +28,14 @@ static __device__ u64 xxh64_group(const u8* p, u64 len, u32 sub, unsigned gmask,
     const u64 stripes = len / 32;
     const u8* q = p + 8 * sub;
     u64 i = 0;
-    // the accumulator chain is serial; keep 8 independent loads in flight ahead of it
-    for (; i + 8 <= stripes; i += 8) {
-      u64 x[8];
+    // the accumulator chain is serial; keep 16 independent loads in flight ahead of it
+    for (; i + 16 <= stripes; i += 16) {
+      u64 x[16];
 #pragma unroll
-      for (int k = 0; k < 8; k++) x[k] = ldg64u(q + 32 * k);
+      for (int k = 0; k < 16; k++) x[k] = ldg64u(q + 32 * k);
 #pragma unroll
-      for (int k = 0; k < 8; k++) v = xxh_round(v, x[k]);
-      q += 256;
+      for (int k = 0; k < 16; k++) v = xxh_round(v, x[k]);
+      q += 512;
     }
     for (; i < stripes; i++) { v = xxh_round(v, ldg64u(q)); q += 32; }
     u64 v1 = __shfl_sync(gmask, v, lead), v2 = __shfl_sync(gmask, v, lead + 1), v3 = __shfl_sync(gmask, v, lead + 2), v4 = __shfl_sync(gmask, v, lead + 3);
