@@ -575,9 +575,9 @@ cudaError_t decode_configure() {
 
 const char* const kDecodeKernelNames[DECODE_KERNELS] = {"k_parse", "k_huf", "k_seq", "k_exec", "k_xxh"};
 
-// The pipeline in two halves so that callers can put them on different streams: the entropy half is latency
-// bound (few warps per SM, shared-memory limited), the execute half is issue/LSU bound and needs no shared
-// memory, so the two co-reside on an SM when they belong to different slices of a batch.
+// The pipeline in two halves (entropy stages, execute stages).  They were split to overlap slices on different
+// streams; that measured slower (the execute warps starve the lone FSE warps of an SM), so decode_launch runs both
+// on one stream.
 cudaError_t decode_launch_entropy(const DecodeArgs& a, cudaStream_t st, int* launches, cudaEvent_t* marks) {
   if (a.n == 0) return cudaSuccess;
   if (marks) cudaEventRecord(marks[0], st);

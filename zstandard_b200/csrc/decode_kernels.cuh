@@ -29,7 +29,7 @@ size_t decode_seq_arena_bytes(u64 max_dst_bytes, u64 max_items);
 cudaError_t decode_configure();
 // enqueues the whole decode pipeline for one batch on `st`; *launches += number of kernels launched
 cudaError_t decode_launch(const DecodeArgs& a, cudaStream_t st, int* launches, cudaEvent_t* marks = nullptr);
-// the two halves of decode_launch, for callers that overlap slices on different streams
+// the two halves of decode_launch
 cudaError_t decode_launch_entropy(const DecodeArgs& a, cudaStream_t st, int* launches, cudaEvent_t* marks = nullptr);
 cudaError_t decode_launch_exec(const DecodeArgs& a, cudaStream_t st, int* launches, cudaEvent_t* marks = nullptr);
 // marks (optional): DECODE_KERNELS + 1 events recorded before the first kernel and after each kernel
