@@ -19,8 +19,9 @@ Reported:
                 kernel's DRAM bytes per launch from the committed ncu capture of this command (profiles/traffic.json)
 The other BASELINE.json configs are the same two workloads with other shapes: --corpus mixed (configs[3]), --corpus tick
 --chunk 4096..1048576 (configs[4]); profiles/ holds the lines measured for them.
-  cpu_baseline  decode: the oracle (C++ port of the reference decoder; the C# reference cannot run in this image);
-                compress: libzstd 1.5.5 (the reference has no compressor) — all host cores in both cases
+  cpu_baseline  decode: the oracle (C++ port of the reference decoder; the C# reference cannot run in this image), with
+                libzstd 1.5.5's own decoder beside it as `cpu_baseline_libzstd`; compress: libzstd 1.5.5 (the reference
+                has no compressor) — all host cores in every case
 `--impl reference` times that CPU baseline alone, rank 0 only, as the reference arm.
 """
 import argparse
@@ -165,6 +166,13 @@ class CpuBaseline:
             self.lib.oracle_decompress_batch.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_uint64, ctypes.c_int]
             self.lib.oracle_decompress_batch.restype = None
             self.kind, self.what = "port", "oracle = C++ restatement of the reference C# decoder, static frame partition over all cores"
+            # second CPU baseline (SURVEY.md §8d ii): libzstd 1.5.5 ZSTD_decompress on all cores (tools/zstd_mt.c)
+            self.zmt = None
+            zp = os.path.join(ROOT, "tools", "_build", "libzstdmt.so")
+            if os.path.exists(zp):
+                self.zmt = ctypes.CDLL(zp)
+                self.zmt.zmt_decompress.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64,
+                                                    ctypes.c_uint64, ctypes.c_int]
         else:
             self.kind, self.what = "port", ("libzstd 1.5.5 ZSTD_compress2 (the reference ships no compressor; libzstd is the stand-in "
                                              "comparator), one context per core")
@@ -182,6 +190,25 @@ class CpuBaseline:
             zstd_ref.compress_chunks(w["raw"], w["chunk"], level=self.args.level, checksum=True, threads=self.cores)
             dt = time.perf_counter() - t
         return dt, w["total"]
+
+
+def libzstd_decode_baseline(cb):
+    """-> {"value": GB/s, ...} of libzstd's own decoder on all cores over the same frames, or None."""
+    if getattr(cb, "zmt", None) is None:
+        return None
+    w = cb.w
+    off = np.ascontiguousarray(w["src_off"], dtype=np.uint64)
+    call = lambda: cb.zmt.zmt_decompress(w["src"].ctypes.data, off.ctypes.data, w["n"], cb.out.ctypes.data, w["chunk"], w["total"], cb.cores)
+    if call() != 0:
+        return None
+    tt, runs = 0.0, 0
+    while tt < 1.5 and runs < 20:
+        t = time.perf_counter()
+        call()
+        tt += time.perf_counter() - t
+        runs += 1
+    return {"value": round(w["total"] * runs / tt / 1e9, 3), "unit": "GB/s", "cores": cb.cores, "kind": "libzstd 1.5.5 ZSTD_decompress",
+            "sample": f"{runs} pass(es) over the full step"}
 
 
 def run_reference(args, rank):
@@ -352,7 +379,7 @@ def main():
     lib.zstdb200_host_free(h_dst)
 
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
-    cpu = None
+    cpu, cpu_libzstd = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = CpuBaseline(args, w)
         cb.run()
@@ -362,6 +389,7 @@ def main():
             tt += dt; nb += b; runs += 1
         cpu = {"value": round(nb / tt / 1e9, 3), "unit": "GB/s", "cores": cb.cores, "kind": cb.kind,
                "sample": f"{runs} pass(es) over the full step ({n} frames, {total} B) = {tt * cb.cores:.1f} core-seconds; {cb.what}"}
+        cpu_libzstd = libzstd_decode_baseline(cb) if decode else None
 
     if rank == 0:
         value = total * world * args.steps / (ms * 1e-3) / 1e9
@@ -382,6 +410,8 @@ def main():
             "kernel_ms": {k: round(v, 4) for k, v in kms.items()},
             "cpu_baseline": cpu,
         }
+        if cpu is not None and cpu_libzstd is not None:
+            line["cpu_baseline_libzstd"] = cpu_libzstd
         if not decode:
             line["config"]["our_compressed_bytes_per_gpu"] = our_compressed
             line["config"]["our_ratio"] = round(total / our_compressed, 4)
