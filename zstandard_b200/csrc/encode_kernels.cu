@@ -593,7 +593,7 @@ size_t encode_bound(size_t srcSize) { return srcSize + (srcSize >> 8) + 32 + 3 *
 // takes up to kSlotsExclusive from the start of the pool; slices of a host batch that run concurrently on
 // different streams each get one of ENC_STREAM_PARTS equal partitions.
 static constexpr u32 kPoolSlots = 148 * 16 * 4;
-static constexpr u32 kSlotsExclusive = 148 * 16;
+static constexpr u32 kSlotsExclusive = 148 * 24;   // upper bound; the launch uses what is resident (EncodeScratch::entWarps)
 static constexpr u32 kSlotsPerPart = kPoolSlots / ENC_STREAM_PARTS;
 
 cudaError_t encode_alloc(EncodeScratch& s, size_t maxBatchBytes, size_t maxItems) {
@@ -616,6 +616,11 @@ static cudaError_t encode_lazy_alloc(EncodeScratch& s) {
   if ((e = cudaMalloc(&s.slots, (size_t)kPoolSlots * slot_bytes())) != cudaSuccess) return e;
   int dev = 0; cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&s.sms, cudaDevAttrMultiProcessorCount, dev);
+  // as many entropy-stage warps as are resident at once: every warp then takes the same number of frames (+-1)
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_enc_entropy, 128, 0) != cudaSuccess || nb < 1) nb = 4;
+  s.entWarps = (u32)(s.sms * nb * 4);
+  if (s.entWarps > kSlotsExclusive) s.entWarps = kSlotsExclusive;
   cudaFuncSetAttribute(k_enc_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   cudaFuncSetAttribute(k_enc_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   return cudaSuccess;
@@ -645,7 +650,7 @@ cudaError_t encode_launch(const EncodeArgs& a, EncodeScratch& s, cudaStream_t st
   else k_enc_match<false><<<grid, 32, smem, st>>>(a, s, hlogL, hlogS, mls);
   const bool exclusive = a.stream_slot == ENC_EXCLUSIVE;
   const u32 slot0 = exclusive ? 0 : (a.stream_slot % ENC_STREAM_PARTS) * kSlotsPerPart;
-  const u32 maxSlots = exclusive ? kSlotsExclusive : kSlotsPerPart;
+  const u32 maxSlots = exclusive ? s.entWarps : kSlotsPerPart;
   const u32 slots = a.n < maxSlots ? a.n : maxSlots;
   if (marks) cudaEventRecord(marks[1], st);
   k_enc_entropy<<<(slots + 3) / 4, 128, 0, st>>>(a, s, slot0, slots);

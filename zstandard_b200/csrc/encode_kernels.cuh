@@ -30,6 +30,7 @@ struct EncodeScratch {
   u8* slots = nullptr;     // entropy-stage work areas (code arrays, FSE state tables), one per resident thread
   size_t maxBytes = 0, maxItems = 0;
   int sms = 148;
+  u32 entWarps = 0;       // entropy-stage warps resident on the device at once (set with the arenas)
 };
 
 size_t encode_bound(size_t srcSize);
