@@ -238,3 +238,50 @@ def huf12_frame(n=700, four_streams=True, seed=5, raw_prefix=0):
     total = len(plain)
     frame = b"\x28\xb5\x2f\xfd" + bytes([0x60]) + (total - 256).to_bytes(2, "little") + blocks    # single segment, 2-byte FCS
     return frame, plain
+
+
+def header_variant_frames(seed=3):
+    """[(frame, capacity)]: every frame-header shape the reference parses (ZStdDecompress.cs:389-499) around one raw
+    block — FCS field of 0/1/2/4/8 bytes, single-segment or window descriptor (incl. too large), dictionary-id field of
+    0/1/2/4 bytes (zero and non-zero), checksum flag with a right and a wrong checksum, the reserved bit, FCS that
+    disagrees with the content, truncations inside the header."""
+    rng = random.Random(seed)
+    import ctypes
+    out = []
+    xxh = Oracle().xxh64
+    for n in (0, 1, 200, 255, 256, 300, 65535 + 256, 70000):
+        payload = bytes(rng.randrange(256) for _ in range(n))
+        block = ((n << 3) | 1).to_bytes(3, "little") + payload                      # one raw block, last
+        for single in (0, 1):
+            for fcs_id in (0, 1, 2, 3):
+                for did in (0, 1, 2, 3):
+                    for checksum in (0, 1):
+                        fhd = (fcs_id << 6) | (single << 5) | (checksum << 2) | did
+                        hdr = b"\x28\xb5\x2f\xfd" + bytes([fhd])
+                        if not single:
+                            hdr += bytes([rng.choice([0x00, 0x38, 0x50, 0xA0, 0xA8, 0xF8])])     # window descriptor (some > 2^30)
+                        dict_id = rng.choice([0, 0, 0, 7])
+                        hdr += dict_id.to_bytes([0, 1, 2, 4][did], "little") if did else b""
+                        if fcs_id == 0:
+                            hdr += bytes([n & 0xFF]) if single else b""
+                        elif fcs_id == 1:
+                            hdr += ((n - 256) & 0xFFFF).to_bytes(2, "little")
+                        elif fcs_id == 2:
+                            hdr += n.to_bytes(4, "little")
+                        else:
+                            hdr += n.to_bytes(8, "little")
+                        frame = hdr + block
+                        if checksum:
+                            frame += (xxh(payload) & 0xFFFFFFFF).to_bytes(4, "little")
+                        out.append((frame, n))
+                        if rng.random() < 0.15:
+                            out.append((frame, max(0, n - 1)))                                   # capacity one short
+                        if rng.random() < 0.15 and checksum:
+                            bad = bytearray(frame); bad[-1] ^= 0x40
+                            out.append((bytes(bad), n))                                          # wrong checksum
+                        if rng.random() < 0.1:
+                            out.append((frame[:rng.randrange(1, len(hdr) + 3)], n))               # cut inside the header / block header
+                        if rng.random() < 0.05:
+                            bad = bytearray(frame); bad[4] |= 0x08
+                            out.append((bytes(bad), n))                                          # reserved bit
+    return out

@@ -316,3 +316,17 @@ def test_multi_megabyte_frames_with_large_windows(gpu_ctx, oracle):
         assert zstd_ref.decompress(frame, len(raw)) == raw
     ro, oo, _ = oracle.decompress(outs[3][:int(cres[3])].tobytes(), len(items[3][1]))
     assert ro == len(items[3][1]) and oo == items[3][1]
+
+
+def test_every_frame_header_shape(gpu_ctx, oracle):
+    """ZSTD_getFrameHeader_advanced / frameHeaderSize (ZStdDecompress.cs:389-499): all field-size combinations, and
+    zstdb200_get_decompressed_size against the oracle's GetDecompressedSize for each."""
+    import zstandard_b200 as zb
+    items = helpers.header_variant_frames()
+    res, dsts = _gpu_decode(gpu_ctx, items)
+    for (frame, cap), r, d in zip(items, res, dsts):
+        ro, oo, _ = oracle.decompress(frame, cap)
+        assert int(r) == ro, (frame[:16].hex(), cap, hex(ro), hex(int(r)))
+        if not helpers.is_err(ro):
+            assert d[:ro].tobytes() == oo
+        assert zb.ZStdDecompress.GetDecompressedSize(frame) == oracle.get_decompressed_size(frame)
