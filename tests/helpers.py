@@ -285,3 +285,65 @@ def header_variant_frames(seed=3):
                             bad = bytearray(frame); bad[4] |= 0x08
                             out.append((bytes(bad), n))                                          # reserved bit
     return out
+
+
+def sequence_count_frames():
+    """[(frame, plaintext, nbSeq of its first block)] covering the three encodings of the sequence count
+    (DecodeSeqHeaders :1121-1136): one byte (< 128), two bytes (< 0x7F00) and 255 + u16 (>= 0x7F00)."""
+    from tools import zstd_ref
+    rng = random.Random(1)
+    toks = [bytes(rng.randrange(256) for _ in range(3)) for _ in range(64)]
+    dense = b"".join(bytes([rng.randrange(256)]) + rng.choice(toks) for _ in range(40000))[:131072]
+    out = []
+    o = Oracle()
+    o.lib.oracle_decompress_trace.restype = ctypes.c_uint32
+    o.lib.oracle_trace_nseq.restype = ctypes.c_uint64
+    for data, level in ((dense[:400], 19), (dense[:20000], 19), (dense, 19)):
+        f = zstd_ref.compress(data, level, checksum=True)
+        dst = ctypes.create_string_buffer(len(data))
+        assert o.lib.oracle_decompress_trace(dst, len(data), f, len(f)) == len(data)
+        out.append((f, data, int(o.lib.oracle_trace_nseq())))
+    return out
+
+
+def rle_modes_frame(nseq=100, tail=3, seed=9, lit_byte=0x78):
+    """Hand-made frame for the modes no encoder at hand emits: an RLE literals section (DecodeLiteralsBlock :755-772,
+    type 1) and all three sequence tables in RLE mode (BuildSeqTable :1046-1050, mode 1: one symbol, zero state bits).
+    Every sequence is litLength 1 (code 1), matchLength 8 (code 5), offset code 2 (offset 1..4 from 2 extra bits), so
+    the bitstream is just 2 bits per sequence.  Returns (frame, plaintext)."""
+    rng = random.Random(seed)
+    extras = [0] + [rng.randrange(4) for _ in range(nseq - 1)]      # the first match can only reach back 1 byte
+    out = bytearray()
+    for e in extras:
+        out.append(lit_byte)
+        off = 1 + e
+        for _ in range(8):
+            out.append(out[-off])
+    out += bytes([lit_byte]) * tail
+    nlit = nseq + tail
+    if nlit < 32:
+        lit = bytes([(nlit << 3) | 1])
+    elif nlit < 4096:
+        lit = (1 | (1 << 2) | (nlit << 4)).to_bytes(2, "little")
+    else:
+        lit = (1 | (3 << 2) | (nlit << 4)).to_bytes(3, "little")
+    lit += bytes([lit_byte])
+    if nseq < 128:
+        cnt = bytes([nseq])
+    elif nseq < 0x7F00:
+        cnt = bytes([(nseq >> 8) + 128, nseq & 0xFF])
+    else:
+        cnt = b"\xff" + (nseq - 0x7F00).to_bytes(2, "little")
+    acc, nbits = 0, 0
+    for e in reversed(extras):                                      # the decoder reads sequence 0 first, from the top
+        acc |= e << nbits
+        nbits += 2
+    acc |= 1 << nbits
+    stream = acc.to_bytes(nbits // 8 + 1, "little")
+    seq = cnt + bytes([(1 << 6) | (1 << 4) | (1 << 2), 1, 2, 5]) + stream   # modes RLE/RLE/RLE; symbols LL 1, OF 2, ML 5
+    block = lit + seq
+    assert len(block) < (1 << 17)
+    total = len(out)
+    hdr = b"\x28\xb5\x2f\xfd" + bytes([0xA0]) + total.to_bytes(4, "little")             # single segment, 4-byte FCS
+    frame = hdr + ((len(block) << 3) | (2 << 1) | 1).to_bytes(3, "little") + block
+    return frame, bytes(out)

@@ -330,3 +330,28 @@ def test_every_frame_header_shape(gpu_ctx, oracle):
         if not helpers.is_err(ro):
             assert d[:ro].tobytes() == oo
         assert zb.ZStdDecompress.GetDecompressedSize(frame) == oracle.get_decompressed_size(frame)
+
+
+def test_sequence_count_encodings(gpu_ctx):
+    """nbSeq in one byte, two bytes and the 255 + u16 form (>= 0x7F00 sequences in one block), DecodeSeqHeaders :1121-1136."""
+    frames = helpers.sequence_count_frames()
+    counts = [n for _, _, n in frames]
+    assert counts[0] < 128 <= counts[1] < 0x7F00 <= counts[2], counts
+    res, dsts = _gpu_decode(gpu_ctx, [(f, len(d)) for f, d, _ in frames])
+    for (f, data, _), r, d in zip(frames, res, dsts):
+        assert int(r) == len(data) and d.tobytes() == data
+
+
+def test_rle_literals_and_rle_mode_tables(gpu_ctx, oracle):
+    """RLE literals sections (1/2/3-byte headers) and LL/OF/ML tables in RLE mode: hand-made frames and their mutations."""
+    rng = random.Random(12)
+    items = []
+    for nseq, tail in ((1, 0), (5, 3), (28, 3), (100, 3), (127, 0), (128, 5), (4000, 200), (5000, 0), (14000, 7)):
+        f, p = helpers.rle_modes_frame(nseq, tail, seed=nseq)
+        items += [(f, len(p)), (f, len(p) - 1), (f[:-1], len(p))] + [(helpers.mutate(rng, f), len(p)) for _ in range(12)]
+    res, dsts = _gpu_decode(gpu_ctx, items)
+    for (frame, cap), r, d in zip(items, res, dsts):
+        ro, oo, _ = oracle.decompress(frame, cap)
+        assert int(r) == ro, (frame.hex()[:60], cap, hex(ro), hex(int(r)))
+        if not helpers.is_err(ro):
+            assert d[:ro].tobytes() == oo

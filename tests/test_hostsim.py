@@ -76,3 +76,26 @@ def test_every_frame_header_shape(hostsim, oracle):
             z = zstd_ref.decompress(frame, cap)        # libzstd refuses some legal shapes (windows > 2^27): only compare when it answers
             assert z is None or z == oo
     assert n_ok > 100
+
+
+def test_sequence_count_encodings(hostsim, oracle):
+    frames = helpers.sequence_count_frames()
+    counts = [n for _, _, n in frames]
+    assert counts[0] < 128 <= counts[1] < 0x7F00 <= counts[2], counts
+    for f, data, _ in frames:
+        rh, oh = hostsim.decompress(f, len(data), oracle)
+        assert rh == len(data) and oh == data
+
+
+def test_rle_literals_and_rle_mode_tables(hostsim, oracle):
+    """Modes no encoder at hand emits (hand-made frames, accepted by libzstd): RLE literals with 1/2/3-byte headers,
+    LL/OF/ML tables in RLE mode; plus mutations of those frames (same result codes)."""
+    from tools import zstd_ref
+    rng = random.Random(12)
+    for nseq, tail in ((1, 0), (5, 3), (28, 3), (100, 3), (127, 0), (128, 5), (4000, 200), (5000, 0), (14000, 7)):
+        f, p = helpers.rle_modes_frame(nseq, tail, seed=nseq)
+        assert zstd_ref.decompress(f, len(p)) == p
+        for frame, cap in [(f, len(p)), (f, len(p) - 1), (f[:-1], len(p))] + [(helpers.mutate(rng, f), len(p)) for _ in range(12)]:
+            ro, oo, _ = oracle.decompress(frame, cap)
+            rh, oh = hostsim.decompress(frame, cap, oracle)
+            assert ro == rh and oo == oh, (nseq, tail, frame.hex()[:60], hex(ro), hex(rh))
