@@ -347,3 +347,61 @@ def rle_modes_frame(nseq=100, tail=3, seed=9, lit_byte=0x78):
     hdr = b"\x28\xb5\x2f\xfd" + bytes([0xA0]) + total.to_bytes(4, "little")             # single segment, 4-byte FCS
     frame = hdr + ((len(block) << 3) | (2 << 1) | 1).to_bytes(3, "little") + block
     return frame, bytes(out)
+
+
+def frame_modes(frame):
+    """Counter of the format modes one data frame uses: ("block", type), ("lit", type, sizeFormat), ("nseq", bytes),
+    ("LL" | "OF" | "ML", mode) — a coverage probe for the test corpora (walks headers only)."""
+    import collections
+    c = collections.Counter()
+    if frame[:4] != b"\x28\xb5\x2f\xfd":
+        return c
+    fhd = frame[4]; did = fhd & 3; single = (fhd >> 5) & 1; fcs = fhd >> 6
+    p = 5 + (0 if single else 1) + [0, 1, 2, 4][did] + [1 if single else 0, 2, 4, 8][fcs]
+    while p + 3 <= len(frame):
+        h = int.from_bytes(frame[p:p + 3], "little"); p += 3
+        last, t, sz = h & 1, (h >> 1) & 3, h >> 3
+        c[("block", t)] += 1
+        if t == 2:
+            b = frame[p:p + sz]
+            lt, sf = b[0] & 3, (b[0] >> 2) & 3
+            c[("lit", lt, sf)] += 1
+            if lt < 2:
+                lh = [1, 2, 1, 3][sf]
+                n = (b[0] >> 3) if lh == 1 else (int.from_bytes(b[:lh], "little") >> 4)
+                q = lh + (n if lt == 0 else 1)
+            else:
+                lh = [3, 3, 4, 5][sf]; v = int.from_bytes(b[:5], "little")
+                cs = ((v >> 14) & 0x3FF) if lh == 3 else (((v >> 18) & 0x3FFF) if lh == 4 else ((v >> 22) & 0x3FFFF))
+                q = lh + cs
+            if q < len(b):
+                ns = b[q]
+                if ns == 0:
+                    c[("nseq", 0)] += 1
+                else:
+                    w = 1 if ns < 128 else (2 if ns < 255 else 3)
+                    c[("nseq", w)] += 1
+                    m = b[q + w]
+                    c[("LL", (m >> 6) & 3)] += 1; c[("OF", (m >> 4) & 3)] += 1; c[("ML", (m >> 2) & 3)] += 1
+            p += sz
+        elif t == 0:
+            p += sz
+        elif t == 1:
+            p += 1
+        else:
+            break
+        if last:
+            break
+    return c
+
+
+def repeat_mode_frames():
+    """[(frame, plaintext)] whose blocks use repeat-mode (mode 3) LL, OF and ML tables and treeless literals
+    (libzstd level 19 on stationary multi-block inputs)."""
+    from tools import zstd_ref
+    rng = random.Random(7)
+    B = bytes(rng.randrange(256) for _ in range(8))
+    a = b"".join(bytes([rng.randrange(256)]) + B for _ in range(40000))
+    toks = [bytes(rng.randrange(256) for _ in range(6)) for _ in range(200)]
+    b = b"".join(rng.choice(toks) for _ in range(131072 // 6 + 1))[:131072] + b"".join(b"x" + rng.choice(toks) for _ in range(8000))
+    return [(zstd_ref.compress(d, 19, checksum=True), d) for d in (a, b)]

@@ -355,3 +355,11 @@ def test_rle_literals_and_rle_mode_tables(gpu_ctx, oracle):
         assert int(r) == ro, (frame.hex()[:60], cap, hex(ro), hex(int(r)))
         if not helpers.is_err(ro):
             assert d[:ro].tobytes() == oo
+
+
+def test_repeat_mode_tables(gpu_ctx, oracle):
+    frames = helpers.repeat_mode_frames()
+    res, dsts = _gpu_decode(gpu_ctx, [(f, len(d)) for f, d in frames] + [(f, len(d) - 1) for f, d in frames])
+    for k, (f, data) in enumerate(frames):
+        assert int(res[k]) == len(data) and dsts[k].tobytes() == data
+        assert int(res[k + len(frames)]) == oracle.decompress(f, len(data) - 1)[0]

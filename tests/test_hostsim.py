@@ -99,3 +99,18 @@ def test_rle_literals_and_rle_mode_tables(hostsim, oracle):
             ro, oo, _ = oracle.decompress(frame, cap)
             rh, oh = hostsim.decompress(frame, cap, oracle)
             assert ro == rh and oo == oh, (nseq, tail, frame.hex()[:60], hex(ro), hex(rh))
+
+
+def test_repeat_mode_tables(hostsim, oracle):
+    import collections
+    frames = helpers.repeat_mode_frames()
+    modes = collections.Counter()
+    for f, _ in frames:
+        modes.update(helpers.frame_modes(f))
+    assert modes[("LL", 3)] and modes[("OF", 3)] and modes[("ML", 3)], modes       # the probe found repeat mode for every kind
+    for f, data in frames:
+        for cap in (len(data), len(data) - 1):
+            ro, oo, _ = oracle.decompress(f, cap)
+            rh, oh = hostsim.decompress(f, cap, oracle)
+            assert ro == rh and oo == oh
+        assert oracle.decompress(f, len(data))[1] == data
