@@ -366,9 +366,9 @@ __device__ __forceinline__ void warp_match(u8* d, u32 off, u32 len, u32 lane) {
   for (u32 i = lane; i < len; i += 32) { d[i] = s[r]; r += stepm; if (r >= off) r -= off; }
 }
 
-// 12 CTAs of 4 warps per SM (40 registers, some spills): measured faster than fewer, fatter warps — the kernel lives on
-// occupancy (6 / 8 / 10 / 12 CTAs: 3.93 / 3.44 / 3.03 / 2.95 ms on the bench workload).
-__global__ void __launch_bounds__(EXEC_THREADS, 12) k_exec(DecodeArgs a) {
+// 16 CTAs of 4 warps per SM (32 registers, spills to local memory included): measured faster than fewer, fatter warps —
+// the kernel lives on occupancy (6 / 8 / 10 / 12 / 16 CTAs: 3.93 / 3.44 / 3.03 / 2.95 / 2.83 ms on the bench workload).
+__global__ void __launch_bounds__(EXEC_THREADS, 16) k_exec(DecodeArgs a) {
   const u32 lane = threadIdx.x & 31;
   const u32 f = (blockIdx.x * EXEC_THREADS + threadIdx.x) >> 5;
   if (f >= a.n) return;
