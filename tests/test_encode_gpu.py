@@ -130,3 +130,27 @@ def test_bad_arguments_are_batch_level_errors(gpu_ctx):
     assert len(gpu_ctx.compress_batch([], [])) == 0           # an empty batch is not an error
     assert len(gpu_ctx.decompress_batch([], [])) == 0
     assert zb.ZStdCompress.CompressBound(0) > 0
+
+
+def test_generous_destination_capacities_fit_the_staging():
+    """Destination capacities well above the compress bound: the sum over a sub-batch may exceed the batch size; the
+    device staging has to be sized for it (it once was not)."""
+    import zstandard_b200 as zb
+    from tools import corpus, zstd_ref
+    ctx = zb.Context(max_batch_bytes=4 << 20)
+    try:
+        chunk, n = 131072, 30
+        raw = corpus.make("log", chunk * n)
+        chunks = [raw[i * chunk:(i + 1) * chunk] for i in range(n)]
+        outs = [np.zeros(300 * 1024, dtype=np.uint8) for _ in range(n)]
+        res = ctx.compress_batch(chunks, outs, level=3, checksum=True)
+        for c, r, o in zip(chunks, res, outs):
+            assert not helpers.is_err(int(r))
+            assert zstd_ref.decompress(o[:int(r)].tobytes(), chunk) == c.tobytes()
+        big = np.zeros(n * 300 * 1024, dtype=np.uint8)                      # the same, destinations back to back (direct DMA)
+        outs2 = [big[i * 300 * 1024:(i + 1) * 300 * 1024] for i in range(n)]
+        res2 = ctx.compress_batch(chunks, outs2, level=1, checksum=False)
+        for c, r, o in zip(chunks, res2, outs2):
+            assert zstd_ref.decompress(o[:int(r)].tobytes(), chunk) == c.tobytes()
+    finally:
+        ctx.close()

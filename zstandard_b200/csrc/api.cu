@@ -84,15 +84,17 @@ int alloc_device(zstdb200_ctx* ctx, Device& d) {
   for (auto& s : d.stream) CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&d.descEv, cudaEventDisableTiming));
   const size_t items = ctx->maxItems;
+  // d_src / d_dst are the codec's input / output staging in both directions: compressed frames of a full batch can
+  // be larger than the batch (compress bounds), so both buffers take the larger size
   CK(cudaMalloc(&d.d_src, ctx->srcCap + 256));
-  CK(cudaMalloc(&d.d_dst, ctx->dstSpan + 256));
+  CK(cudaMalloc(&d.d_dst, ctx->srcCap + 256));
   CK(cudaMalloc(&d.d_srcOff, items * 8)); CK(cudaMalloc(&d.d_dstOff, items * 8));
   CK(cudaMalloc(&d.d_srcSize, items * 4)); CK(cudaMalloc(&d.d_dstCap, items * 4)); CK(cudaMalloc(&d.d_result, items * 4));
   CK(cudaMalloc(&d.d_info, items * sizeof(FrameInfo)));
   CK(cudaMalloc(&d.d_more, NSTREAMS * 4)); CK(cudaMallocHost(&d.h_more, NSTREAMS * 4));
   CK(cudaMalloc(&d.d_lit, decode_lit_arena_bytes(ctx->dstSpan, items)));
   CK(cudaMalloc(&d.d_seq, decode_seq_arena_bytes(ctx->dstSpan, items)));
-  CK(cudaMallocHost(&d.h_src, ctx->srcCap + 256)); CK(cudaMallocHost(&d.h_dst, ctx->dstSpan + 256));
+  CK(cudaMallocHost(&d.h_src, ctx->srcCap + 256)); CK(cudaMallocHost(&d.h_dst, ctx->srcCap + 256));
   CK(cudaMallocHost(&d.h_srcOff, items * 8)); CK(cudaMallocHost(&d.h_dstOff, items * 8));
   CK(cudaMallocHost(&d.h_srcSize, items * 4)); CK(cudaMallocHost(&d.h_dstCap, items * 4)); CK(cudaMallocHost(&d.h_result, items * 4));
   CK(decode_configure());
@@ -122,7 +124,7 @@ std::vector<Range> make_subbatches(size_t n, size_t maxIn, size_t maxOut, size_t
   while (lo < n) {
     size_t in = 0, out = 0, hi = lo;
     while (hi < n && hi - lo < maxItems) {
-      size_t a = align_up(inBytes(hi), 16) + 64, b = align_up(outBytes(hi), 16);
+      size_t a = align_up(inBytes(hi), 16), b = align_up(outBytes(hi), 16);   // exactly what run_subbatch lays out
       if (in + a > maxIn || out + b > maxOut) break;
       in += a; out += b; hi++;
     }
@@ -294,9 +296,10 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
 int run_host_batch(zstdb200_ctx* ctx, const Job& j, size_t n) {
   if (n == 0) return 0;
   if (!j.src || !j.srcSize || !j.dst || !j.dstCap || !j.result) { ctx->err = "null argument"; return 1; }
-  // staging limits: decode: in = compressed (srcCap), out = raw (dstSpan); encode: in = raw, out = frames
-  const size_t maxIn = j.op == Op::Decompress ? ctx->srcCap : ctx->maxBatch;
-  const size_t maxOut = j.op == Op::Decompress ? ctx->maxBatch : ctx->srcCap;
+  // staging limits.  decode: in = frames (d_src, srcCap), out = content (dstSpan: what the literal / sequence arenas
+  // are sized for); encode: in = raw chunks (dstSpan: what the encoder arenas are sized for), out = frames (d_dst, srcCap)
+  const size_t maxIn = j.op == Op::Decompress ? ctx->srcCap : ctx->dstSpan;
+  const size_t maxOut = j.op == Op::Decompress ? ctx->dstSpan : ctx->srcCap;
   bool tooBig = false;
   std::vector<Range> subs = make_subbatches(n, maxIn, maxOut, ctx->maxItems,
       [&](size_t i) { return (size_t)j.srcSize[i]; }, [&](size_t i) { return (size_t)j.dstCap[i]; }, &tooBig);
