@@ -5,6 +5,8 @@
 // with g++ and drives them the way the kernels do (k_parse -> k_huf lanes -> k_seq -> a serial stand-in for the
 // warp-cooperative k_exec) so that tests/test_hostsim.py can compare them with the oracle before any GPU time
 // is spent.  It is never linked into libzstdb200.so.
+#include <stdio.h>
+#include <stdlib.h>
 #include <cstring>
 #include <cstdlib>
 #include <vector>
@@ -110,20 +112,26 @@ u32 sim_exec(const u8* src, u32 size, const FrameInfo& fi, u8* dst, u64 cap, con
       if (fi.seq_err_block == blk && fi.seq_err_index == 0xFFFFFFFFu) { err = fi.seq_err_code; break; }
       u64 litPos = 0;
       if (nbSeq) {
-        const SeqRec* r = recs + recRun;
-        for (; (r->x | r->y) != 0; r++) {
-          if (r->x == 0) { if (op + r->y > cap) { err = ZE_dstSize_tooSmall; break; } continue; }   // split sequence ahead: whole-sequence check
-          u32 ll = r->y & 0xFFFF, ml = r->y >> 16, off = r->x;
-          if (op + ll + ml > cap) { err = ZE_dstSize_tooSmall; break; }
-          if (litPos + ll > litSize) { err = ZE_corruption_detected; break; }
-          if ((u64)off > op + ll) { err = ZE_corruption_detected; break; }
+        // header record (count, output bytes, literal bytes), then self-describing records (zb_decode.cuh)
+        u32 nRecs = 0;
+        if (recRun < seq_capacity(cap)) nRecs = recs[recRun].x;
+        const SeqRec* r = recs + recRun + 1;
+        const u64 blockBase = op;
+        for (u32 k = 0; k < nRecs; k++, r++) {
+          const u32 ll = rec_ll(*r), ml = rec_ml(*r), off = r->z;
+          const u64 start = blockBase + r->x;
+          if (start != op && start <= cap) { fprintf(stderr, "hostsim: record position %llu != %llu\n", (unsigned long long)start, (unsigned long long)op); abort(); }
+          if (start + ll + ml > cap) { err = ZE_dstSize_tooSmall; break; }
+          if ((u64)rec_lpos(*r) + ll > litSize) { err = ZE_corruption_detected; break; }
+          if ((u64)off > start + ll) { err = ZE_corruption_detected; break; }
+          if (rec_lpos(*r) != litPos) { fprintf(stderr, "hostsim: literal position mismatch\n"); abort(); }
           if (!dry) for (u32 i = 0; i < ll; i++) dst[op + i] = isRle ? (u8)rleByte : lit[litPos + i];
           op += ll; litPos += ll;
           if (!dry) for (u32 i = 0; i < ml; i++) dst[op + i] = dst[op + i - off];
           op += ml;
         }
         if (err) break;
-        recRun = (u64)(r - recs) + 1;
+        recRun += 1 + (u64)nRecs;
         if (fi.seq_err_block == blk) { err = fi.seq_err_code; break; }
       }
       u64 lastLL = litSize - litPos;
@@ -216,7 +224,7 @@ extern "C" uint32_t hostsim_stages(const uint8_t* src_in, uint32_t size, uint32_
   seq_decode_frame(src, size, fi.body_off, fi.window, T, recs.data(), seq_capacity(cap), res, sim->llInfo, sim->mlInfo, normBuf, nextBuf, ringBuf);
   memcpy(lit_out, lit.data(), cap);
   u32 n = (u32)std::min<size_t>(max_recs, recs.size());
-  memcpy(rec_out, recs.data(), (size_t)n * 8);
+  memcpy(rec_out, recs.data(), (size_t)n * sizeof(SeqRec));
   info_out[0] = fi.huf_err_block; info_out[1] = fi.huf_err_code; info_out[2] = res.err_block; info_out[3] = res.err_code; info_out[4] = res.err_index;
   return 0;
 }

@@ -59,10 +59,11 @@ def load_library():
     """Loads libzstdb200.so (built by zstandard_b200/build.py).  Raises if it is missing: no fallback exists."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("ZSTDB200_LIB") or LIB_PATH      # development aid: a variant build (zstandard_b200/build.py --debug)
+        if not os.path.exists(path):
             raise RuntimeError(f"{LIB_PATH} is missing: run `python -m zstandard_b200.build` (nvcc, sm_100a). "
                                "zstandard_b200 has no CPU implementation.")
-        lib = ctypes.CDLL(LIB_PATH)
+        lib = ctypes.CDLL(path)
         for name, (res, args) in ABI.items():
             fn = getattr(lib, name)
             fn.restype = res

@@ -24,21 +24,28 @@ def _stale():
     return os.path.getmtime(os.path.join(HERE, "..", "include", "zstdb200.h")) > t
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, extra=None, out=None):
+    """extra / out: development aid — a variant build (e.g. extra=["-DZB_EXEC_DEBUG"]) written next to the product
+    library and loaded with ZSTDB200_LIB=<path>."""
+    lib = out or LIB
+    if not force and not extra and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
-    os.makedirs(os.path.join(HERE, "_build"), exist_ok=True)
+    bdir = os.path.join(HERE, "_build" if not out else "_build_" + os.path.basename(out))
+    os.makedirs(bdir, exist_ok=True)
     for s in SOURCES:
-        o = os.path.join(HERE, "_build", s.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
+        o = os.path.join(bdir, s.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + (extra or []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, s), "-o", o]
         subprocess.run(cmd, check=True)
         objs.append(o)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["--cudart", "static", "-Xlinker", "--no-undefined", "-lpthread", "-ldl", "-lrt"]
+    cmd = [nvcc, "-shared", "-o", lib] + objs + ["--cudart", "static", "-Xlinker", "--no-undefined", "-lpthread", "-ldl", "-lrt"]
     subprocess.run(cmd, check=True)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--debug" in sys.argv:
+        print(build(force=True, extra=["-DZB_EXEC_DEBUG"], out=os.path.join(HERE, "libzstdb200_dbg.so")))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

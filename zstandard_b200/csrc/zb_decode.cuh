@@ -11,25 +11,35 @@
 
 namespace zb {
 
-// 8-byte sequence record consumed by the execute stage.
-//   x = offset (>= 1 for a match)
-//   y = litLength | matchLength << 16       (both < 65536; longer ones are split into several records,
-//                                            a literals-only piece has matchLength 0 and offset 1)
-//   x == 0, y == 0 : end of a block's records
-//   x == 0, y != 0 : announces a split sequence: y = its litLength + matchLength, so that the execute stage can
-//                    make the reference's whole-sequence capacity check (:1278) before any check of the pieces
-struct alignas(8) SeqRec { u32 x, y; };
-ZB_HD void rec_store(SeqRec* p, u32 x, u32 y) {
+// 16-byte sequence record consumed by the execute stage.  A record is self-describing — it carries where its
+// bytes go and where its literals come from — so the execute stage needs no prefix sums and its warps can work on
+// different groups of a block's records without a positional chain between them.
+//   x = dpos : output position of the sequence's literal run, relative to the block's first output byte
+//              (saturates at 0xFFFFFFFF: such a record can never pass the capacity check)
+//   y = lpos (18 bits: position of its literals within the block's literals, saturates at 0x3FFFF)
+//       | matchLength >> 15 << 18 (2 bits)
+//   z = offset (>= 1 for a well-formed match; garbage offsets of corrupted streams use all 32 bits)
+//   w = litLength (17 bits) | (matchLength & 0x7FFF) << 17
+// The records of one compressed block are preceded by one header record:
+//   x = number of records that follow, y = output bytes of those records (saturating), z = literal bytes they take
+//   (saturating at 0x3FFFF), w = 0
+struct alignas(16) SeqRec { u32 x, y, z, w; };
+ZB_HD void rec_store(SeqRec* p, u32 x, u32 y, u32 z, u32 w) {
 #if defined(__CUDA_ARCH__)
-  *reinterpret_cast<uint2*>(p) = make_uint2(x, y);
+  *reinterpret_cast<uint4*>(p) = make_uint4(x, y, z, w);
 #else
-  p->x = x; p->y = y;
+  p->x = x; p->y = y; p->z = z; p->w = w;
 #endif
 }
+ZB_HD u32 rec_ll(const SeqRec& r) { return r.w & 0x1FFFF; }
+ZB_HD u32 rec_ml(const SeqRec& r) { return (r.w >> 17) | (((r.y >> 18) & 3) << 15); }
+ZB_HD u32 rec_lpos(const SeqRec& r) { return r.y & 0x3FFFF; }
+ZB_HD u32 sat_add32(u32 a, u32 b) { const u32 s = a + b; return s < a ? 0xFFFFFFFFu : s; }
+ZB_HD u32 sat_lpos(u32 lpos, u32 ll) { const u32 s = lpos + ll; return s > 0x3FFFFu ? 0x3FFFFu : s; }
 
 // Capacity rule shared with the host side: records for a frame whose output capacity is `cap` bytes.
-// Every record with a match yields >= 3 bytes and each block adds one terminator, so a frame that fits its
-// capacity needs fewer than 2*(cap/3) + 24 records; running out of room therefore means dstSize_tooSmall.
+// Every sequence yields >= 3 bytes and each block with sequences adds one header record, so a frame that fits
+// its capacity needs fewer than 2*(cap/3) + 24 records; running out of room therefore means dstSize_tooSmall.
 ZB_HD u64 seq_capacity(u64 cap) { return 2 * (cap / 3) + 24; }
 
 struct SeqTableSet {
@@ -42,20 +52,6 @@ struct SeqTableSet {
 struct SeqFrameOut {
   u32 err_block, err_code, err_index;
 };
-
-// slow path of the record writer: lengths that do not fit 16 bits are split (ZStdDecompress.cs allows
-// litLength <= 131071 and matchLength <= 131074)
-#if defined(__CUDA_ARCH__)
-__noinline__
-#endif
-ZB_HD u32 seq_emit_long(SeqRec* out, u32 n, u32 cap, u32 off, u32 ll, u32 ml) {
-  if (n < cap) rec_store(out + n, 0, ll + ml);
-  n++;
-  while (ll > 65535) { if (n < cap) rec_store(out + n, 1, 65535); n++; ll -= 65535; }
-  while (ml > 65535) { if (n < cap) rec_store(out + n, off, ll | (65535u << 16)); n++; ll = 0; ml -= 65535; }
-  if (n < cap) rec_store(out + n, off, ll | (ml << 16));
-  return n + 1;
-}
 
 // n bits (0..32) from the top of a left-aligned 64-bit window; the double shift makes n == 0 yield 0
 // (the reference's LookBits does the same, BitStream.cs:412-416)
@@ -142,7 +138,7 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, S
   u32 rep0 = 1, rep1 = 4, rep2 = 8;                      // ZStdInternal.cs:111, ZStdDecompress.cs:2492
   bool haveRepeat = false;
   const u32 cap = (u32)cap64;                            // seq_capacity of a u32 capacity fits 32 bits
-  u32 n = 0;
+  u32 n = 0;                                             // record slots used so far (headers included)
   for (int k = 0; k < 3; k++) { T.cur[k] = T.space[k]; T.curStride[k] = T.stride; T.log[k] = 0; }
   while (true) {
     BlockHdr bh;
@@ -178,6 +174,8 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, S
         haveRepeat = true;                                                         // fseEntropy = 1 (:1575)
         // ---- bitstream ----
         BitCursor c;
+        const u32 hdrSlot = n++;                                                   // the block's header record, written last
+        u32 dpos = 0, lpos = 0;                                                    // running output / literal positions within the block
         u32 decoded = 0; bool bad = false;
         if (!bc_init(c, sp + hdr, ssz - hdr)) bad = true;                          // :1577 -> corruption_detected
         if (!bad) {
@@ -208,13 +206,13 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, S
             const u32 mlv = shr_c(hi << ofBits, 32 - mlBits);                      // (:1504, :1534, :1542)
             const u32 llv = shr_c(hi << (ofBits + mlBits), 32 - llBits);
             const u32 ml = (iML & 0xFFFFFF) + mlv, ll = (iLL & 0xFFFFFF) + llv;
-            // the one rare exit of the loop: >= 32 value bits (the 32-bit extraction above is then wrong) or a length that
-            // needs a split record — nothing has been committed yet, the careful loop redoes this sequence
-            if (valBits >= 32 || (ll | ml) > 65535) break;
+            // the one rare exit of the loop: >= 32 value bits (the 32-bit extraction above is then wrong) — nothing has
+            // been committed yet, the careful loop redoes this sequence
+            if (valBits >= 32) break;
             const u32 h2 = fshl(lo, hi, valBits);                                  // the 32 bits after the value bits
             const u32 offset = rep_resolve(rep0, rep1, rep2, ofBits, ofv, llSym);
-            if (n < cap) rec_store(out + n, offset, ll | (ml << 16));
-            n++;
+            if (n < cap) rec_store(out + n, dpos, lpos | ((ml >> 15) << 18), offset, ll | (ml << 17));
+            n++; dpos = sat_add32(dpos, ll + ml); lpos = sat_lpos(lpos, ll);
             stLL = cell_base(lLL) + shr_c(h2, 32 - nLL);                           // state update LL, ML, OF (:1547-1550)
             stML = cell_base(lML) + shr_c(h2 << nLL, 32 - nML);
             stOF = cell_base(lOF) + shr_c(h2 << (nLL + nML), 32 - nOF);
@@ -243,8 +241,8 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, S
             else if (valBits + stBits > 64) w = bc_window64(c, Pv);                // rare: more than 64 bits in one sequence
             const u32 offset = rep_resolve(rep0, rep1, rep2, ofBits, ofv, llSym);
             const u32 ml = (iML & 0xFFFFFF) + mlv, ll = (iLL & 0xFFFFFF) + llv;
-            if ((ll | ml) <= 65535) { if (n < cap) rec_store(out + n, offset, ll | (ml << 16)); n++; }
-            else n = seq_emit_long(out, n, cap, offset, ll, ml);
+            if (n < cap) rec_store(out + n, dpos, lpos | ((ml >> 15) << 18), offset, ll | (ml << 17));
+            n++; dpos = sat_add32(dpos, ll + ml); lpos = sat_lpos(lpos, ll);
             decoded++;
             // past the last sequence these bits do not exist (the stream ends after its value bits)
             stLL = cell_base(lLL) + top_bits(w, nLL); w <<= nLL;
@@ -253,10 +251,9 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, S
             P = Pv - (i32)stBits;
           }
         }
-        // terminator; when the region is full the last slot is sacrificed so that the execute stage stops there
-        const bool overflow = n >= cap;
-        rec_store(out + (overflow ? cap - 1 : n), 0, 0);
-        n++;
+        // header record: how many records the execute stage may run (those that fit the region)
+        const bool overflow = n > cap;
+        if (hdrSlot < cap) rec_store(out + hdrSlot, (overflow ? cap : n) - hdrSlot - 1, dpos, lpos, 0);
         if (overflow) { res.err_block = blk; res.err_code = ZE_dstSize_tooSmall; res.err_index = 0; return; }
         if (bad) { res.err_block = blk; res.err_code = ZE_corruption_detected; res.err_index = decoded; return; }
       }
