@@ -45,7 +45,10 @@ def build(force=False, verbose=False, extra=None, out=None):
 
 
 if __name__ == "__main__":
-    if "--debug" in sys.argv:
+    if "--variant" in sys.argv:      # e.g. --variant c12 -DEXEC_MIN_CTAS=12
+        i = sys.argv.index("--variant")
+        print(build(force=True, extra=sys.argv[i + 2:], out=os.path.join(HERE, "libzstdb200_%s.so" % sys.argv[i + 1]), verbose="-v" in sys.argv))
+    elif "--debug" in sys.argv:
         print(build(force=True, extra=["-DZB_EXEC_DEBUG"], out=os.path.join(HERE, "libzstdb200_dbg.so")))
     else:
         print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -5,7 +5,7 @@
 
 namespace zb {
 
-#define EXEC_THREADS 256
+#define EXEC_THREADS 128
 
 // All pointers are device pointers.  dst_off must be non-decreasing with dst_off[i] + dst_cap[i] <= dst_off[i+1]
 // (the scratch arenas are addressed from dst_off, see DESIGN.md "HBM layout").
