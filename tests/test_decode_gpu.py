@@ -363,3 +363,101 @@ def test_repeat_mode_tables(gpu_ctx, oracle):
     for k, (f, data) in enumerate(frames):
         assert int(res[k]) == len(data) and dsts[k].tobytes() == data
         assert int(res[k + len(frames)]) == oracle.decompress(f, len(data) - 1)[0]
+
+
+def test_long_offset_regime_window_above_32_mib(gpu_ctx, oracle):
+    """Offset codes >= 25 in a frame whose window exceeds 2^25 (ZStdDecompress.cs:1494-1501 split read, :1898-1905 dispatch):
+    2 MiB of random bytes, 34 MiB of zeros, the same 2 MiB again — libzstd's long-distance matcher codes the second copy
+    as matches 36 MiB back."""
+    from tools import zstd_ref
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 256, 2 << 20, dtype=np.uint8).tobytes()
+    data = a + bytes(34 << 20) + a
+    c = zstd_ref._Z.ZSTD_createCCtx()
+    try:
+        for param, value in ((zstd_ref.ZSTD_c_compressionLevel, 3), (zstd_ref.ZSTD_c_checksumFlag, 1), (zstd_ref.ZSTD_c_windowLog, 27), (160, 1)):
+            zstd_ref._Z.ZSTD_CCtx_setParameter(c, param, value)          # 160 = ZSTD_c_enableLongDistanceMatching
+        import ctypes
+        cap = zstd_ref.compress_bound(len(data))
+        buf = ctypes.create_string_buffer(cap)
+        n = zstd_ref._Z.ZSTD_compress2(c, buf, cap, data, len(data))
+        assert not zstd_ref._Z.ZSTD_isError(n)
+        frame = buf.raw[:n]
+    finally:
+        zstd_ref._Z.ZSTD_freeCCtx(c)
+    assert len(frame) < (3 << 20)                  # the second copy was found: the frame holds the random block once
+    assert (frame[4] >> 5) & 1 and len(data) > (1 << 25)   # single-segment frame: window = content size, above 2^25
+    ro, oo, _ = oracle.decompress(frame, len(data))
+    assert ro == len(data) and oo == data
+    items = [(frame, len(data)), (frame, len(data) - 1), (frame[:-5], len(data))]
+    res, dsts = _gpu_decode(gpu_ctx, items)
+    for (f, cap), r, d in zip(items, res, dsts):
+        want, out, _ = oracle.decompress(f, cap)
+        assert int(r) == want, (hex(int(r)), hex(want))
+        if not helpers.is_err(want):
+            assert d[:want].tobytes() == out
+
+
+def test_capacity_larger_than_the_context_arena():
+    """The reference accepts any dstCapacity (ZStdDecompress.cs:2182-2191): a small frame decoded into a large reusable
+    scratch buffer must not be refused because the buffer is larger than the context's max_batch_bytes; a frame that
+    overshoots its declared content size still gets the reference's verdict, not the clamped capacity's."""
+    import zstandard_b200 as zb
+    from tools import zstd_ref
+    orc = helpers.Oracle()
+    rng = random.Random(12)
+    ctx = zb.Context(max_batch_bytes=1 << 20)
+    try:
+        data = helpers.sample_payload(rng, 0, 50000)
+        frame = zstd_ref.compress(data, 3, checksum=True)
+        lying = bytearray(frame)                   # FCS field (2 bytes at offset 5, value - 256) declares 100 bytes less
+        assert lying[4] >> 6 == 1 and (lying[4] >> 5) & 1
+        fcs = int.from_bytes(lying[5:7], "little") - 100
+        lying[5:7] = fcs.to_bytes(2, "little")
+        items = [(frame, 4 << 20), (bytes(lying), 4 << 20), (frame, 50000), (bytes(lying), 50000 - 100), (frame, 49999)]
+        dsts = [np.zeros(c, dtype=np.uint8) for _, c in items]
+        res = ctx.decompress_batch([f for f, _ in items], dsts)
+        for (f, cap), r, d in zip(items, res, dsts):
+            want, out, _ = orc.decompress(f, cap)
+            assert int(r) == want, (cap, hex(int(r)), hex(want))
+            if not helpers.is_err(want):
+                assert d[:want].tobytes() == out
+        # compress: a destination far larger than the bound is fine as well
+        out = np.zeros(8 << 20, dtype=np.uint8)
+        r = ctx.compress_batch([np.frombuffer(data, dtype=np.uint8)], [out], level=1, checksum=True)[0]
+        assert not helpers.is_err(int(r))
+        ro, oo, _ = orc.decompress(out[:int(r)].tobytes(), len(data))
+        assert ro == len(data) and oo == data
+    finally:
+        ctx.close()
+
+
+def test_pinned_contiguous_buffers_take_the_direct_path_and_pageable_ones_the_staged_path(gpu_ctx, oracle):
+    """The same batch through pinned memory laid out back to back (direct DMA), through pageable numpy arrays and through
+    a non-contiguous destination (refused)."""
+    import ctypes
+    import zstandard_b200 as zb
+    lib = zb.load_library()
+    frames = helpers.make_frames(77, 40, sizes=[3000, 20000, 65536])
+    total_src = sum(len(f) for f, _ in frames); total_dst = sum(len(d) for _, d in frames)
+    lib.zstdb200_host_alloc.restype = ctypes.c_void_p
+    hs = lib.zstdb200_host_alloc(total_src + 64); hd = lib.zstdb200_host_alloc(total_dst + 64)
+    try:
+        src = np.ctypeslib.as_array((ctypes.c_uint8 * total_src).from_address(hs))
+        dst = np.ctypeslib.as_array((ctypes.c_uint8 * total_dst).from_address(hd))
+        srcs, dsts, so, do = [], [], 0, 0
+        for f, d in frames:
+            src[so:so + len(f)] = np.frombuffer(f, dtype=np.uint8)
+            srcs.append(src[so:so + len(f)]); dsts.append(dst[do:do + len(d)])
+            so += len(f); do += len(d)
+        res = gpu_ctx.decompress_batch(srcs, dsts)
+        pageable = [np.zeros(len(d), dtype=np.uint8) for _, d in frames]
+        res2 = gpu_ctx.decompress_batch([f for f, _ in frames], pageable)
+        for (f, d), r, r2, o, o2 in zip(frames, res, res2, dsts, pageable):
+            assert int(r) == int(r2) == len(d)
+            assert o.tobytes() == d and o2.tobytes() == d
+    finally:
+        lib.zstdb200_host_free(ctypes.c_void_p(hs)); lib.zstdb200_host_free(ctypes.c_void_p(hd))
+    strided = np.zeros(2 * len(frames[0][1]), dtype=np.uint8)[::2]
+    with pytest.raises(ValueError):
+        gpu_ctx.decompress_batch([frames[0][0]], [strided])

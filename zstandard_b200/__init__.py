@@ -87,9 +87,17 @@ def error_name(code):
     return ERROR_NAMES.get((-int(code)) & 0xFFFFFFFF, "unknown") if is_error(code) else "no_error"
 
 
-def _as_u8(buf):
-    """Zero-copy uint8 view of bytes / bytearray / numpy input (read-only inputs are viewed, not copied)."""
+def _as_u8(buf, writable=False):
+    """Zero-copy uint8 view of bytes / bytearray / numpy input (read-only inputs are viewed, not copied).
+    A source that is not contiguous is copied; a destination must be written in place, so a non-contiguous (or
+    read-only) destination is an error rather than a silent copy that the caller never sees."""
     if isinstance(buf, np.ndarray):
+        if writable:
+            if not buf.flags.c_contiguous:
+                raise ValueError("destination buffers must be C-contiguous")
+            if not buf.flags.writeable:
+                raise ValueError("destination buffers must be writable")
+            return buf.view(np.uint8).reshape(-1)
         return np.ascontiguousarray(buf).view(np.uint8).reshape(-1)
     return np.frombuffer(buf, dtype=np.uint8)
 
@@ -148,7 +156,7 @@ class Context:
     def _batch(self, fn, pre, srcs, dsts):
         n = len(srcs)
         sv = [_as_u8(s) for s in srcs]
-        dv = [_as_u8(d) for d in dsts]
+        dv = [_as_u8(d, writable=True) for d in dsts]
         sp = (_c.c_void_p * n)(*[v.ctypes.data if v.size else None for v in sv])
         dp = (_c.c_void_p * n)(*[v.ctypes.data if v.size else None for v in dv])
         ss = np.array([v.size for v in sv], dtype=np.uint32)
@@ -237,11 +245,11 @@ class ZStdDecompress:
     def Decompress(dst, *args):
         if len(args) == 1:
             src = args[0]
-            dv, sv = _as_u8(dst), _as_u8(src)
+            dv, sv = _as_u8(dst, writable=True), _as_u8(src)
             cap, n = dv.size, sv.size
         elif len(args) == 3:
             cap, src, n = args
-            dv, sv = _as_u8(dst), _as_u8(src)
+            dv, sv = _as_u8(dst, writable=True), _as_u8(src)
         else:
             raise TypeError("Decompress(dst, src) or Decompress(dst, dstCapacity, src, srcSize)")
         ctx = default_context()
@@ -262,7 +270,7 @@ class ZStdCompress:
 
     @staticmethod
     def Compress(dst, src, level=3, checksum=True):
-        dv, sv = _as_u8(dst), _as_u8(src)
+        dv, sv = _as_u8(dst, writable=True), _as_u8(src)
         ctx = default_context()
         return int(load_library().zstdb200_compress(ctx.handle, int(level), 1 if checksum else 0, dv.ctypes.data if dv.size else None,
                                                     dv.size, sv.ctypes.data if sv.size else None, sv.size))

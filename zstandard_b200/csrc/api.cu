@@ -47,14 +47,18 @@ struct Device {
   cudaEvent_t descEv = nullptr;                 // descriptors of the current sub-batch are on the device
   // device memory
   u8 *d_src = nullptr, *d_dst = nullptr;       // staging for the host-pointer API
-  u64 *d_srcOff = nullptr, *d_dstOff = nullptr; u32 *d_srcSize = nullptr, *d_dstCap = nullptr, *d_result = nullptr;
+  // descriptors of one sub-batch of m items, packed so that they travel in ONE copy: [srcOff m x 8][dstOff m x 8][srcSize m x 4][dstCap m x 4]
+  u8* d_desc = nullptr;
+  // counters and results come back in ONE copy: [more NSTREAMS x 4][result maxItems x 4]
+  u32 *d_result = nullptr;
   FrameInfo* d_info = nullptr; u8* d_lit = nullptr; SeqRec* d_seq = nullptr;
   u32* d_more = nullptr;                        // per-stream counters of items with another data frame to decode (DecodeArgs::more)
   EncodeScratch enc;                            // encoder arenas (encode_kernels.cuh)
   // pinned host memory
   u8 *h_src = nullptr, *h_dst = nullptr;
-  u64 *h_srcOff = nullptr, *h_dstOff = nullptr; u32 *h_srcSize = nullptr, *h_dstCap = nullptr, *h_result = nullptr;
-  u32* h_more = nullptr;
+  u8* h_desc = nullptr;
+  u64 *h_srcOff = nullptr, *h_dstOff = nullptr; u32 *h_srcSize = nullptr, *h_dstCap = nullptr;   // views into h_desc for the current sub-batch
+  u32 *h_result = nullptr, *h_more = nullptr;
 };
 
 }  // namespace
@@ -88,15 +92,14 @@ int alloc_device(zstdb200_ctx* ctx, Device& d) {
   // be larger than the batch (compress bounds), so both buffers take the larger size
   CK(cudaMalloc(&d.d_src, ctx->srcCap + 256));
   CK(cudaMalloc(&d.d_dst, ctx->srcCap + 256));
-  CK(cudaMalloc(&d.d_srcOff, items * 8)); CK(cudaMalloc(&d.d_dstOff, items * 8));
-  CK(cudaMalloc(&d.d_srcSize, items * 4)); CK(cudaMalloc(&d.d_dstCap, items * 4)); CK(cudaMalloc(&d.d_result, items * 4));
+  CK(cudaMalloc(&d.d_desc, items * 24 + 64));
+  CK(cudaMalloc(&d.d_more, (NSTREAMS + items) * 4)); d.d_result = d.d_more + NSTREAMS;
+  CK(cudaMallocHost(&d.h_more, (NSTREAMS + items) * 4)); d.h_result = d.h_more + NSTREAMS;
   CK(cudaMalloc(&d.d_info, items * sizeof(FrameInfo)));
-  CK(cudaMalloc(&d.d_more, NSTREAMS * 4)); CK(cudaMallocHost(&d.h_more, NSTREAMS * 4));
   CK(cudaMalloc(&d.d_lit, decode_lit_arena_bytes(ctx->dstSpan, items)));
   CK(cudaMalloc(&d.d_seq, decode_seq_arena_bytes(ctx->dstSpan, items)));
   CK(cudaMallocHost(&d.h_src, ctx->srcCap + 256)); CK(cudaMallocHost(&d.h_dst, ctx->srcCap + 256));
-  CK(cudaMallocHost(&d.h_srcOff, items * 8)); CK(cudaMallocHost(&d.h_dstOff, items * 8));
-  CK(cudaMallocHost(&d.h_srcSize, items * 4)); CK(cudaMallocHost(&d.h_dstCap, items * 4)); CK(cudaMallocHost(&d.h_result, items * 4));
+  CK(cudaMallocHost(&d.h_desc, items * 24 + 64));
   CK(decode_configure());
   cudaError_t ee = encode_alloc(d.enc, ctx->maxBatch, items);
   if (ee != cudaSuccess) { ctx->err = std::string("encoder arena allocation failed: ") + cudaGetErrorString(ee); return 1; }
@@ -106,16 +109,59 @@ int alloc_device(zstdb200_ctx* ctx, Device& d) {
 void free_device(Device& d) {
   cudaSetDevice(d.id);
   for (auto& s : d.stream) if (s) cudaStreamSynchronize(s);
-  cudaFree(d.d_src); cudaFree(d.d_dst); cudaFree(d.d_srcOff); cudaFree(d.d_dstOff); cudaFree(d.d_srcSize); cudaFree(d.d_dstCap);
-  cudaFree(d.d_result); cudaFree(d.d_info); cudaFree(d.d_lit); cudaFree(d.d_seq); cudaFree(d.d_more); cudaFreeHost(d.h_more);
+  cudaFree(d.d_src); cudaFree(d.d_dst); cudaFree(d.d_desc);
+  cudaFree(d.d_info); cudaFree(d.d_lit); cudaFree(d.d_seq); cudaFree(d.d_more); cudaFreeHost(d.h_more);
   encode_free(d.enc);
-  cudaFreeHost(d.h_src); cudaFreeHost(d.h_dst); cudaFreeHost(d.h_srcOff); cudaFreeHost(d.h_dstOff); cudaFreeHost(d.h_srcSize);
-  cudaFreeHost(d.h_dstCap); cudaFreeHost(d.h_result);
+  cudaFreeHost(d.h_src); cudaFreeHost(d.h_dst); cudaFreeHost(d.h_desc);
   for (auto& s : d.stream) if (s) cudaStreamDestroy(s);
   if (d.descEv) cudaEventDestroy(d.descEv);
 }
 
 struct Range { size_t lo, hi; };
+
+// true when the driver can DMA the range directly (cudaMallocHost / cudaHostRegister memory).  A managed caller's
+// `fixed`-pinned byte[] (ZStdDecompress.cs:2182-2186) is pinned for the GC only: pageable for CUDA.
+bool is_dma_able(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// fn(lo, hi) over [0, n) on up to `maxThreads` host threads (staging copies between pageable caller memory and the
+// context's pinned buffers: one thread moves ~10 GB/s, the PCIe link wants ~50)
+template <class F>
+void parallel_for(size_t n, size_t bytes, F fn) {
+  static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const size_t want = bytes >> 22;                                   // one thread per 4 MiB
+  const size_t nt = std::min<size_t>(std::min<size_t>(hw, 16), std::min(n, want));
+  if (nt <= 1) { fn(0, n); return; }
+  std::vector<std::thread> th;
+  for (size_t t = 0; t < nt; t++) th.emplace_back(fn, n * t / nt, n * (t + 1) / nt);
+  for (auto& t : th) t.join();
+}
+
+// Sum of the frame content sizes of an item when every data frame declares one (header walk only: frame headers,
+// block headers, checksum fields — ZStdDecompress.cs:2096-2160, 2033-2067).  false = unknown / malformed.
+bool host_item_content_size(const u8* src, u32 size, u64* total) {
+  u32 pos = 0; u64 sum = 0;
+  while (true) {
+    FrameInfo fi; u32 r = 0;
+    if (!parse_item(src, size, fi, &r, pos, 0)) { if (is_err(r)) return false; *total = sum; return true; }
+    if (!(fi.flags & FI_FCS_KNOWN)) return false;
+    sum += fi.fcs;
+    if (sum > 0xFFFFFFFFull) return false;
+    u32 p = fi.body_off;
+    while (true) {
+      BlockHdr bh;
+      if (read_block_hdr(src + p, size - p, bh)) return false;
+      p += 3 + bh.csize;
+      if (bh.last) break;
+    }
+    if (fi.flags & FI_CHECKSUM) { if (size - p < 4) return false; p += 4; }
+    pos = p;
+  }
+}
 
 // Greedy split of [0, n) into consecutive sub-batches that respect the per-device arena limits.
 template <class FI, class FO>
@@ -154,6 +200,9 @@ cudaError_t decode_more_passes(Device& d, DecodeArgs a, u32 slot, cudaStream_t s
 struct Job {
   Op op; int level, checksum;
   const void* const* src; const uint32_t* srcSize; void* const* dst; const uint32_t* dstCap; uint32_t* result;
+  // Capacity each item gets on the device: min(dstCap, what a well-formed item can produce) — a caller's large reusable
+  // scratch buffer must not reserve that much of the arenas (run_host_batch).  == dstCap unless clamped.
+  const uint32_t* effCap;
 };
 
 // One sub-batch [lo, hi) on one device: slices over NSTREAMS streams, direct DMA where the layout allows.
@@ -168,27 +217,34 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     const u8 *s0 = (const u8*)j.src[i], *s1 = (const u8*)j.src[i + 1];
     if (!(s1 >= s0 + j.srcSize[i] && s1 <= s0 + j.srcSize[i] + 64)) srcDirect = false;
     const u8 *d0 = (const u8*)j.dst[i], *d1 = (const u8*)j.dst[i + 1];
-    if (d1 != d0 + j.dstCap[i]) dstDirect = false;
+    if (d1 != d0 + j.dstCap[i] || j.effCap[i] != j.dstCap[i]) dstDirect = false;
   }
+  if (j.effCap[hi - 1] != j.dstCap[hi - 1]) dstDirect = false;
   const u8* srcBase = (const u8*)j.src[lo]; u8* dstBase = (u8*)j.dst[lo];
+  // pageable caller memory goes through the pinned staging with parallel host copies (a pageable cudaMemcpyAsync
+  // is a synchronous, single-threaded bounce inside the driver)
+  if (srcDirect && !is_dma_able(srcBase)) srcDirect = false;
+  if (dstDirect && !is_dma_able(dstBase)) dstDirect = false;
   if (srcDirect) {
     const size_t span = (size_t)((const u8*)j.src[hi - 1] - srcBase) + j.srcSize[hi - 1];
     const size_t lim = j.op == Op::Decompress ? ctx->srcCap : ctx->dstSpan;
     if (span > lim || !srcBase) srcDirect = false;
   }
   if (dstDirect) {
-    const size_t span = (size_t)((u8*)j.dst[hi - 1] - dstBase) + j.dstCap[hi - 1];
+    const size_t span = (size_t)((u8*)j.dst[hi - 1] - dstBase) + j.effCap[hi - 1];
     const size_t lim = j.op == Op::Decompress ? ctx->dstSpan : ctx->srcCap;
     if (span > lim || !dstBase) dstDirect = false;
   }
-  // ---- descriptors (device offsets) ----
+  // ---- descriptors (device offsets), packed for this m ----
+  d.h_srcOff = (u64*)d.h_desc; d.h_dstOff = d.h_srcOff + m; d.h_srcSize = (u32*)(d.h_dstOff + m); d.h_dstCap = d.h_srcSize + m;
+  u64* const d_srcOff = (u64*)d.d_desc; u64* const d_dstOff = d_srcOff + m; u32* const d_srcSize = (u32*)(d_dstOff + m); u32* const d_dstCap = d_srcSize + m;
   size_t in = 0, out = 0;
   for (size_t k = 0; k < m; k++) {
     const size_t i = lo + k;
-    d.h_srcSize[k] = j.srcSize[i]; d.h_dstCap[k] = j.dstCap[i];
+    d.h_srcSize[k] = j.srcSize[i]; d.h_dstCap[k] = j.effCap[i];
     d.h_srcOff[k] = srcDirect ? (u64)((const u8*)j.src[i] - srcBase) : in;
     d.h_dstOff[k] = dstDirect ? (u64)((u8*)j.dst[i] - dstBase) : out;
-    in += align_up(j.srcSize[i], 16); out += align_up(j.dstCap[i], 16);
+    in += align_up(j.srcSize[i], 16); out += align_up(j.effCap[i], 16);
   }
   // ---- slices ----
   static const int nStreams = env_int("ZSTDB200_STREAMS", NSTREAMS, 1, NSTREAMS);
@@ -216,12 +272,11 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
   {
     cudaStream_t s0 = d.stream[0];
     e = cudaMemsetAsync(d.d_more, 0, NSTREAMS * 4, s0); if (e) return fail("memset", e);
-    e = cudaMemcpyAsync(d.d_srcOff, d.h_srcOff, m * 8, cudaMemcpyHostToDevice, s0); if (e) return fail("H2D desc", e);
-    e = cudaMemcpyAsync(d.d_dstOff, d.h_dstOff, m * 8, cudaMemcpyHostToDevice, s0); if (e) return fail("H2D desc", e);
-    e = cudaMemcpyAsync(d.d_srcSize, d.h_srcSize, m * 4, cudaMemcpyHostToDevice, s0); if (e) return fail("H2D desc", e);
-    e = cudaMemcpyAsync(d.d_dstCap, d.h_dstCap, m * 4, cudaMemcpyHostToDevice, s0); if (e) return fail("H2D desc", e);
-    e = cudaEventRecord(d.descEv, s0); if (e) return fail("event", e);
-    for (int k = 1; k < NSTREAMS; k++) { e = cudaStreamWaitEvent(d.stream[k], d.descEv, 0); if (e) return fail("event wait", e); }
+    e = cudaMemcpyAsync(d.d_desc, d.h_desc, m * 24, cudaMemcpyHostToDevice, s0); if (e) return fail("H2D desc", e);
+    if (slices.size() > 1) {
+      e = cudaEventRecord(d.descEv, s0); if (e) return fail("event", e);
+      for (int k = 1; k < NSTREAMS; k++) { e = cudaStreamWaitEvent(d.stream[k], d.descEv, 0); if (e) return fail("event wait", e); }
+    }
   }
   static const bool trace = getenv("ZSTDB200_TRACE") != nullptr;   // per-slice timeline on stderr (tuning aid)
   std::vector<cudaEvent_t> tev;
@@ -234,17 +289,19 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     if (srcDirect) {
       if (inHi > inLo) { e = cudaMemcpyAsync(d.d_src + inLo, srcBase + inLo, inHi - inLo, cudaMemcpyHostToDevice, st); if (e) return fail("H2D src", e); }
     } else {
-      for (size_t k = a; k < b; k++) if (d.h_srcSize[k]) memcpy(d.h_src + d.h_srcOff[k], j.src[lo + k], d.h_srcSize[k]);
+      parallel_for(b - a, inHi - inLo, [&](size_t x, size_t y) {
+        for (size_t k = a + x; k < a + y; k++) if (d.h_srcSize[k]) memcpy(d.h_src + d.h_srcOff[k], j.src[lo + k], d.h_srcSize[k]);
+      });
       if (inHi > inLo) { e = cudaMemcpyAsync(d.d_src + inLo, d.h_src + inLo, inHi - inLo, cudaMemcpyHostToDevice, st); if (e) return fail("H2D src", e); }
     }
     if (trace) cudaEventRecord(tev[1 + 3 * s], st);
     int nl = 0;
     if (j.op == Op::Decompress) {
-      DecodeArgs ar{d.d_src, d.d_srcOff + a, d.d_srcSize + a, d.d_dst, d.d_dstOff + a, d.d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
+      DecodeArgs ar{d.d_src, d_srcOff + a, d_srcSize + a, d.d_dst, d_dstOff + a, d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
                     d.d_info + a, d.d_lit, d.d_seq, 0, d.d_more + (s % nStreams)};
       e = decode_launch(ar, st, &nl);
     } else {
-      EncodeArgs ar{d.d_src, d.d_srcOff + a, d.d_srcSize + a, d.d_dst, d.d_dstOff + a, d.d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
+      EncodeArgs ar{d.d_src, d_srcOff + a, d_srcSize + a, d.d_dst, d_dstOff + a, d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
                     j.level, j.checksum, (u32)(s % nStreams)};
       e = encode_launch(ar, d.enc, st, &nl);
     }
@@ -258,8 +315,10 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     }
     if (trace) cudaEventRecord(tev[3 + 3 * s], st);
   }
-  for (auto& st : d.stream) { e = cudaStreamSynchronize(st); if (e) return fail("stream sync", e); }
+  // a single slice ran on stream 0 alone: its results ride the same stream and one synchronisation ends the call
+  if (slices.size() > 1) for (auto& st : d.stream) { e = cudaStreamSynchronize(st); if (e) return fail("stream sync", e); }
   if (trace) {
+    if (slices.size() == 1) cudaStreamSynchronize(d.stream[0]);
     for (size_t s = 0; s < slices.size(); s++) {
       float t1 = 0, t2 = 0, t3 = 0;
       cudaEventElapsedTime(&t1, tev[0], tev[1 + 3 * s]); cudaEventElapsedTime(&t2, tev[0], tev[2 + 3 * s]); cudaEventElapsedTime(&t3, tev[0], tev[3 + 3 * s]);
@@ -267,8 +326,7 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     }
     for (auto& x : tev) cudaEventDestroy(x);
   }
-  e = cudaMemcpyAsync(d.h_result, d.d_result, m * 4, cudaMemcpyDeviceToHost, d.stream[0]); if (e) return fail("D2H result", e);
-  e = cudaMemcpyAsync(d.h_more, d.d_more, NSTREAMS * 4, cudaMemcpyDeviceToHost, d.stream[0]); if (e) return fail("D2H counters", e);
+  e = cudaMemcpyAsync(d.h_more, d.d_more, (NSTREAMS + m) * 4, cudaMemcpyDeviceToHost, d.stream[0]); if (e) return fail("D2H results", e);
   e = cudaStreamSynchronize(d.stream[0]); if (e) return fail("stream sync", e);
   u32 anyMore = 0;
   for (int k = 0; k < NSTREAMS; k++) anyMore |= d.h_more[k];
@@ -276,7 +334,7 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     // rare path: some items hold several data frames.  Everything is still resident: decode the remaining frames
     // pass by pass over the whole sub-batch, then fetch results and output again.
     cudaStream_t st = d.stream[0]; int nl = 0;
-    DecodeArgs ar{d.d_src, d.d_srcOff, d.d_srcSize, d.d_dst, d.d_dstOff, d.d_dstCap, d.d_result, (u32)m, 0, d.d_info, d.d_lit, d.d_seq, 0, nullptr};
+    DecodeArgs ar{d.d_src, d_srcOff, d_srcSize, d.d_dst, d_dstOff, d_dstCap, d.d_result, (u32)m, 0, d.d_info, d.d_lit, d.d_seq, 0, nullptr};
     e = decode_more_passes(d, ar, 0, st, &nl); *launches += nl;
     if (e) return fail("multi-frame passes", e);
     e = cudaMemcpyAsync(d.h_result, d.d_result, m * 4, cudaMemcpyDeviceToHost, st); if (e) return fail("D2H result", e);
@@ -284,25 +342,49 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     if (outHi > outLo) { e = cudaMemcpyAsync(dstDirect ? dstBase + outLo : d.h_dst + outLo, d.d_dst + outLo, outHi - outLo, cudaMemcpyDeviceToHost, st); if (e) return fail("D2H dst", e); }
     e = cudaStreamSynchronize(st); if (e) return fail("stream sync", e);
   }
-  for (size_t k = 0; k < m; k++) {
-    const size_t i = lo + k; const u32 r = d.h_result[k];
-    j.result[i] = r;
-    // staged output: copy what was produced; on error the reference leaves dst partially written, we copy nothing
-    if (!dstDirect && !is_err(r) && r) memcpy(j.dst[i], d.h_dst + d.h_dstOff[k], std::min<u32>(r, j.dstCap[i]));
-  }
+  for (size_t k = 0; k < m; k++) j.result[lo + k] = d.h_result[k];
+  // staged output: copy what was produced; on error the reference leaves dst partially written, we copy nothing
+  if (!dstDirect) parallel_for(m, d.h_dstOff[m - 1] + d.h_dstCap[m - 1], [&](size_t x, size_t y) {
+    for (size_t k = x; k < y; k++) {
+      const size_t i = lo + k; const u32 r = d.h_result[k];
+      if (!is_err(r) && r) memcpy(j.dst[i], d.h_dst + d.h_dstOff[k], std::min<u32>(r, j.dstCap[i]));
+    }
+  });
   return "";
 }
 
-int run_host_batch(zstdb200_ctx* ctx, const Job& j, size_t n) {
+int run_host_batch(zstdb200_ctx* ctx, const Job& j0, size_t n, bool clamp = true) {
   if (n == 0) return 0;
-  if (!j.src || !j.srcSize || !j.dst || !j.dstCap || !j.result) { ctx->err = "null argument"; return 1; }
+  if (!j0.src || !j0.srcSize || !j0.dst || !j0.dstCap || !j0.result) { ctx->err = "null argument"; return 1; }
   // staging limits.  decode: in = frames (d_src, srcCap), out = content (dstSpan: what the literal / sequence arenas
   // are sized for); encode: in = raw chunks (dstSpan: what the encoder arenas are sized for), out = frames (d_dst, srcCap)
-  const size_t maxIn = j.op == Op::Decompress ? ctx->srcCap : ctx->dstSpan;
-  const size_t maxOut = j.op == Op::Decompress ? ctx->dstSpan : ctx->srcCap;
+  const size_t maxIn = j0.op == Op::Decompress ? ctx->srcCap : ctx->dstSpan;
+  const size_t maxOut = j0.op == Op::Decompress ? ctx->dstSpan : ctx->srcCap;
+  // Device-side capacity per item.  The reference accepts any dstCapacity (a small frame into a large reusable scratch
+  // buffer is fine, ZStdDecompress.cs:2182-2191), so the arenas must not be sized by it:
+  //  * compress: no frame is larger than compress_bound(srcSize);
+  //  * decompress: when every data frame of the item declares its content size, a well-formed item produces exactly
+  //    their sum.  A malformed one may try to produce more; its dstSize_tooSmall under the clamped capacity says
+  //    nothing about the caller's real one, so such items are run again below with the caller's capacity;
+  //  * either way at most what the arena of a lone item holds (the limit of this context, reported as an error).
+  std::vector<uint32_t> eff(n);
+  const size_t lone = (maxOut & ~(size_t)15) - 16;
+  for (size_t i = 0; i < n; i++) {
+    uint64_t c = j0.dstCap[i];
+    if (clamp) {
+      if (j0.op == Op::Compress) c = std::min<uint64_t>(c, encode_bound(j0.srcSize[i]));
+      else if (j0.src[i] && j0.srcSize[i] >= 5) {
+        const u64 declared = zstdb200_get_decompressed_size(j0.src[i], j0.srcSize[i]);   // first frame's header only: cheap filter
+        u64 total;
+        if (declared && declared < c && host_item_content_size((const u8*)j0.src[i], j0.srcSize[i], &total)) c = std::min<uint64_t>(c, total);
+      }
+    }
+    eff[i] = (uint32_t)std::min<uint64_t>(c, lone);
+  }
+  Job j = j0; j.effCap = eff.data();
   bool tooBig = false;
   std::vector<Range> subs = make_subbatches(n, maxIn, maxOut, ctx->maxItems,
-      [&](size_t i) { return (size_t)j.srcSize[i]; }, [&](size_t i) { return (size_t)j.dstCap[i]; }, &tooBig);
+      [&](size_t i) { return (size_t)j.srcSize[i]; }, [&](size_t i) { return (size_t)j.effCap[i]; }, &tooBig);
   if (tooBig) { ctx->err = "an item is larger than the context's max_batch_bytes"; return 1; }
   // a single sub-batch on a multi-GPU context is re-cut so that every device gets a share
   const size_t nd = ctx->dev.size();
@@ -312,12 +394,12 @@ int run_host_batch(zstdb200_ctx* ctx, const Job& j, size_t n) {
       // equal shares of bytes (in + out), not of items: a raw-block frame costs a copy, a text frame a full decode
       const size_t parts = std::min(nd, r.hi - r.lo);
       uint64_t total = 0;
-      for (size_t i = r.lo; i < r.hi; i++) total += (uint64_t)j.srcSize[i] + j.dstCap[i] + 1;
+      for (size_t i = r.lo; i < r.hi; i++) total += (uint64_t)j.srcSize[i] + j.effCap[i] + 1;
       size_t lo = r.lo; uint64_t acc = 0;
       for (size_t p = 0; p < parts; p++) {
         size_t hi = lo;
         const uint64_t want = total * (p + 1) / parts;
-        while (hi < r.hi && (acc < want || hi == lo) && (r.hi - hi) > (parts - 1 - p)) { acc += (uint64_t)j.srcSize[hi] + j.dstCap[hi] + 1; hi++; }
+        while (hi < r.hi && (acc < want || hi == lo) && (r.hi - hi) > (parts - 1 - p)) { acc += (uint64_t)j.srcSize[hi] + j.effCap[hi] + 1; hi++; }
         if (p + 1 == parts) hi = r.hi;
         cut.push_back({lo, hi}); lo = hi;
       }
@@ -339,6 +421,19 @@ int run_host_batch(zstdb200_ctx* ctx, const Job& j, size_t n) {
   else { std::vector<std::thread> th; for (size_t di = 0; di < nd; di++) th.emplace_back(worker, di); for (auto& t : th) t.join(); }
   for (size_t di = 0; di < nd; di++) ctx->launches += launches[di];
   for (size_t di = 0; di < nd; di++) if (!errs[di].empty()) { ctx->err = "device " + std::to_string(ctx->dev[di].id) + ": " + errs[di]; return 1; }
+  // items that ran out of a capacity smaller than the caller's: once more with the real one (malformed frames that
+  // overshoot their declared size, or items larger than what the arenas were clamped to)
+  std::vector<size_t> again;
+  for (size_t i = 0; i < n; i++) if (eff[i] < j.dstCap[i] && j.result[i] == zerr(ZE_dstSize_tooSmall)) again.push_back(i);
+  if (!again.empty()) {
+    if (!clamp) { ctx->err = "an item is larger than the context's max_batch_bytes"; return 1; }
+    const size_t m = again.size();
+    std::vector<const void*> s2(m); std::vector<void*> d2(m); std::vector<uint32_t> ss2(m), dc2(m), r2(m);
+    for (size_t k = 0; k < m; k++) { const size_t i = again[k]; s2[k] = j.src[i]; d2[k] = j.dst[i]; ss2[k] = j.srcSize[i]; dc2[k] = j.dstCap[i]; }
+    Job jr{j.op, j.level, j.checksum, s2.data(), ss2.data(), d2.data(), dc2.data(), r2.data(), nullptr};
+    if (run_host_batch(ctx, jr, m, false)) return 1;
+    for (size_t k = 0; k < m; k++) j.result[again[k]] = r2[k];
+  }
   return 0;
 }
 
@@ -409,7 +504,7 @@ int zstdb200_decompress_batch(zstdb200_ctx* ctx, const void* const* src, const u
                               void* const* dst, const uint32_t* dstCap, uint32_t* result, size_t n) {
   if (!ctx) return 1;
   ctx->err.clear();
-  Job j{Op::Decompress, 0, 0, src, srcSize, dst, dstCap, result};
+  Job j{Op::Decompress, 0, 0, src, srcSize, dst, dstCap, result, nullptr};
   return run_host_batch(ctx, j, n);
 }
 
@@ -417,8 +512,8 @@ uint32_t zstdb200_decompress(zstdb200_ctx* ctx, void* dst, uint32_t dstCapacity,
   uint32_t r = zerr(ZE_GENERIC);
   const void* s = src; void* d = dst;
   static unsigned char dummy[16];
-  if (!d) d = dummy;
-  if (!s) s = dummy;
+  if (!d) { d = dummy; dstCapacity = 0; }        // a null array is an empty one (the C# shim passes null for byte[0])
+  if (!s) { s = dummy; srcSize = 0; }
   if (zstdb200_decompress_batch(ctx, &s, &srcSize, &d, &dstCapacity, &r, 1)) return zerr(ZE_GENERIC);
   return r;
 }
@@ -481,7 +576,7 @@ int zstdb200_compress_batch(zstdb200_ctx* ctx, int level, int checksum, const vo
   if (!ctx) return 1;
   ctx->err.clear();
   if (level < 1 || level > 3) { ctx->err = "level must be 1..3"; return 1; }
-  Job j{Op::Compress, level, checksum, src, srcSize, dst, dstCap, result};
+  Job j{Op::Compress, level, checksum, src, srcSize, dst, dstCap, result, nullptr};
   return run_host_batch(ctx, j, n);
 }
 
@@ -489,8 +584,8 @@ uint32_t zstdb200_compress(zstdb200_ctx* ctx, int level, int checksum, void* dst
   uint32_t r = zerr(ZE_GENERIC);
   const void* s = src; void* d = dst;
   static unsigned char dummy[16];
-  if (!s) s = dummy;
-  if (!d) d = dummy;
+  if (!s) { s = dummy; srcSize = 0; }
+  if (!d) { d = dummy; dstCapacity = 0; }
   if (zstdb200_compress_batch(ctx, level, checksum, &s, &srcSize, &d, &dstCapacity, &r, 1)) return zerr(ZE_GENERIC);
   return r;
 }
