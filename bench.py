@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--level", type=int, default=3)
     ap.add_argument("--chunk", type=int, default=0, help="frame / chunk size in bytes (default: the workload's 64 KiB / 128 KiB)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the compress block, the pageable / single-call / single-context measurements")
     return ap.parse_args()
 
 
@@ -113,19 +114,22 @@ class ClockSampler(threading.Thread):
 # ----------------------------------------------------------------------------------------------------------
 # workload: host-side description of one step.  `src` is the codec's input, `dst` its output.
 # ----------------------------------------------------------------------------------------------------------
-def prepare(args, rank):
+def prepare(args, rank, workload=None, level=None, raw=None):
     from tools import corpus, zstd_ref
     import zstandard_b200 as zb
-    chunk = args.chunk or CHUNK[args.workload]
-    raw = corpus.make(args.corpus, args.bytes, shard=rank)
+    workload = workload or args.workload
+    level = level or args.level
+    chunk = (args.chunk if workload == args.workload else 0) or CHUNK[workload]
+    if raw is None:
+        raw = corpus.make(args.corpus, args.bytes, shard=rank)
     total = len(raw)
     n = (total + chunk - 1) // chunk
     raw_off = np.arange(n + 1, dtype=np.uint64) * chunk
     raw_off[-1] = total
-    w = {"raw": raw, "chunk": chunk, "n": n, "total": total, "kind": args.workload}
-    blob, off = zstd_ref.compress_chunks(raw, chunk, level=args.level, checksum=True, threads=max(1, os.cpu_count() or 1))
+    w = {"raw": raw, "chunk": chunk, "n": n, "total": total, "kind": workload, "level": level}
+    blob, off = zstd_ref.compress_chunks(raw, chunk, level=level, checksum=True, threads=max(1, os.cpu_count() or 1))
     w["ref_compressed_bytes"] = int(off[-1])
-    if args.workload == "decode64k":
+    if workload == "decode64k":
         w.update(src=blob, src_off=off, dst_cap=np.diff(raw_off).astype(np.uint32), dst_stride=chunk)
     else:
         bound = (zb.ZStdCompress.CompressBound(chunk) + 15) // 16 * 16
@@ -135,10 +139,10 @@ def prepare(args, rank):
 
 def workload_config(args, w):
     if w["kind"] == "decode64k":
-        what = (f"decode{w['chunk'] // 1024}k: batched decompression of {w['total']} B/GPU of libzstd-1.5.5 level-{args.level} {args.corpus} text held as "
+        what = (f"decode{w['chunk'] // 1024}k: batched decompression of {w['total']} B/GPU of libzstd-1.5.5 level-{w['level']} {args.corpus} text held as "
                 f"{w['chunk'] // 1024} KiB independent frames with XXH64 checksums")
     else:
-        what = (f"compress{w['chunk'] // 1024}k: batched level-{args.level} compression of {w['total']} B/GPU of {args.corpus} text in "
+        what = (f"compress{w['chunk'] // 1024}k: batched level-{w['level']} compression of {w['total']} B/GPU of {args.corpus} text in "
                 f"{w['chunk'] // 1024} KiB chunks, one frame each, with XXH64 checksums")
     return {"workload": what, "frames_per_gpu": w["n"], "libzstd_compressed_bytes_per_gpu": w["ref_compressed_bytes"],
             "libzstd_ratio": round(w["total"] / w["ref_compressed_bytes"], 4),
@@ -187,7 +191,7 @@ class CpuBaseline:
             assert (self.res == self.dc).all(), "oracle failed to decode the workload"
         else:
             from tools import zstd_ref
-            zstd_ref.compress_chunks(w["raw"], w["chunk"], level=self.args.level, checksum=True, threads=self.cores)
+            zstd_ref.compress_chunks(w["raw"], w["chunk"], level=w["level"], checksum=True, threads=self.cores)
             dt = time.perf_counter() - t
         return dt, w["total"]
 
@@ -232,31 +236,44 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def main():
-    args = parse_args()
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    if args.impl == "reference":
-        run_reference(args, rank)
-        return
+class Gpu:
+    """One rank's device, context and (optional) process group."""
 
-    import torch
-    import zstandard_b200 as zb
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+    def __init__(self, args):
+        import torch
+        import zstandard_b200 as zb
+        self.torch, self.zb = torch, zb
+        self.rank = int(os.environ.get("RANK", 0))
+        self.world = int(os.environ.get("WORLD_SIZE", 1))
+        self.local = int(os.environ.get("LOCAL_RANK", 0))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        self.lib = zb.load_library()
+        self.ctx = zb.Context(devices=[self.local], max_batch_bytes=max(args.bytes, 1 << 20))
 
-    w = prepare(args, rank)
-    n, total, decode = w["n"], w["total"], w["kind"] == "decode64k"
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.dist:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+
+
+def measure(g, args, w, steps, warmup, sampler=None, extras=False):
+    """One workload on this rank's GPU: device-resident pipeline (CUDA events, max over ranks), per-kernel times, and the
+    host-buffer C-ABI call from pinned memory.  extras: also pageable caller memory and the single-item call (decode)."""
+    torch, ctx, lib, dev = g.torch, g.ctx, g.lib, g.dev
+    n, total, decode, level = w["n"], w["total"], w["kind"] == "decode64k", w["level"]
     src_bytes = int(w["src_off"][-1])
     dst_span = n * w["dst_stride"]
-    ctx = zb.Context(devices=[local], max_batch_bytes=max(total, 1 << 20))
-    lib = zb.load_library()
-
     # ---------------- device-resident arm ----------------
     t_src = torch.empty(src_bytes + 64, dtype=torch.uint8, device=dev)
     t_src[:src_bytes] = torch.from_numpy(w["src"]).to(dev)
@@ -281,7 +298,7 @@ def main():
         if decode:
             ctx.decompress_batch_device(*dargs, stream=stream)
         else:
-            ctx.compress_batch_device(args.level, True, *dargs, stream=stream)
+            ctx.compress_batch_device(level, True, *dargs, stream=stream)
 
     def verify(res_u32, out_bytes):
         """what is being timed must be right: decode -> the corpus; compress -> frames an independent decoder accepts"""
@@ -298,89 +315,193 @@ def main():
             assert zstd_ref.decompress(f, int(ssz[k])) == w["raw"][lo:lo + int(ssz[k])].tobytes(), "frame does not round-trip"
         return int(res_u32.astype(np.int64).sum())
 
-    for _ in range(max(3, args.warmup)):
+    for _ in range(max(3, warmup)):
         step_device()
     torch.cuda.synchronize()
     our_compressed = verify(t_res.cpu().numpy().view(np.uint32), t_dst.cpu().numpy())
 
-    sampler = ClockSampler(local)
-    sampler.start()
+    if sampler:
+        sampler.start()
     l0 = ctx.kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if dist:
-        dist.barrier()
+    g.barrier()
     torch.cuda.synchronize()
     ev0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_device()
     ev1.record()
     torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
-    ms = ev0.elapsed_time(ev1)
+    g.barrier()
+    ms = g.max_over_ranks(ev0.elapsed_time(ev1))
     launches = ctx.kernel_launches - l0
-    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if dist:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms = float(t_ms.item())
 
     # per-kernel device times (CUDA events between the kernels, separate synchronised runs)
     kms = {}
-    reps = max(3, args.steps)
-    if decode:
-        for _ in range(reps):
-            for k, v in ctx.decompress_batch_device_timed(*dargs, stream=stream).items():
-                kms[k] = kms.get(k, 0.0) + v / reps
-    else:
-        for _ in range(reps):
-            for k, v in ctx.compress_batch_device_timed(args.level, True, *dargs, stream=stream).items():
-                kms[k] = kms.get(k, 0.0) + v / reps
-    dom = max(kms, key=kms.get)
-    out_bytes_algo = total if decode else our_compressed
-    algo_bytes = src_bytes + out_bytes_algo
-    peak, peak_src = measured_peak()
-    achieved = algo_bytes / (kms[dom] * 1e-3) / 1e9
+    reps = max(3, steps)
+    for _ in range(reps):
+        per = ctx.decompress_batch_device_timed(*dargs, stream=stream) if decode else ctx.compress_batch_device_timed(level, True, *dargs, stream=stream)
+        for k, v in per.items():
+            kms[k] = kms.get(k, 0.0) + v / reps
+    del t_src, t_dst
 
     # ---------------- end-to-end arm: host buffers through the C ABI ----------------
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    ss_u, dc_u, res_u = ssz.view(np.uint32).copy(), w["dst_cap"].copy(), np.zeros(n, dtype=np.uint32)
+
+    def host_call(sp, dp, cnt=n):
+        if decode:
+            rc = lib.zstdb200_decompress_batch(ctx.handle, sp, ss_u.ctypes.data_as(u32p), dp, dc_u.ctypes.data_as(u32p),
+                                               res_u.ctypes.data_as(u32p), cnt)
+        else:
+            rc = lib.zstdb200_compress_batch(ctx.handle, level, 1, sp, ss_u.ctypes.data_as(u32p), dp, dc_u.ctypes.data_as(u32p),
+                                             res_u.ctypes.data_as(u32p), cnt)
+        assert rc == 0, ctx.last_error()
+
+    def timed_host(sp, dp, dst_view, k_steps):
+        for _ in range(max(1, min(warmup, 2))):
+            host_call(sp, dp)
+        verify(res_u, dst_view)
+        g.barrier()
+        t0 = time.perf_counter()
+        for _ in range(k_steps):
+            host_call(sp, dp)
+        return g.max_over_ranks(time.perf_counter() - t0)
+
     h_src = lib.zstdb200_host_alloc(src_bytes + 64)
     h_dst = lib.zstdb200_host_alloc(dst_span + 64)
     ctypes.memmove(h_src, w["src"].ctypes.data, src_bytes)
     sp = (ctypes.c_void_p * n)(*[h_src + int(w["src_off"][i]) for i in range(n)])
     dp = (ctypes.c_void_p * n)(*[h_dst + i * w["dst_stride"] for i in range(n)])
-    ss_u, dc_u, res_u = ssz.view(np.uint32).copy(), w["dst_cap"].copy(), np.zeros(n, dtype=np.uint32)
-    u32p = ctypes.POINTER(ctypes.c_uint32)
-
-    def step_e2e():
-        if decode:
-            rc = lib.zstdb200_decompress_batch(ctx.handle, sp, ss_u.ctypes.data_as(u32p), dp, dc_u.ctypes.data_as(u32p),
-                                               res_u.ctypes.data_as(u32p), n)
-        else:
-            rc = lib.zstdb200_compress_batch(ctx.handle, args.level, 1, sp, ss_u.ctypes.data_as(u32p), dp, dc_u.ctypes.data_as(u32p),
-                                             res_u.ctypes.data_as(u32p), n)
-        assert rc == 0, ctx.last_error()
-
-    for _ in range(max(1, min(args.warmup, 2))):
-        step_e2e()
     got = np.ctypeslib.as_array(ctypes.cast(h_dst, ctypes.POINTER(ctypes.c_uint8)), shape=(dst_span,))
-    verify(res_u, got)
-    if dist:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    e2e_s = time.perf_counter() - t0
-    sampler.stop_flag = True      # clocks are sampled through both timed regions (device-resident and host-buffer)
-    sampler.join()
-    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if dist:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_s = float(t_e.item())
+    e2e_s = timed_host(sp, dp, got, steps)
     lib.zstdb200_host_free(h_src)
     lib.zstdb200_host_free(h_dst)
 
+    out = {"ms": ms, "steps": steps, "launches": int(launches), "kernel_ms": kms, "our_compressed": our_compressed, "e2e_s": e2e_s,
+           "src_bytes": src_bytes, "n": n, "total": total}
+    if extras and decode:
+        # the memory a managed caller really has: pageable (a `fixed` byte[] is pinned for the GC, not for CUDA,
+        # ZStdDecompress.cs:2182-2186) — one contiguous array pair, and one separate array per frame
+        p_dst = np.zeros(dst_span + 64, dtype=np.uint8)
+        sp2 = (ctypes.c_void_p * n)(*[w["src"].ctypes.data + int(w["src_off"][i]) for i in range(n)])
+        dp2 = (ctypes.c_void_p * n)(*[p_dst.ctypes.data + i * w["dst_stride"] for i in range(n)])
+        k_steps = max(1, min(steps, 3))
+        out["e2e_pageable_s"] = timed_host(sp2, dp2, p_dst, k_steps) / k_steps
+        srcs = [w["src"][int(w["src_off"][i]):int(w["src_off"][i + 1])].copy() for i in range(n)]
+        dsts = [np.zeros(int(w["dst_cap"][i]), dtype=np.uint8) for i in range(n)]
+        sp3 = (ctypes.c_void_p * n)(*[a.ctypes.data for a in srcs])
+        dp3 = (ctypes.c_void_p * n)(*[a.ctypes.data for a in dsts])
+        host_call(sp3, dp3)
+        assert all((dsts[i] == w["raw"][i * w["chunk"]:i * w["chunk"] + len(dsts[i])]).all() for i in range(0, n, max(1, n // 64)))
+        t0 = time.perf_counter()
+        for _ in range(k_steps):
+            host_call(sp3, dp3)
+        out["e2e_scattered_s"] = g.max_over_ranks(time.perf_counter() - t0) / k_steps
+        # one frame per call: ZStdDecompress.Decompress(byte[], uint, byte[], uint) as the shim issues it
+        lib.zstdb200_decompress.restype = ctypes.c_uint32
+        lib.zstdb200_decompress.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32]
+        one = []
+        for k in range(24):
+            i = (k * 37) % n
+            t0 = time.perf_counter()
+            r = lib.zstdb200_decompress(ctx.handle, dsts[i].ctypes.data, len(dsts[i]), srcs[i].ctypes.data, len(srcs[i]))
+            one.append(time.perf_counter() - t0)
+            assert r == len(dsts[i])
+        out["single_call_us"] = float(np.median(one[4:]) * 1e6)
+    return out
+
+
+def single_context_all_devices(g, args, w, steps):
+    """Rank 0 drives ONE context over all N devices of the box (the library's own sharding: sub-batches dealt to one
+    host thread per device, api.cu run_host_batch) on N x the per-GPU workload; verified against the corpus."""
+    zb, lib = g.zb, g.lib
+    N, n, total = g.world, w["n"], w["total"]
+    src_bytes, stride = int(w["src_off"][-1]), w["dst_stride"]
+    ctx = zb.Context(devices=list(range(N)), max_batch_bytes=max(total, 1 << 20))
+    try:
+        span_s = (src_bytes + 63) // 64 * 64
+        h_src = lib.zstdb200_host_alloc(N * span_s + 64)
+        h_dst = lib.zstdb200_host_alloc(N * n * stride + 64)
+        for k in range(N):
+            ctypes.memmove(h_src + k * span_s, w["src"].ctypes.data, src_bytes)
+        sp = (ctypes.c_void_p * (N * n))(*[h_src + k * span_s + int(w["src_off"][i]) for k in range(N) for i in range(n)])
+        dp = (ctypes.c_void_p * (N * n))(*[h_dst + (k * n + i) * stride for k in range(N) for i in range(n)])
+        ss = np.tile(np.diff(w["src_off"]).astype(np.uint32), N)
+        dc = np.tile(w["dst_cap"], N)
+        res = np.zeros(N * n, dtype=np.uint32)
+        u32p = ctypes.POINTER(ctypes.c_uint32)
+        call = lambda: lib.zstdb200_decompress_batch(ctx.handle, sp, ss.ctypes.data_as(u32p), dp, dc.ctypes.data_as(u32p), res.ctypes.data_as(u32p), N * n)
+        assert call() == 0, ctx.last_error()
+        assert (res == dc).all()
+        got = np.ctypeslib.as_array(ctypes.cast(h_dst, ctypes.POINTER(ctypes.c_uint8)), shape=(N * n * stride,))
+        for k in range(N):
+            assert (got[k * n * stride:k * n * stride + total] == w["raw"]).all(), "single-context decode differs from the corpus"
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            assert call() == 0
+        dt = time.perf_counter() - t0
+        lib.zstdb200_host_free(h_src)
+        lib.zstdb200_host_free(h_dst)
+        return {"value": round(N * total * steps / dt / 1e9, 3), "unit": "GB/s", "devices": N,
+                "what": "one process, one zstdb200 context over all devices, pinned host buffers, verified against the corpus"}
+    finally:
+        ctx.close()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    g = Gpu(args)
+    world = g.world
+    w = prepare(args, g.rank)
+    decode = w["kind"] == "decode64k"
+    sampler = ClockSampler(g.local)
+    m = measure(g, args, w, args.steps, args.warmup, sampler=sampler, extras=not args.no_extras)
+    sampler.stop_flag = True      # clocks are sampled through both timed regions (device-resident and host-buffer)
+    sampler.join()
+    n, total, src_bytes, ms, kms = m["n"], m["total"], m["src_bytes"], m["ms"], m["kernel_ms"]
+    our_compressed = m["our_compressed"]
+    dom = max(kms, key=kms.get)
+    algo_bytes = src_bytes + (total if decode else our_compressed)
+    peak, peak_src = measured_peak()
+    achieved = algo_bytes / (kms[dom] * 1e-3) / 1e9
+
+    # ---------------- the other direction of BASELINE.json's metric (configs[2]): compression at levels 1-3 ----------------
+    compress = None
+    if decode and args.corpus == "log" and not args.chunk and not args.no_extras:
+        compress = {}
+        for lvl in (1, 2, 3):
+            wc = prepare(args, g.rank, workload="compress128k", level=lvl, raw=w["raw"])
+            k_steps = max(2, min(args.steps, 3))
+            mc = measure(g, args, wc, k_steps, 3)
+            cdom = max(mc["kernel_ms"], key=mc["kernel_ms"].get)
+            calgo = mc["src_bytes"] + mc["our_compressed"]
+            compress[f"L{lvl}"] = {
+                "value": round(total * world * k_steps / (mc["ms"] * 1e-3) / 1e9, 3), "unit": "GB/s",
+                "e2e": round(total * world * k_steps / mc["e2e_s"] / 1e9, 3),
+                "our_ratio": round(total / mc["our_compressed"], 4), "libzstd_ratio": round(total / wc["ref_compressed_bytes"], 4),
+                "kernel_ms": {k: round(v, 3) for k, v in mc["kernel_ms"].items()},
+                "roofline_frac": round(calgo / (mc["kernel_ms"][cdom] * 1e-3) / 1e9 / peak, 5), "roofline_kernel": cdom,
+                "pipeline_frac": round(calgo * k_steps / (mc["ms"] * 1e-3) / 1e9 / peak, 5), "gpu_launches": mc["launches"]}
+        compress["workload"] = (f"compress128k: {total} B/GPU of log text in 128 KiB chunks, one frame each with XXH64; ratio comparator = libzstd 1.5.5 at the "
+                                "same level (the reference has no compressor: ratio parity is unpinned by the reference)")
+
+    single = None
+    if world > 1 and decode and not args.no_extras:
+        g.barrier()
+        if g.rank == 0:
+            try:
+                single = single_context_all_devices(g, args, w, max(1, min(args.steps, 3)))
+            except Exception as e:      # e.g. host memory for N x the workload is not available on this box
+                single = {"unavailable": str(e)[:200]}
+        g.barrier()
+
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu, cpu_libzstd = None, None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if g.rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = CpuBaseline(args, w)
         cb.run()
         tt, nb, runs = 0.0, 0, 0
@@ -391,22 +512,23 @@ def main():
                "sample": f"{runs} pass(es) over the full step ({n} frames, {total} B) = {tt * cb.cores:.1f} core-seconds; {cb.what}"}
         cpu_libzstd = libzstd_decode_baseline(cb) if decode else None
 
-    if rank == 0:
-        value = total * world * args.steps / (ms * 1e-3) / 1e9
+    if g.rank == 0:
+        steps = args.steps
+        value = total * world * steps / (ms * 1e-3) / 1e9
         d2h = (total if decode else our_compressed) + n * 4
         line = {
             "metric": METRIC[args.workload], "value": round(value, 3), "unit": "GB/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+            "steps": steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms / steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(args, w),
-            "e2e": {"value": round(total * world * args.steps / e2e_s / 1e9, 3), "unit": "GB/s",
+            "e2e": {"value": round(total * world * steps / m["e2e_s"] / 1e9, 3), "unit": "GB/s",
                     "h2d_bytes_per_step": int(src_bytes + n * 24), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(launches),
+            "gpu_launches": m["launches"],
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
                          "traffic": recorded_traffic(f"{args.workload}/{args.corpus}/{w['chunk']}/{total}/L{args.level}", dom), "kernel": dom, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo_bytes),
-                         "pipeline_frac": round(algo_bytes * args.steps / (ms * 1e-3) / 1e9 / peak, 5)},
+                         "pipeline_frac": round(algo_bytes * steps / (ms * 1e-3) / 1e9 / peak, 5)},
             "kernel_ms": {k: round(v, 4) for k, v in kms.items()},
             "cpu_baseline": cpu,
         }
@@ -415,10 +537,18 @@ def main():
         if not decode:
             line["config"]["our_compressed_bytes_per_gpu"] = our_compressed
             line["config"]["our_ratio"] = round(total / our_compressed, 4)
+        if "e2e_pageable_s" in m:
+            line["e2e_pageable"] = {"contiguous": round(total * world / m["e2e_pageable_s"] / 1e9, 3), "scattered": round(total * world / m["e2e_scattered_s"] / 1e9, 3),
+                                    "unit": "GB/s", "what": "the same C-ABI call on pageable (malloc / numpy) caller memory: one array pair, and one array per frame"}
+            line["single_call_us"] = round(m["single_call_us"], 1)
+        if compress:
+            line["compress"] = compress
+        if single:
+            line["e2e_single_ctx"] = single
         print(json.dumps(line), flush=True)
-    ctx.close()
-    if dist:
-        dist.destroy_process_group()
+    g.ctx.close()
+    if g.dist:
+        g.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

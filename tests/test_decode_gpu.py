@@ -267,8 +267,8 @@ def test_one_context_over_two_devices(oracle):
 
 
 def test_batches_larger_than_the_context_arena_are_cut_into_sub_batches():
-    """A small context (4 MiB of arena) takes a 24 MiB batch in several sub-batches; an item that cannot fit at all is
-    a batch-level error (`zstdb200_last_error`), not a crash."""
+    """A small context (4 MiB of arena) takes a 24 MiB batch in several sub-batches; an item whose content cannot fit at
+    all is a batch-level error (`zstdb200_last_error`), not a crash."""
     import zstandard_b200 as zb
     from tools import corpus, zstd_ref
     ctx = zb.Context(max_batch_bytes=4 << 20)
@@ -287,8 +287,13 @@ def test_batches_larger_than_the_context_arena_are_cut_into_sub_batches():
         cres = ctx.compress_batch(chunks, outs, level=1, checksum=True)
         for k in range(0, n, 11):
             assert zstd_ref.decompress(outs[k][:int(cres[k])].tobytes(), chunk) == chunks[k].tobytes()
+        # a destination larger than the arena is fine as long as the content fits (capacity clamp, api.cu) ...
+        big = np.zeros(8 << 20, dtype=np.uint8)
+        assert int(ctx.decompress_batch([srcs[0]], [big])[0]) == chunk and (big[:chunk] == raw[:chunk]).all()
+        # ... an item whose content cannot fit at all is the batch-level error
+        huge = zstd_ref.compress(raw[:8 << 20].tobytes(), 1, checksum=False)
         with pytest.raises(RuntimeError):
-            ctx.decompress_batch([srcs[0]], [np.zeros(8 << 20, dtype=np.uint8)])
+            ctx.decompress_batch([huge], [big])
     finally:
         ctx.close()
 

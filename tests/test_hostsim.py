@@ -114,3 +114,15 @@ def test_repeat_mode_tables(hostsim, oracle):
             rh, oh = hostsim.decompress(f, cap, oracle)
             assert ro == rh and oo == oh
         assert oracle.decompress(f, len(data))[1] == data
+
+
+def test_maximum_match_length_records(hostsim, oracle):
+    """A block that is one repeat-offset match of 131 072 bytes (matchLength needs 18 bits in the sequence record), and
+    frames of long runs in general."""
+    from tools import zstd_ref
+    for data in (bytes(1 << 20), b"ab" * (300 << 10), bytes(131072 + 7)):
+        frame = zstd_ref.compress(data, 3, checksum=True)
+        want, out, _ = oracle.decompress(frame, len(data))
+        assert want == len(data) and out == data
+        r, got = hostsim.decompress(frame, len(data), oracle)
+        assert r == want and got == data

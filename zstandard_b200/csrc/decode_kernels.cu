@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(EXEC_THREADS, 16) k_exec(DecodeArgs a) {
           const bool valid = g0 + lane < nRecs;
           const uint4 rec = valid ? __ldg(rv + g0 + lane) : make_uint4(0, 0, 0, 0);
           if (lane < 2 && g0 + 32 < nRecs) prefetch_line(rv + g0 + 32 + 16 * lane);   // next group's 512 bytes
-          const u32 ll = valid ? (rec.w & 0x1FFFF) : 0, ml = valid ? ((rec.w >> 17) | (((rec.y >> 18) & 3) << 15)) : 0, off = rec.z, lpos = rec.y & 0x3FFFF;
+          const u32 ll = valid ? (rec.w & 0x1FFFF) : 0, ml = valid ? ((rec.w >> 17) | (((rec.y >> 18) & 7) << 15)) : 0, off = rec.z, lpos = rec.y & 0x3FFFF;
           // checks in the reference's order (:1278, :1279, :1290-1294)
           const u64 start64 = (u64)blockBase + rec.x;
           const bool e1 = valid && start64 + ll + ml > cap;

@@ -17,7 +17,7 @@ namespace zb {
 //   x = dpos : output position of the sequence's literal run, relative to the block's first output byte
 //              (saturates at 0xFFFFFFFF: such a record can never pass the capacity check)
 //   y = lpos (18 bits: position of its literals within the block's literals, saturates at 0x3FFFF)
-//       | matchLength >> 15 << 18 (2 bits)
+//       | matchLength >> 15 << 18 (3 bits: matchLength <= 131074)
 //   z = offset (>= 1 for a well-formed match; garbage offsets of corrupted streams use all 32 bits)
 //   w = litLength (17 bits) | (matchLength & 0x7FFF) << 17
 // The records of one compressed block are preceded by one header record:
@@ -32,7 +32,7 @@ ZB_HD void rec_store(SeqRec* p, u32 x, u32 y, u32 z, u32 w) {
 #endif
 }
 ZB_HD u32 rec_ll(const SeqRec& r) { return r.w & 0x1FFFF; }
-ZB_HD u32 rec_ml(const SeqRec& r) { return (r.w >> 17) | (((r.y >> 18) & 3) << 15); }
+ZB_HD u32 rec_ml(const SeqRec& r) { return (r.w >> 17) | (((r.y >> 18) & 7) << 15); }
 ZB_HD u32 rec_lpos(const SeqRec& r) { return r.y & 0x3FFFF; }
 ZB_HD u32 sat_add32(u32 a, u32 b) { const u32 s = a + b; return s < a ? 0xFFFFFFFFu : s; }
 ZB_HD u32 sat_lpos(u32 lpos, u32 ll) { const u32 s = lpos + ll; return s > 0x3FFFFu ? 0x3FFFFu : s; }
