@@ -47,12 +47,17 @@ int zstdb200_is_error(uint32_t code);
 
 /* ZStdDecompress.Decompress(byte[] dst, uint dstCapacity, byte[] src, uint srcSize) —
  * csharp/src/ZStdDecompress.cs:2182-2186 (Java: ZstdDecompressor.decompress, ZstdDecompressor.java:22-28).
- * One item through the batched path (n = 1).  Returns the reference's result code. */
+ * One item through the batched path (n = 1): one descriptor copy, the kernels, the output copy, one synchronisation.
+ * A NULL dst or src is an empty array (capacity / size taken as 0).  Returns the reference's result code. */
 uint32_t zstdb200_decompress(zstdb200_ctx* ctx, void* dst, uint32_t dstCapacity, const void* src, uint32_t srcSize);
 
 /* Batched overload of the same call: item i decodes src[i][0..srcSize[i]) into dst[i][0..dstCap[i]) and stores
  * its result code in result[i].  Host pointers; the call returns after all outputs are in host memory.
- * Items are sharded over the context's devices by bytes; there is no cross-device traffic. */
+ * Items are sharded over the context's devices by bytes; there is no cross-device traffic.
+ * dstCap[i] may exceed max_batch_bytes (a large reusable scratch buffer): the device-side capacity is what the item
+ * can produce; only an item whose CONTENT exceeds the context's arenas fails the call.
+ * Bytes of dst[i] past result[i] are unspecified after the call when dst buffers lie back to back in pinned memory
+ * (they are DMA'd as one span); on an error result the output is unspecified (the reference leaves a partial decode). */
 int zstdb200_decompress_batch(zstdb200_ctx* ctx, const void* const* src, const uint32_t* srcSize,
                               void* const* dst, const uint32_t* dstCap, uint32_t* result, size_t n);
 
@@ -77,6 +82,11 @@ uint32_t zstdb200_compress(zstdb200_ctx* ctx, int level, int checksum, void* dst
 int zstdb200_compress_batch(zstdb200_ctx* ctx, int level, int checksum,
                             const void* const* src, const uint32_t* srcSize,
                             void* const* dst, const uint32_t* dstCap, uint32_t* result, size_t n);
+/* Device-pointer variant.  Requirements (the encoder's scratch arenas are addressed from src_off, nothing is
+ * validated on the device): src_off is non-decreasing with src_off[i] + src_size[i] <= src_off[i+1];
+ * src_off[n-1] + src_size[n-1] <= max_batch_bytes; the source is readable 8 bytes past its last item; dst ranges do
+ * not overlap; n <= zstdb200_max_items(ctx).  The call fetches src_size once (one small copy, one synchronisation of
+ * `stream`) to size the match finder's tables by the largest chunk, then only enqueues. */
 int zstdb200_compress_batch_device(zstdb200_ctx* ctx, int device_index, int level, int checksum,
                                    const void* src_base, const uint64_t* src_off, const uint32_t* src_size,
                                    void* dst_base, const uint64_t* dst_off, const uint32_t* dst_cap,

@@ -65,7 +65,7 @@ class HostSim:
         d = os.path.join(ROOT, "tests", "hostsim")
         path = os.path.join(d, "_build", "libhostsim.so")
         deps = [os.path.join(d, "hostsim.cpp")] + [os.path.join(ROOT, "zstandard_b200", "csrc", f)
-                                                  for f in ("zb_common.cuh", "zb_format.cuh", "zb_decode.cuh", "zb_encode.cuh")]
+                                                  for f in ("zb_common.cuh", "zb_format.cuh", "zb_decode.cuh", "zb_encode.cuh")] + [os.path.join(d, "serial_encoder.h")]
         if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(p) for p in deps):
             os.makedirs(os.path.dirname(path), exist_ok=True)
             subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-static-libstdc++", "-static-libgcc",

@@ -12,6 +12,7 @@
 #include <vector>
 #include "../../zstandard_b200/csrc/zb_decode.cuh"
 #include "../../zstandard_b200/csrc/zb_encode.cuh"
+#include "serial_encoder.h"
 
 using namespace zb;
 
@@ -323,13 +324,18 @@ struct WarpMatcher {
 };
 }  // namespace
 
-extern "C" uint32_t hostsim_compress_warp(uint8_t* dst, uint32_t cap, const uint8_t* src_in, uint32_t size, int level, int checksum) {
+// batch_max: the largest chunk of the call the frame is part of (the kernels choose their table sizes per call)
+extern "C" uint32_t hostsim_compress_warp2(uint8_t* dst, uint32_t cap, const uint8_t* src_in, uint32_t size, int level, int checksum, uint32_t batch_max) {
   std::vector<u8> padded(size + 64, 0);
   u8* src = padded.data() + 16;
   if (size) memcpy(src, src_in, size);
-  WarpMatcher m; m.src = src; m.size = size; m.dfast = level >= 3; m.hlogL = getenv("HS_HLOGL") ? atoi(getenv("HS_HLOGL")) : enc_hlog_long(level); m.hlogS = getenv("HS_HLOGS") ? atoi(getenv("HS_HLOGS")) : enc_hlog_short(level); m.mls = level <= 1 ? 6 : 5;
+  const bool big = batch_max > BLOCKSIZE_MAX;
+  WarpMatcher m; m.src = src; m.size = size; m.dfast = level >= 3; m.hlogL = getenv("HS_HLOGL") ? atoi(getenv("HS_HLOGL")) : enc_hlog_long(level, big); m.hlogS = getenv("HS_HLOGS") ? atoi(getenv("HS_HLOGS")) : enc_hlog_short(level, big); m.mls = level <= 1 ? 6 : 5;
   m.tab.assign((1u << m.hlogL) + (1u << m.hlogS), 0);
   const u32 seqCap = BLOCKSIZE_MAX / 4 + 64;
   std::vector<u8> codes(3 * seqCap), sym(4096); std::vector<u16> ct(3 * 514 + 16);
   return encode_frame_with(src, size, dst, cap, level, checksum, codes.data(), ct.data(), sym.data(), m);
+}
+extern "C" uint32_t hostsim_compress_warp(uint8_t* dst, uint32_t cap, const uint8_t* src_in, uint32_t size, int level, int checksum) {
+  return hostsim_compress_warp2(dst, cap, src_in, size, level, checksum, size);
 }

@@ -203,6 +203,7 @@ struct Job {
   // Capacity each item gets on the device: min(dstCap, what a well-formed item can produce) — a caller's large reusable
   // scratch buffer must not reserve that much of the arenas (run_host_batch).  == dstCap unless clamped.
   const uint32_t* effCap;
+  uint32_t maxSrc;     // largest srcSize of the call (compress: table sizes of the match stage)
 };
 
 // One sub-batch [lo, hi) on one device: slices over NSTREAMS streams, direct DMA where the layout allows.
@@ -302,7 +303,7 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
       e = decode_launch(ar, st, &nl);
     } else {
       EncodeArgs ar{d.d_src, d_srcOff + a, d_srcSize + a, d.d_dst, d_dstOff + a, d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
-                    j.level, j.checksum, (u32)(s % nStreams)};
+                    j.level, j.checksum, j.maxSrc, (u32)(s % nStreams)};
       e = encode_launch(ar, d.enc, st, &nl);
     }
     *launches += nl;
@@ -382,6 +383,7 @@ int run_host_batch(zstdb200_ctx* ctx, const Job& j0, size_t n, bool clamp = true
     eff[i] = (uint32_t)std::min<uint64_t>(c, lone);
   }
   Job j = j0; j.effCap = eff.data();
+  if (clamp) { j.maxSrc = 0; for (size_t i = 0; i < n; i++) j.maxSrc = std::max(j.maxSrc, j0.srcSize[i]); }
   bool tooBig = false;
   std::vector<Range> subs = make_subbatches(n, maxIn, maxOut, ctx->maxItems,
       [&](size_t i) { return (size_t)j.srcSize[i]; }, [&](size_t i) { return (size_t)j.effCap[i]; }, &tooBig);
@@ -430,7 +432,7 @@ int run_host_batch(zstdb200_ctx* ctx, const Job& j0, size_t n, bool clamp = true
     const size_t m = again.size();
     std::vector<const void*> s2(m); std::vector<void*> d2(m); std::vector<uint32_t> ss2(m), dc2(m), r2(m);
     for (size_t k = 0; k < m; k++) { const size_t i = again[k]; s2[k] = j.src[i]; d2[k] = j.dst[i]; ss2[k] = j.srcSize[i]; dc2[k] = j.dstCap[i]; }
-    Job jr{j.op, j.level, j.checksum, s2.data(), ss2.data(), d2.data(), dc2.data(), r2.data(), nullptr};
+    Job jr{j.op, j.level, j.checksum, s2.data(), ss2.data(), d2.data(), dc2.data(), r2.data(), nullptr, j.maxSrc};
     if (run_host_batch(ctx, jr, m, false)) return 1;
     for (size_t k = 0; k < m; k++) j.result[again[k]] = r2[k];
   }
@@ -504,7 +506,7 @@ int zstdb200_decompress_batch(zstdb200_ctx* ctx, const void* const* src, const u
                               void* const* dst, const uint32_t* dstCap, uint32_t* result, size_t n) {
   if (!ctx) return 1;
   ctx->err.clear();
-  Job j{Op::Decompress, 0, 0, src, srcSize, dst, dstCap, result, nullptr};
+  Job j{Op::Decompress, 0, 0, src, srcSize, dst, dstCap, result, nullptr, 0};
   return run_host_batch(ctx, j, n);
 }
 
@@ -571,12 +573,24 @@ const char* zstdb200_decode_kernel_name(int k) { return (k >= 0 && k < DECODE_KE
 
 size_t zstdb200_compress_bound(size_t srcSize) { return encode_bound(srcSize); }
 
+// The device-pointer compress entry points learn the largest chunk of the call (it selects the match stage's table
+// sizes) by fetching the size array once: one small copy and one synchronisation of the stream.
+static int device_max_u32(zstdb200_ctx* ctx, Device& d, const uint32_t* d_vals, size_t n, cudaStream_t st, u32* out) {
+  *out = 0;
+  if (n == 0) return 0;
+  u32* h = (u32*)d.h_desc;
+  CK(cudaMemcpyAsync(h, d_vals, n * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (size_t i = 0; i < n; i++) *out = std::max(*out, h[i]);
+  return 0;
+}
+
 int zstdb200_compress_batch(zstdb200_ctx* ctx, int level, int checksum, const void* const* src, const uint32_t* srcSize,
                             void* const* dst, const uint32_t* dstCap, uint32_t* result, size_t n) {
   if (!ctx) return 1;
   ctx->err.clear();
   if (level < 1 || level > 3) { ctx->err = "level must be 1..3"; return 1; }
-  Job j{Op::Compress, level, checksum, src, srcSize, dst, dstCap, result, nullptr};
+  Job j{Op::Compress, level, checksum, src, srcSize, dst, dstCap, result, nullptr, 0};
   return run_host_batch(ctx, j, n);
 }
 
@@ -600,7 +614,9 @@ int zstdb200_compress_batch_device(zstdb200_ctx* ctx, int device_index, int leve
   if (n > ctx->maxItems) { ctx->err = "n exceeds zstdb200_max_items"; return 1; }
   Device& d = ctx->dev[device_index];
   CK(cudaSetDevice(d.id));
-  EncodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, 0, level, checksum, ENC_EXCLUSIVE};
+  u32 maxSrc = 0;
+  if (device_max_u32(ctx, d, src_size, n, stream ? (cudaStream_t)stream : d.stream[0], &maxSrc)) return 1;
+  EncodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, 0, level, checksum, maxSrc, ENC_EXCLUSIVE};
   int nl = 0;
   CK(encode_launch(a, d.enc, stream ? (cudaStream_t)stream : d.stream[0], &nl));
   ctx->launches += nl;
@@ -621,7 +637,9 @@ int zstdb200_compress_batch_device_timed(zstdb200_ctx* ctx, int device_index, in
   cudaStream_t st = stream ? (cudaStream_t)stream : d.stream[0];
   cudaEvent_t ev[ENCODE_KERNELS + 1];
   for (auto& e : ev) CK(cudaEventCreate(&e));
-  EncodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, 0, level, checksum, ENC_EXCLUSIVE};
+  u32 maxSrc = 0;
+  if (device_max_u32(ctx, d, src_size, n, st, &maxSrc)) return 1;
+  EncodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, 0, level, checksum, maxSrc, ENC_EXCLUSIVE};
   int nl = 0;
   CK(encode_launch(a, d.enc, st, &nl, ev));
   ctx->launches += nl;

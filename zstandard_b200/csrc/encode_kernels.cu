@@ -640,7 +640,8 @@ cudaError_t encode_launch(const EncodeArgs& a, EncodeScratch& s, cudaStream_t st
   // level 1: 2^12 (8 KB, 24 warps/SM), level 2: 2^13 (16 KB, 12 warps/SM), level 3: 2^11 long + 2^12 short (12 KB, 16 warps/SM).
   // Measured with the lock-step emulation (tests/hostsim): tick records stay within -2.4 % of libzstd at 128 KiB
   // chunks, log text gains ratio with the smaller tables.
-  const u32 hlogL = envLog ? (u32)envLog : enc_hlog_long(a.level), hlogS = envLog ? (u32)envLog - 1 : enc_hlog_short(a.level), mls = a.level <= 1 ? 6 : 5;
+  const bool big = a.max_src_size > BLOCKSIZE_MAX;
+  const u32 hlogL = envLog ? (u32)envLog : enc_hlog_long(a.level, big), hlogS = envLog ? (u32)envLog - 1 : enc_hlog_short(a.level, big), mls = a.level <= 1 ? 6 : 5;
   const size_t smem = ((size_t)(1u << hlogL) + (dfast ? (1u << hlogS) : 0)) * 2;
   const u32 capSm = envPerSm ? (u32)envPerSm : 32;
   u32 perSm = (u32)((220 * 1024) / (smem + 1024)); if (perSm > capSm) perSm = capSm;

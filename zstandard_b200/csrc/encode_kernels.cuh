@@ -18,6 +18,7 @@ struct EncodeArgs {
   u32* result; u32 n;
   u32 item_base;     // index of item 0 within the scratch numbering (slices of one batch share the arenas)
   int level, checksum;
+  u32 max_src_size;  // largest src_size of the whole call (selects the match stage's table sizes, zb_encode.cuh enc_hlog_*)
   u32 stream_slot;   // partition (0..ENC_STREAM_PARTS-1) of the entropy stage's slot pool for launches that run concurrently
                      // on different streams, or ENC_EXCLUSIVE when the launch has the context to itself
 };

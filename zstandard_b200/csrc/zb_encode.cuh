@@ -15,65 +15,12 @@
 
 namespace zb {
 
-// ------------------------------------------------------------------------------------------------
-// parameters per level (libzstd's table for sources <= 128 KiB; hash logs shrink with the input)
-// ------------------------------------------------------------------------------------------------
-struct EncParams { u32 hashLog, chainLog /* short table of double-fast */, minMatch; bool dfast; };
-ZB_HD EncParams enc_params(int level, u32 srcSize) {
-  EncParams p;
-  if (level <= 1) { p.hashLog = 13; p.chainLog = 0; p.minMatch = 6; p.dfast = false; }
-  else if (level == 2) { p.hashLog = 15; p.chainLog = 0; p.minMatch = 5; p.dfast = false; }
-  else { p.hashLog = 16; p.chainLog = 15; p.minMatch = 5; p.dfast = true; }
-  u32 srcLog = srcSize < 64 ? 6 : highbit(srcSize - 1) + 1;
-  if (p.hashLog > srcLog + 1) p.hashLog = srcLog + 1;
-  if (p.chainLog > srcLog) p.chainLog = srcLog;
-  return p;
-}
-ZB_HD u32 enc_table_words(int level) { return level <= 1 ? (1u << 13) : (level == 2 ? (1u << 15) : (1u << 16) + (1u << 15)); }
 
-// per-frame scratch layout (all in HBM; addressed by the kernel from the item index)
-struct EncScratch {
-  u32* table;      // enc_table_words(level) position entries (0 = empty; positions are stored +1)
-  u8* lits;        // BLOCKSIZE_MAX bytes
-  u32* seqs;       // per sequence: litLength, matchLength-3 | offCode... packed as 2 words (see seq_push)
-  u32 seqCap;      // sequences
-  u8* codes;       // 3 * seqCap bytes: llCode, ofCode, mlCode per sequence
-  u16* ctables;    // FSE state tables scratch: 3 * 512 u16
-  u8* tmp;         // BLOCKSIZE_MAX + 1024 bytes: block assembled here before the raw/compressed decision
-};
-ZB_HD size_t enc_scratch_bytes_per_frame(int level) {
-  return (size_t)enc_table_words(level) * 4 + BLOCKSIZE_MAX + (size_t)(BLOCKSIZE_MAX / 4 + 64) * (8 + 3) + 3 * 512 * 2 + BLOCKSIZE_MAX + 2048;
-}
 
 ZB_HD u64 rd64u(const u8* p) { return ld64(p); }
 ZB_HD u32 rd32u(const u8* p) { return ld32(p); }
 
-// hashes of the first mls bytes at p (zstd's multiplicative hashes)
-ZB_HD u32 hash_bytes(const u8* p, u32 hlog, u32 mls) {
-  if (mls >= 8) return (u32)((rd64u(p) * 0xCF1BBCDCB7A56463ull) >> (64 - hlog));
-  if (mls == 7) return (u32)(((rd64u(p) << 8) * 0xCF1BBCDCBFA563ull) >> (64 - hlog));
-  if (mls == 6) return (u32)(((rd64u(p) << 16) * 0xCF1BBCDCBF9Bull) >> (64 - hlog));
-  if (mls == 5) return (u32)(((rd64u(p) << 24) * 0xCF1BBCDCBBull) >> (64 - hlog));
-  return (rd32u(p) * 2654435761u) >> (32 - hlog);
-}
 
-// number of equal bytes at a and b, both readable up to `end` on a's side
-ZB_HD u32 count_match(const u8* a, const u8* b, const u8* aend) {
-  const u8* s = a;
-  while (a + 8 <= aend) {
-    u64 d = rd64u(a) ^ rd64u(b);
-    if (d) {
-#if defined(__CUDA_ARCH__)
-      return (u32)(a - s) + ((u32)__ffsll((long long)d) - 1) / 8;
-#else
-      return (u32)(a - s) + (u32)__builtin_ctzll(d) / 8;
-#endif
-    }
-    a += 8; b += 8;
-  }
-  while (a < aend && *a == *b) { a++; b++; }
-  return (u32)(a - s);
-}
 
 // ------------------------------------------------------------------------------------------------
 // sequence store of one block
@@ -82,14 +29,6 @@ struct SeqStore {
   u32* seqs; u32 n, cap;       // word0 = litLength, word1 = (matchLength - 3) | offCodeLow... see push
   u8* lits; u32 nlits;
 };
-// offBase: 1..3 = repeat codes, >= 4 = offset + 3 (zstd's "offBase" convention)
-ZB_HD void seq_push(SeqStore& st, const u8* litSrc, u32 ll, u32 offBase, u32 ml) {
-  for (u32 i = 0; i < ll; i++) st.lits[st.nlits + i] = litSrc[i];
-  st.nlits += ll;
-  st.seqs[2 * st.n] = (ll & 0xFFFF) | (((ml - 3) & 0xFFFF) << 16);   // both lengths need 17 bits: bit 16 of each lives in word 1
-  st.seqs[2 * st.n + 1] = (offBase & 0x3FFFFFFFu) | ((((ml - 3) >> 16) & 1) << 30) | (((ll >> 16) & 1) << 31);
-  st.n++;
-}
 ZB_HD void seq_get(const SeqStore& st, u32 i, u32& ll, u32& offBase, u32& mlm3) {
   u32 a = st.seqs[2 * i], b = st.seqs[2 * i + 1];
   ll = (a & 0xFFFF) | ((b >> 31) << 16);
@@ -97,127 +36,7 @@ ZB_HD void seq_get(const SeqStore& st, u32 i, u32& ll, u32& offBase, u32& mlm3) 
   offBase = b & 0x3FFFFFFFu;
 }
 
-// ------------------------------------------------------------------------------------------------
-// match finders.  base = frame start, [istart, iend) = the block; window = everything since base.
-// rep[0..1] carried across blocks.  Positions in the tables are (index from base) + 1, 0 = empty.
-// ------------------------------------------------------------------------------------------------
-// "fast" strategy in its pipelined form: two positions are probed per round, the repeat offset is tried two
-// bytes ahead *before* the hash candidate of the current position, and the stride grows by one every 128 bytes
-// without a match (incompressible runs are skimmed).  The look-ahead position ip1 is only entered into the
-// table while the stride is small: with a large stride it can lie beyond the end of the match just found, and
-// an entry at or after the restart position would later be found as its own candidate (offset 0).
-ZB_HD void match_fast(SeqStore& st, u32* table, u32 hlog, u32 mls, const u8* base, const u8* istart, const u8* iend, u32 rep[2]) {
-  const u8* ip0 = istart; const u8* anchor = istart;
-  const u8* const ilimit = iend - 8;
-  u32 off1 = rep[0], off2 = rep[1], saved = 0;
-  const bool run = iend - istart >= 16;
-  if (run && ip0 == base) ip0++;
-  { u32 maxRep = (u32)(ip0 - base); if (off2 > maxRep) { saved = off2; off2 = 0; } if (off1 > maxRep) { saved = off1; off1 = 0; } }
-  while (run) {
-    u32 step = 2; const u8* nextStep = ip0 + 128;
-    const u8 *ip1 = ip0 + 1, *ip2 = ip0 + step, *ip3 = ip2 + 1;
-    if (ip3 >= ilimit) break;
-    u32 hash0 = hash_bytes(ip0, hlog, mls), hash1 = hash_bytes(ip1, hlog, mls);
-    u32 idx = table[hash0], cur0 = 0, found = 0, mlen = 0, offBase = 0;
-    const u8* match0 = nullptr;
-    do {
-      const u32 rval = off1 ? rd32u(ip2 - off1) : 0;
-      cur0 = (u32)(ip0 - base); table[hash0] = cur0 + 1;
-      if (off1 > 0 && rd32u(ip2) == rval) {                         // repeat offset two bytes ahead
-        ip0 = ip2; match0 = ip0 - off1; mlen = ip0[-1] == match0[-1]; ip0 -= mlen; match0 -= mlen; offBase = 1; mlen += 4;
-        table[hash1] = (u32)(ip1 - base) + 1; found = 1; break;
-      }
-      if (idx != 0 && rd32u(base + idx - 1) == rd32u(ip0)) { if (step <= 4) table[hash1] = (u32)(ip1 - base) + 1; found = 2; break; }
-      idx = table[hash1]; hash0 = hash1; hash1 = hash_bytes(ip2, hlog, mls);
-      ip0 = ip1; ip1 = ip2; ip2 = ip3;
-      cur0 = (u32)(ip0 - base); table[hash0] = cur0 + 1;
-      if (idx != 0 && rd32u(base + idx - 1) == rd32u(ip0)) { if (step <= 4) table[hash1] = (u32)(ip1 - base) + 1; found = 2; break; }
-      idx = table[hash1]; hash0 = hash1; hash1 = hash_bytes(ip2, hlog, mls);
-      ip0 = ip1; ip1 = ip2; ip2 = ip0 + step; ip3 = ip1 + step;
-      if (ip2 >= nextStep) { step++; nextStep += 128; }
-    } while (ip3 < ilimit);
-    if (!found) break;
-    if (found == 2) {
-      match0 = base + idx - 1; off2 = off1; off1 = (u32)(ip0 - match0); offBase = off1 + 3; mlen = 4;
-      while (ip0 > anchor && match0 > base && ip0[-1] == match0[-1]) { ip0--; match0--; mlen++; }   // catch up
-    }
-    mlen += count_match(ip0 + mlen, match0 + mlen, iend);
-    seq_push(st, anchor, (u32)(ip0 - anchor), offBase, mlen);
-    ip0 += mlen; anchor = ip0;
-    if (ip0 <= ilimit) {
-      table[hash_bytes(base + cur0 + 2, hlog, mls)] = cur0 + 2 + 1;
-      table[hash_bytes(ip0 - 2, hlog, mls)] = (u32)(ip0 - 2 - base) + 1;
-      while (off2 > 0 && ip0 <= ilimit && rd32u(ip0) == rd32u(ip0 - off2)) {   // immediate repeat of the older offset
-        const u32 rlen = count_match(ip0 + 4, ip0 + 4 - off2, iend) + 4;
-        { u32 t = off2; off2 = off1; off1 = t; }
-        table[hash_bytes(ip0, hlog, mls)] = (u32)(ip0 - base) + 1;
-        seq_push(st, anchor, 0, 1, rlen);
-        ip0 += rlen; anchor = ip0;
-      }
-    }
-  }
-  rep[0] = off1 ? off1 : saved; rep[1] = off2 ? off2 : saved;
-  { u32 ll = (u32)(iend - anchor); for (u32 i = 0; i < ll; i++) st.lits[st.nlits + i] = anchor[i]; st.nlits += ll; }
-}
 
-ZB_HD void match_dfast(SeqStore& st, u32* hashLong, u32 hlogL, u32* hashSmall, u32 hlogS, u32 mls, const u8* base, const u8* istart,
-                       const u8* iend, u32 rep[2]) {
-  const u8* ip = istart; const u8* anchor = istart;
-  const u8* const ilimit = iend - 8;
-  u32 off1 = rep[0], off2 = rep[1], saved = 0;
-  const bool run = iend - istart >= 16;
-  if (run && ip == base) ip++;
-  { u32 maxRep = (u32)(ip - base); if (off2 > maxRep) { saved = off2; off2 = 0; } if (off1 > maxRep) { saved = off1; off1 = 0; } }
-  while (run && ip < ilimit) {
-    u32 mlen;
-    const u32 h2 = hash_bytes(ip, hlogL, 8), h = hash_bytes(ip, hlogS, mls);
-    const u32 cur = (u32)(ip - base);
-    const u32 miL = hashLong[h2], miS = hashSmall[h];
-    hashLong[h2] = hashSmall[h] = cur + 1;
-    if (off1 > 0 && rd32u(ip + 1 - off1) == rd32u(ip + 1)) {
-      mlen = count_match(ip + 1 + 4, ip + 1 + 4 - off1, iend) + 4;
-      ip++;
-      seq_push(st, anchor, (u32)(ip - anchor), 1, mlen);
-    } else {
-      u32 offset; const u8* match;
-      const u8* mL = base + miL - 1; const u8* mS = base + miS - 1;
-      if (miL != 0 && rd64u(mL) == rd64u(ip)) {
-        mlen = count_match(ip + 8, mL + 8, iend) + 8; match = mL;
-        while (ip > anchor && match > base && ip[-1] == match[-1]) { ip--; match--; mlen++; }
-      } else if (miS != 0 && rd32u(mS) == rd32u(ip)) {
-        // a short match: try the long table one position later first
-        const u32 hl3 = hash_bytes(ip + 1, hlogL, 8);
-        const u32 mi3 = hashLong[hl3];
-        hashLong[hl3] = cur + 1 + 1;
-        const u8* m3 = base + mi3 - 1;
-        if (mi3 != 0 && rd64u(m3) == rd64u(ip + 1)) {
-          mlen = count_match(ip + 9, m3 + 8, iend) + 8; ip++; match = m3;
-          while (ip > anchor && match > base && ip[-1] == match[-1]) { ip--; match--; mlen++; }
-        } else {
-          mlen = count_match(ip + 4, mS + 4, iend) + 4; match = mS;
-          while (ip > anchor && match > base && ip[-1] == match[-1]) { ip--; match--; mlen++; }
-        }
-      } else { ip += ((ip - anchor) >> 8) + 1; continue; }
-      offset = (u32)(ip - match);
-      off2 = off1; off1 = offset;
-      seq_push(st, anchor, (u32)(ip - anchor), offset + 3, mlen);
-    }
-    ip += mlen; anchor = ip;
-    if (ip <= ilimit) {
-      hashLong[hash_bytes(base + cur + 2, hlogL, 8)] = hashSmall[hash_bytes(base + cur + 2, hlogS, mls)] = cur + 2 + 1;
-      hashLong[hash_bytes(ip - 2, hlogL, 8)] = hashSmall[hash_bytes(ip - 2, hlogS, mls)] = (u32)(ip - 2 - base) + 1;
-      while (ip <= ilimit && off2 > 0 && rd32u(ip) == rd32u(ip - off2)) {
-        const u32 rlen = count_match(ip + 4, ip + 4 - off2, iend) + 4;
-        { u32 t = off2; off2 = off1; off1 = t; }
-        hashSmall[hash_bytes(ip, hlogS, mls)] = hashLong[hash_bytes(ip, hlogL, 8)] = (u32)(ip - base) + 1;
-        seq_push(st, anchor, 0, 1, rlen);
-        ip += rlen; anchor = ip;
-      }
-    }
-  }
-  rep[0] = off1 ? off1 : saved; rep[1] = off2 ? off2 : saved;
-  { u32 ll = (u32)(iend - anchor); for (u32 i = 0; i < ll; i++) st.lits[st.nlits + i] = anchor[i]; st.nlits += ll; }
-}
 
 // ------------------------------------------------------------------------------------------------
 // forward bit writer (the decoder reads it backwards: BitStream.cs:322-497).  Bits are appended LSB first.
@@ -271,99 +90,76 @@ ZB_HD u32 fse_optimal_log(u32 maxLog, u32 total, u32 maxSym, u32 minus = 2) {
   return tl;
 }
 
-// proportional normalisation to a sum of 1 << tableLog; every present symbol gets >= 1 (-1 marks "less than
-// one" and costs a full tableLog-bit state, as in the format)
+// Normalised counts: integers n_s >= 1 for every present symbol with sum 1 << tableLog (what ReadNCount accepts:
+// EntropyCommon.cs:79-188 only requires the counts to add up; the "-1 = less than one" form is never needed, a rare
+// symbol simply gets one cell).
+// Rounding rule: the cost of coding symbol s with n cells is count_s * log2(tableSize / n), so between floor(x) = n and
+// n + 1 (x = the exact share) the better choice flips where x^2 = n (n + 1), the geometric mean — not at n + 1/2.  The
+// rounded counts rarely add up exactly; the difference goes to / comes from the symbols with the most cells, where one
+// cell more or less changes the code length least.  Returns false when one symbol holds every count (the caller
+// writes an RLE table instead).
 ZB_HD bool fse_normalize(s16* norm, u32 tableLog, const u32* count, u32 total, u32 maxSym) {
-  const u64 scale = 62 - tableLog, step = ((u64)1 << 62) / total, vStep = (u64)1 << (scale - 20);
-  const u32 lowThreshold = total >> tableLog;
-  i32 stillToDistribute = 1 << tableLog; u32 largest = 0; s16 largestP = 0;
-  static const u32 rtb[8] = {0, 473195, 504333, 520860, 550000, 700000, 750000, 830000};
+  const u32 tableSize = 1u << tableLog;
+  const u64 step = ((u64)1 << 40) / total;               // total <= 2^17: count * step < 2^57
+  const u32 shift = 40 - tableLog - 16;                  // share in Q16
+  i32 sum = 0;
   for (u32 s = 0; s <= maxSym; s++) {
-    if (count[s] == total) return false;   // rle: caller handles
+    if (count[s] == total) return false;
     if (count[s] == 0) { norm[s] = 0; continue; }
-    if (count[s] <= lowThreshold) { norm[s] = -1; stillToDistribute--; }
+    const u64 x = (count[s] * step) >> shift;            // Q16, < 2^(tableLog + 16)
+    u64 n = x >> 16;
+    if (x * x > ((n * (n + 1)) << 32)) n++;
+    if (n == 0) n = 1;
+    norm[s] = (s16)n; sum += (i32)n;
+  }
+  i32 diff = (i32)tableSize - sum;                       // > 0: cells left over, < 0: too many handed out
+  while (diff != 0) {
+    u32 best = 0; s16 bestN = 0;
+    for (u32 s = 0; s <= maxSym; s++) if (norm[s] > bestN) { bestN = norm[s]; best = s; }
+    if (diff > 0) { norm[best] = (s16)(norm[best] + diff); diff = 0; }
     else {
-      s16 proba = (s16)((count[s] * step) >> scale);
-      if (proba < 8) { u64 restToBeat = vStep * rtb[proba]; proba += (count[s] * step) - ((u64)proba << scale) > restToBeat; }
-      if (proba > largestP) { largestP = proba; largest = s; }
-      norm[s] = proba; stillToDistribute -= proba;
+      if (bestN <= 1) return false;                      // more present symbols than cells: cannot happen for tableLog >= log2(alphabet)
+      const i32 take = -diff < bestN / 2 ? -diff : (bestN / 2 > 0 ? bestN / 2 : 1);   // at most half of a symbol's cells at a time
+      norm[best] = (s16)(bestN - take); diff += take;
     }
   }
-  if (-stillToDistribute >= (norm[largest] >> 1)) {
-    // corner case: redistribute with the secondary method
-    const s16 NOT_YET = -2; u32 distributed = 0; u32 ToDistribute;
-    const u32 lowOne = (u32)((total * 3ull) >> (tableLog + 1));
-    u32 tot = total;
-    for (u32 s = 0; s <= maxSym; s++) {
-      if (count[s] == 0) { norm[s] = 0; continue; }
-      if (count[s] <= lowThreshold) { norm[s] = -1; distributed++; tot -= count[s]; continue; }
-      if (count[s] <= lowOne) { norm[s] = 1; distributed++; tot -= count[s]; continue; }
-      norm[s] = NOT_YET;
-    }
-    ToDistribute = (1u << tableLog) - distributed;
-    if (ToDistribute == 0) return true;
-    if ((tot / ToDistribute) > lowOne) {
-      const u32 lowOne2 = (u32)((tot * 3ull) / (ToDistribute * 2));
-      for (u32 s = 0; s <= maxSym; s++) if (norm[s] == NOT_YET && count[s] <= lowOne2) { norm[s] = 1; distributed++; tot -= count[s]; }
-      ToDistribute = (1u << tableLog) - distributed;
-    }
-    if (distributed == maxSym + 1) {
-      u32 maxV = 0, maxC = 0;
-      for (u32 s = 0; s <= maxSym; s++) if (count[s] > maxC) { maxV = s; maxC = count[s]; }
-      norm[maxV] += (s16)ToDistribute; return true;
-    }
-    if (tot == 0) { for (u32 s = 0; ToDistribute > 0; s = (s + 1) % (maxSym + 1)) if (norm[s] > 0) { ToDistribute--; norm[s]++; } return true; }
-    {
-      const u64 vStepLog = 62 - tableLog, mid = ((u64)1 << (vStepLog - 1)) - 1;
-      const u64 rStep = ((((u64)1 << vStepLog) * ToDistribute) + mid) / tot;
-      u64 tmpTotal = mid;
-      for (u32 s = 0; s <= maxSym; s++) if (norm[s] == NOT_YET) {
-        const u64 end = tmpTotal + (count[s] * rStep);
-        const u32 sStart = (u32)(tmpTotal >> vStepLog), sEnd = (u32)(end >> vStepLog), weight = sEnd - sStart;
-        if (weight < 1) return false;
-        norm[s] = (s16)weight; tmpTotal = end;
-      }
-    }
-  } else norm[largest] += (s16)stillToDistribute;
   return true;
 }
 
-// header writer, the inverse of ReadNCount; returns bytes written or 0 when out of room
+// Header writer: the inverse of ReadNCount (EntropyCommon.cs:79-188), written against the reader.  The reader keeps
+// `remaining` (cells not yet assigned, + 1) and `threshold` (the power of two above it): a count field stores n + 1 in
+// nbBits - 1 bits when that value is below max = 2 * threshold - 1 - remaining, else in nbBits bits (values at or above
+// threshold shifted up by max so that their low bits never look like a short field).  After a symbol with n = 0 the
+// reader expects the length of the zero run that follows: 16 one-bits per 24 zeros, then the 2-bit value 3 per 3
+// zeros, then the rest in 2 bits.  The table ends when every cell is assigned; the last byte is zero-padded.
+// Returns bytes written or 0 when out of room.
 ZB_HD u32 fse_write_ncount(u8* out, u32 cap, const s16* norm, u32 maxSym, u32 tableLog) {
-  u32 op = 0; const i32 tableSize = 1 << tableLog;
-  i32 remaining = tableSize + 1, threshold = tableSize, nbBits = (i32)tableLog + 1;
-  u32 bitStream = tableLog - 5; i32 bitCount = 4; u32 symbol = 0; const u32 alphabet = maxSym + 1; bool previousIs0 = false;
-  while (symbol < alphabet && remaining > 1) {
-    if (previousIs0) {
-      u32 start = symbol;
-      while (symbol < alphabet && !norm[symbol]) symbol++;
-      if (symbol == alphabet) break;
-      while (symbol >= start + 24) {
-        start += 24; bitStream += 0xFFFFu << bitCount;
-        if (op + 2 > cap) return 0;
-        out[op] = (u8)bitStream; out[op + 1] = (u8)(bitStream >> 8); op += 2; bitStream >>= 16;
-      }
-      while (symbol >= start + 3) { start += 3; bitStream += 3u << bitCount; bitCount += 2; }
-      bitStream += (symbol - start) << bitCount; bitCount += 2;
-      if (bitCount > 16) { if (op + 2 > cap) return 0; out[op] = (u8)bitStream; out[op + 1] = (u8)(bitStream >> 8); op += 2; bitStream >>= 16; bitCount -= 16; }
+  u64 acc = tableLog - 5; u32 nb = 4, op = 0;            // forward bit stream, least significant bit first
+  i32 remaining = (1 << tableLog) + 1, threshold = 1 << tableLog, nbBits = (i32)tableLog + 1;
+  u32 s = 0; bool afterZero = false;
+  while (s <= maxSym && remaining > 1) {
+    if (afterZero) {
+      u32 run = 0;
+      while (s + run <= maxSym && norm[s + run] == 0) run++;
+      if (s + run > maxSym) return 0;                    // cells unassigned but no symbol left: not a valid distribution
+      s += run;
+      while (run >= 24) { acc |= (u64)0xFFFF << nb; nb += 16; run -= 24; while (nb >= 8) { if (op >= cap) return 0; out[op++] = (u8)acc; acc >>= 8; nb -= 8; } }
+      while (run >= 3) { acc |= (u64)3 << nb; nb += 2; run -= 3; while (nb >= 8) { if (op >= cap) return 0; out[op++] = (u8)acc; acc >>= 8; nb -= 8; } }
+      acc |= (u64)run << nb; nb += 2;
     }
-    {
-      i32 count = norm[symbol++];
-      const i32 max = (2 * threshold - 1) - remaining;
-      remaining -= count < 0 ? -count : count;
-      count++;
-      if (count >= threshold) count += max;
-      bitStream += (u32)count << bitCount; bitCount += nbBits; bitCount -= (count < max);
-      previousIs0 = (count == 1);
-      if (remaining < 1) return 0;
-      while (remaining < threshold) { nbBits--; threshold >>= 1; }
-    }
-    if (bitCount > 16) { if (op + 2 > cap) return 0; out[op] = (u8)bitStream; out[op + 1] = (u8)(bitStream >> 8); op += 2; bitStream >>= 16; bitCount -= 16; }
+    const i32 n = norm[s++];
+    const i32 max = 2 * threshold - 1 - remaining;
+    const i32 c = n + 1;                                 // stored value (n = -1 would store 0)
+    if (c < max) { acc |= (u64)c << nb; nb += (u32)nbBits - 1; }
+    else { acc |= (u64)(c < threshold ? c : c + max) << nb; nb += (u32)nbBits; }
+    remaining -= n < 0 ? -n : n;
+    if (remaining < 1) return 0;
+    while (remaining < threshold) { nbBits--; threshold >>= 1; }
+    afterZero = n == 0;
+    while (nb >= 8) { if (op >= cap) return 0; out[op++] = (u8)acc; acc >>= 8; nb -= 8; }
   }
   if (remaining != 1) return 0;
-  if (op + 2 > cap) return 0;
-  out[op] = (u8)bitStream; out[op + 1] = (u8)(bitStream >> 8);
-  op += (u32)(bitCount + 7) / 8;
+  if (nb) { if (op >= cap) return 0; out[op++] = (u8)acc; }
   return op;
 }
 
@@ -423,8 +219,12 @@ struct HufEnc { HufCode code[256]; u8 weight[256]; u32 maxSym; u32 tableLog; };
 // way zstd's HUF_setMaxHeight does (pay back the Kraft debt on the longest cheap symbols).
 // Working arrays of huf_build (4 KB): callers choose where they live (the GPU kernel lends shared memory).
 // hash-table logs of the warp-parallel match finder (k_enc_match and its lock-step emulation in tests/hostsim)
-ZB_HD u32 enc_hlog_long(int level) { return level == 2 ? 13 : (level >= 3 ? 11 : 12); }
-ZB_HD u32 enc_hlog_short(int /*level*/) { return 12; }
+// Table sizes of the match stage (log2 of u16 entries).  big: the launch holds chunks above one block (128 KiB): there a
+// table of 2^12 entries forgets a position after ~4 KiB of input and the ratio falls out of the 3 % band against
+// libzstd (tick records, 256 KiB: -3.7 %, 1 MiB: -4.1 %); 2^13 entries keep it inside (-2.0 % / -2.2 %) at about half the
+// resident warps.
+ZB_HD u32 enc_hlog_long(int level, bool big) { return big ? 13 : (level == 2 ? 13 : (level >= 3 ? 11 : 12)); }
+ZB_HD u32 enc_hlog_short(int /*level*/, bool big) { return big ? 13 : 12; }
 
 struct HufBuildScratch { u32 nodeCount[512]; u16 parent[512]; u16 order[256]; u8 depth[512]; };
 
@@ -499,10 +299,6 @@ ZB_HD bool huf_build_sorted(HufEnc& he, const u32* count, u32 n, u32 maxBits, Hu
   }
   return true;
 }
-ZB_HD bool huf_build(HufEnc& he, const u32* count, u32 maxSym, u32 maxBits, HufBuildScratch& sc) {
-  const u32 n = huf_sort_symbols(sc.order, count, maxSym);
-  return huf_build_sorted(he, count, n, maxBits, sc);
-}
 
 // weight header: FSE-compressed weights when that is smaller, else 4-bit nibbles (needs maxSym <= 128 there)
 ZB_HD u32 huf_write_header(u8* out, u32 cap, const HufEnc& he, u16* stateScratch, u8* symScratch) {
@@ -560,64 +356,6 @@ ZB_HD u32 huf_encode_stream(u8* out, u32 cap, const u8* src, u32 n, const HufEnc
   return e ? (u32)(e - out) : 0;
 }
 
-// literals section (DecodeLiteralsBlock ZStdDecompress.cs:683-821).  Returns bytes written (0 = no room).
-ZB_HD u32 enc_literals(u8* out, u32 cap, const u8* lits, u32 n, u16* stateScratch, u8* symScratch) {
-  auto raw = [&]() -> u32 {
-    const u32 lh = n < 32 ? 1 : (n < 4096 ? 2 : 3);
-    if (lh + n > cap) return 0;
-    if (lh == 1) out[0] = (u8)(n << 3); else if (lh == 2) { u32 v = (1u << 2) | (n << 4); out[0] = (u8)v; out[1] = (u8)(v >> 8); }
-    else { u32 v = (3u << 2) | (n << 4); out[0] = (u8)v; out[1] = (u8)(v >> 8); out[2] = (u8)(v >> 16); }
-    for (u32 i = 0; i < n; i++) out[lh + i] = lits[i];
-    return lh + n;
-  };
-  if (n < 64) return raw();
-  u32 count[256]; for (u32 i = 0; i < 256; i++) count[i] = 0;
-  for (u32 i = 0; i < n; i++) count[lits[i]]++;
-  u32 maxSym = 255; while (maxSym > 0 && !count[maxSym]) maxSym--;
-  u32 largest = 0; for (u32 s = 0; s <= maxSym; s++) if (count[s] > largest) largest = count[s];
-  if (largest == n) {   // rle literals
-    const u32 lh = n < 32 ? 1 : (n < 4096 ? 2 : 3);
-    if (lh + 1 > cap) return 0;
-    if (lh == 1) out[0] = (u8)(1 | (n << 3)); else if (lh == 2) { u32 v = 1 | (1u << 2) | (n << 4); out[0] = (u8)v; out[1] = (u8)(v >> 8); }
-    else { u32 v = 1 | (3u << 2) | (n << 4); out[0] = (u8)v; out[1] = (u8)(v >> 8); out[2] = (u8)(v >> 16); }
-    out[lh] = lits[0];
-    return lh + 1;
-  }
-  if (largest <= (n >> 7) + 4) return raw();   // too flat to be worth it
-  HufEnc he; HufBuildScratch hsc;
-  u32 maxBits = fse_optimal_log(11, n, maxSym, 1); if (maxBits > 11) maxBits = 11;
-  if (!huf_build(he, count, maxSym, maxBits, hsc)) return raw();
-  const bool single = n < 256;
-  const u32 lhSize = 3 + (n >= 1024) + (n >= 16384);
-  if (lhSize + 8 > cap) return 0;
-  u8* body = out + lhSize; const u32 bodyCap = cap - lhSize;
-  u32 hdr = huf_write_header(body, bodyCap, he, stateScratch, symScratch);
-  if (!hdr) return raw();
-  u32 csize = hdr;
-  if (single) {
-    u32 s = huf_encode_stream(body + csize, bodyCap - csize, lits, n, he);
-    if (!s) return raw();
-    csize += s;
-  } else {
-    const u32 seg = (n + 3) / 4;
-    if (csize + 6 > bodyCap) return raw();
-    u8* jump = body + csize; csize += 6;
-    for (u32 k = 0; k < 4; k++) {
-      const u32 from = k * seg, len = k < 3 ? seg : n - 3 * seg;
-      u32 s = huf_encode_stream(body + csize, bodyCap - csize, lits + from, len, he);
-      if (!s || s > 65535) return raw();
-      if (k < 3) { jump[2 * k] = (u8)s; jump[2 * k + 1] = (u8)(s >> 8); }
-      csize += s;
-    }
-  }
-  const u32 minGain = (n >> 6) + 2;
-  if (csize + minGain >= n) return raw();
-  // header: type 2 (compressed), size format by lhSize
-  if (lhSize == 3) { u32 v = 2 | ((single ? 0u : 1u) << 2) | (n << 4) | (csize << 14); out[0] = (u8)v; out[1] = (u8)(v >> 8); out[2] = (u8)(v >> 16); }
-  else if (lhSize == 4) { u32 v = 2 | (2u << 2) | (n << 4) | (csize << 18); out[0] = (u8)v; out[1] = (u8)(v >> 8); out[2] = (u8)(v >> 16); out[3] = (u8)(v >> 24); }
-  else { u32 v = 2 | (3u << 2) | (n << 4) | (csize << 22); out[0] = (u8)v; out[1] = (u8)(v >> 8); out[2] = (u8)(v >> 16); out[3] = (u8)(v >> 24); out[4] = (u8)(csize >> 10); }
-  return lhSize + csize;
-}
 
 // ------------------------------------------------------------------------------------------------
 // sequences section (DecodeSeqHeaders :1110-1180, DecodeSequence :1473-1553)
@@ -669,12 +407,6 @@ ZB_HD u32 enc_seq_table_counts(FseCTable& ct, u16* stateTable, u8* symScratch, u
   fse_build_ctable(ct, stateTable, norm, maxSym, tl, symScratch);
   return 2;
 }
-ZB_HD u32 enc_seq_table(FseCTable& ct, u16* stateTable, u8* symScratch, const u8* codes, u32 nbSeq, const SeqKind& k, int level,
-                        u8* out, u32 cap, u32* used) {
-  u32 count[53]; for (u32 i = 0; i <= k.maxSym; i++) count[i] = 0;
-  for (u32 i = 0; i < nbSeq; i++) count[codes[i]]++;
-  return enc_seq_table_counts(ct, stateTable, symScratch, count, codes[nbSeq - 1], nbSeq, k, level, out, cap, used);
-}
 
 ZB_HD u32 enc_seq_count_header(u8* out, u32 nbSeq) {
   u32 op = 0;
@@ -684,44 +416,6 @@ ZB_HD u32 enc_seq_count_header(u8* out, u32 nbSeq) {
   return op;
 }
 
-// bitstream: sequences last to first; per sequence the decoder reads offset, matchLength, litLength extra
-// bits, then the LL, ML, OF state bits (:1504-1550) — so we write them in the opposite order.
-// Returns the end of the stream or nullptr when out of room.
-// The encoder's running state, so that callers can feed the sequences in pieces (the GPU kernel stages them
-// through shared memory a chunk at a time).
-struct SeqBits { BitWriter w; u32 sLL, sOF, sML; };
-ZB_HD void seqbits_first(SeqBits& b, u8* out, u8* end, const FseCTable& ctLL, const FseCTable& ctOF, const FseCTable& ctML,
-                         u32 ll, u32 ob, u32 mlm3, u32 lc, u32 oc, u32 mc) {   // the last sequence of the block
-  bw_init(b.w, out, end);
-  fse_init_state(ctML, b.sML, mc); fse_init_state(ctOF, b.sOF, oc); fse_init_state(ctLL, b.sLL, lc);
-  bw_add(b.w, ll - kLLbase[lc], kLLbits[lc]);
-  bw_add(b.w, mlm3 + 3 - kMLbase[mc], kMLbits[mc]); bw_flush(b.w);
-  bw_add(b.w, ob - (1u << oc), oc); bw_flush(b.w);
-}
-ZB_HD void seqbits_next(SeqBits& b, const FseCTable& ctLL, const FseCTable& ctOF, const FseCTable& ctML,
-                        u32 ll, u32 ob, u32 mlm3, u32 lc, u32 oc, u32 mc) {    // the others, last to first
-  fse_encode(b.w, ctOF, b.sOF, oc); fse_encode(b.w, ctML, b.sML, mc); bw_flush(b.w);
-  fse_encode(b.w, ctLL, b.sLL, lc);
-  bw_add(b.w, ll - kLLbase[lc], kLLbits[lc]); bw_flush(b.w);
-  bw_add(b.w, mlm3 + 3 - kMLbase[mc], kMLbits[mc]); bw_flush(b.w);
-  bw_add(b.w, ob - (1u << oc), oc); bw_flush(b.w);
-}
-ZB_HD u8* seqbits_finish(SeqBits& b, const FseCTable& ctLL, const FseCTable& ctOF, const FseCTable& ctML) {
-  fse_flush_state(b.w, ctML, b.sML); fse_flush_state(b.w, ctOF, b.sOF); fse_flush_state(b.w, ctLL, b.sLL);
-  return bw_close(b.w);
-}
-ZB_HD u8* enc_seq_bitstream(u8* out, u8* end, const SeqStore& st, const u8* llc, const u8* ofc, const u8* mlc,
-                            const FseCTable& ctLL, const FseCTable& ctOF, const FseCTable& ctML) {
-  const u32 nbSeq = st.n;
-  SeqBits b;
-  { const u32 i = nbSeq - 1; u32 ll, ob, mlm3; seq_get(st, i, ll, ob, mlm3);
-    seqbits_first(b, out, end, ctLL, ctOF, ctML, ll, ob, mlm3, llc[i], ofc[i], mlc[i]); }
-  for (i32 n = (i32)nbSeq - 2; n >= 0; n--) {
-    u32 ll, ob, mlm3; seq_get(st, (u32)n, ll, ob, mlm3);
-    seqbits_next(b, ctLL, ctOF, ctML, ll, ob, mlm3, llc[n], ofc[n], mlc[n]);
-  }
-  return seqbits_finish(b, ctLL, ctOF, ctML);
-}
 
 ZB_HD SeqKind seq_kind(int kind) {
   if (kind == KIND_LL) return SeqKind{MaxLL, LLFSELog, 6, kLLnorm};
@@ -729,120 +423,8 @@ ZB_HD SeqKind seq_kind(int kind) {
   return SeqKind{MaxML, MLFSELog, 6, kMLnorm};
 }
 
-// Returns bytes written, 0 on failure (caller falls back to a raw block).
-ZB_HD u32 enc_sequences(u8* out, u32 cap, const SeqStore& st, u8* codes, u16* ctables, u8* symScratch, int level) {
-  const u32 nbSeq = st.n;
-  if (cap < 4) return 0;
-  u32 op = enc_seq_count_header(out, nbSeq);
-  if (nbSeq == 0) return op;
-  u8 *llc = codes, *ofc = codes + st.cap, *mlc = codes + 2 * st.cap;
-  for (u32 i = 0; i < nbSeq; i++) {
-    u32 ll, ob, mlm3; seq_get(st, i, ll, ob, mlm3);
-    llc[i] = (u8)ll_code(ll); ofc[i] = (u8)highbit(ob); mlc[i] = (u8)ml_code(mlm3);
-  }
-  const SeqKind kLL = seq_kind(KIND_LL), kOF = seq_kind(KIND_OF), kML = seq_kind(KIND_ML);
-  u8* modeByte = out + op++; u32 used;
-  FseCTable ctLL, ctOF, ctML;
-  const u32 mLL = enc_seq_table(ctLL, ctables, symScratch, llc, nbSeq, kLL, level, out + op, cap - op, &used); if (mLL == 0xFF) return 0; op += used;
-  const u32 mOF = enc_seq_table(ctOF, ctables + 514, symScratch, ofc, nbSeq, kOF, level, out + op, cap - op, &used); if (mOF == 0xFF) return 0; op += used;
-  const u32 mML = enc_seq_table(ctML, ctables + 1028, symScratch, mlc, nbSeq, kML, level, out + op, cap - op, &used); if (mML == 0xFF) return 0; op += used;
-  *modeByte = (u8)((mLL << 6) | (mOF << 4) | (mML << 2));
-  u8* e = enc_seq_bitstream(out + op, out + cap, st, llc, ofc, mlc, ctLL, ctOF, ctML);
-  if (!e) return 0;
-  return (u32)(e - out);
-}
 
-// ------------------------------------------------------------------------------------------------
-// frame assembly (frame header ZStdDecompress.cs:421-499, block header :646-659)
-// ------------------------------------------------------------------------------------------------
-// Writes a complete frame for src[0..size) at dst (capacity cap).  Returns the frame size without the
-// 4-byte content checksum slot (the checksum kernel fills it), or an error code.
-//
-// `blockSeqs(st, blockIndex, bstart, bsize)` supplies the block's sequence store: either by running a match
-// finder right here (SerialMatcher: the thread-per-frame replay used by tests/hostsim) or by pointing at what
-// an emulation of the warp-parallel match kernel (WarpMatcher, tests/hostsim).  k_enc_entropy mirrors this function
-// warp-wide on what k_enc_match left in HBM (encode_kernels.cu).
-// Block bodies are written straight into dst and replaced by a raw copy when they do not pay.
-template <class BlockSeqs>
-ZB_HD u32 encode_frame_with(const u8* src, u32 size, u8* dst, u32 cap, int level, int checksum, u8* codes, u16* ctables, u8* symScratch,
-                            BlockSeqs& blockSeqs) {
-  u32 op = 0;
-  const u32 fcsCode = size < 256 ? 0 : (size < 65536 + 256 ? 1 : 2);
-  const u32 fhs = 4 + 1 + (fcsCode == 0 ? 1 : (fcsCode == 1 ? 2 : 4));
-  if (cap < fhs + 3 + (checksum ? 4 : 0)) return zerr(ZE_dstSize_tooSmall);
-  dst[0] = 0x28; dst[1] = 0xB5; dst[2] = 0x2F; dst[3] = 0xFD;
-  dst[4] = (u8)((fcsCode << 6) | (1u << 5) | (checksum ? 4 : 0));     // single segment, no dictionary
-  if (fcsCode == 0) dst[5] = (u8)size;
-  else if (fcsCode == 1) { const u32 v = size - 256; dst[5] = (u8)v; dst[6] = (u8)(v >> 8); }
-  else { dst[5] = (u8)size; dst[6] = (u8)(size >> 8); dst[7] = (u8)(size >> 16); dst[8] = (u8)(size >> 24); }
-  op = fhs;
-  const u32 tail = checksum ? 4 : 0;
-  u32 pos = 0, blk = 0;
-  do {
-    const u32 bsize = size - pos < BLOCKSIZE_MAX ? size - pos : BLOCKSIZE_MAX;
-    const u32 last = pos + bsize == size;
-    const u8* bstart = src + pos;
-    if (op + 3 + tail > cap) return zerr(ZE_dstSize_tooSmall);
-    bool rle = bsize > 0;
-    for (u32 i = 1; i < bsize && rle; i++) if (bstart[i] != bstart[0]) rle = false;
-    SeqStore st; st.n = 0; st.nlits = 0; st.seqs = nullptr; st.lits = nullptr; st.cap = 0;
-    const bool haveSeqs = blockSeqs(st, blk, bstart, bsize, rle && bsize >= 2);   // always called: keeps matcher state in step
-    if (rle && bsize >= 2) {
-      if (op + 4 + tail > cap) return zerr(ZE_dstSize_tooSmall);
-      const u32 h = last | (1u << 1) | (bsize << 3);
-      dst[op] = (u8)h; dst[op + 1] = (u8)(h >> 8); dst[op + 2] = (u8)(h >> 16); dst[op + 3] = bstart[0]; op += 4;
-    } else {
-      u32 csize = 0; bool compressed = false;
-      if (haveSeqs) {
-        u32 room = bsize - 1 < BLOCKSIZE_MAX - 1 ? bsize - 1 : BLOCKSIZE_MAX - 1;   // must beat raw and stay < 128 KiB (:1880)
-        const u32 avail = cap - op - 3 - tail;
-        if (room > avail) room = avail;
-        u8* body = dst + op + 3;
-        const u32 l = enc_literals(body, room, st.lits, st.nlits, ctables, symScratch);
-        if (l) {
-          const u32 s = enc_sequences(body + l, room - l, st, codes, ctables, symScratch, level);
-          if (s && l + s < bsize) { csize = l + s; compressed = true; }
-        }
-        blockSeqs.done(compressed);
-      }
-      if (compressed) {
-        const u32 h = last | (2u << 1) | (csize << 3);
-        dst[op] = (u8)h; dst[op + 1] = (u8)(h >> 8); dst[op + 2] = (u8)(h >> 16); op += 3 + csize;
-      } else {
-        if (op + 3 + bsize + tail > cap) return zerr(ZE_dstSize_tooSmall);
-        const u32 h = last | (0u << 1) | (bsize << 3);
-        dst[op] = (u8)h; dst[op + 1] = (u8)(h >> 8); dst[op + 2] = (u8)(h >> 16); op += 3;
-        for (u32 i = 0; i < bsize; i++) dst[op + i] = bstart[i];
-        op += bsize;
-      }
-    }
-    pos += bsize; blk++;
-  } while (pos < size);
-  return op;
-}
 
-// match finding inside the encoding thread (thread-per-frame replay)
-struct SerialMatcher {
-  const EncScratch& sc; EncParams pr; const u8* base; u32 rep[2], savedRep[2];
-  ZB_HD SerialMatcher(const EncScratch& s, int level, const u8* src, u32 size) : sc(s), pr(enc_params(level, size)), base(src) {
-    const u32 tw = (1u << pr.hashLog) + (pr.dfast ? (1u << pr.chainLog) : 0);
-    for (u32 i = 0; i < tw; i++) sc.table[i] = 0;
-    rep[0] = 1; rep[1] = 4; savedRep[0] = 1; savedRep[1] = 4;
-  }
-  ZB_HD bool operator()(SeqStore& st, u32, const u8* bstart, u32 bsize, bool isRle) {
-    if (isRle || bsize < 64) return false;
-    st.seqs = sc.seqs; st.n = 0; st.cap = sc.seqCap; st.lits = sc.lits; st.nlits = 0;
-    savedRep[0] = rep[0]; savedRep[1] = rep[1];
-    if (pr.dfast) match_dfast(st, sc.table, pr.hashLog, sc.table + (1u << pr.hashLog), pr.chainLog, pr.minMatch, base, bstart, bstart + bsize, rep);
-    else match_fast(st, sc.table, pr.hashLog, pr.minMatch, base, bstart, bstart + bsize, rep);
-    return true;
-  }
-  ZB_HD void done(bool compressed) { if (!compressed) { rep[0] = savedRep[0]; rep[1] = savedRep[1]; } }   // a raw block leaves the decoder's history alone
-};
 
-ZB_HD u32 encode_frame(const u8* src, u32 size, u8* dst, u32 cap, int level, int checksum, const EncScratch& sc) {
-  SerialMatcher m(sc, level, src, size);
-  return encode_frame_with(src, size, dst, cap, level, checksum, sc.codes, sc.ctables, sc.tmp, m);
-}
 
 }  // namespace zb
