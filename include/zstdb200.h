@@ -51,6 +51,15 @@ int zstdb200_is_error(uint32_t code);
  * A NULL dst or src is an empty array (capacity / size taken as 0).  Returns the reference's result code. */
 uint32_t zstdb200_decompress(zstdb200_ctx* ctx, void* dst, uint32_t dstCapacity, const void* src, uint32_t srcSize);
 
+/* ZSTD_decompress_usingDict — csharp/src/ZStdDecompress.cs:2162-2167, dictionary loading :2366-2475 (present in the
+ * reference but unreachable from its public API, which passes no dictionary, :2171).  The dictionary
+ * becomes part of the context: every later zstdb200_decompress* call starts each data frame from it (content as the
+ * window's prefix; for a dictionary with magic 0xEC30A437 also its Huffman table, sequence tables and repeat offsets).
+ * A malformed entropy section makes every data frame fail with dictionary_corrupted; a frame that names another
+ * dictionary id fails with dictionary_wrong — the reference's codes.  dict == NULL or dictSize == 0 removes it.
+ * The bytes are copied; returns 0, or non-zero on a CUDA / allocation failure (zstdb200_last_error). */
+int zstdb200_load_dictionary(zstdb200_ctx* ctx, const void* dict, uint32_t dictSize);
+
 /* Batched overload of the same call: item i decodes src[i][0..srcSize[i]) into dst[i][0..dstCap[i]) and stores
  * its result code in result[i].  Host pointers; the call returns after all outputs are in host memory.
  * Items are sharded over the context's devices by bytes; there is no cross-device traffic.

@@ -458,10 +458,14 @@ struct DCtx {
   u64 fcs, windowSize; u32 checksumFlag, dictID, headerSize; bool skippable;
   Xxh64 xxh;
   bool overread; Trace* trace;
+  // dictionary (ZSTD_decompress_usingDict :2162-2167; null for the public API, :2171)
+  const u8* dict; u32 dictSize;
+  const u8* dictContent; u32 dictContentSize; u32 ctxDictID;           // set by insertDictionary: the window's virtual prefix
   void begin() {                                                       // :2478-2499
     huf.maxTableLog = 12; huf.tableType = 0; huf.tableLog = 12;        // hufTable[0] = HufLog*0x1000001
     litEntropy = fseEntropy = 0; rep[0] = 1; rep[1] = 4; rep[2] = 8;
     LL = &LLspace; ML = &MLspace; OF = &OFspace;
+    dictContent = nullptr; dictContentSize = 0; ctxDictID = 0;
   }
 };
 
@@ -661,14 +665,27 @@ Seq decodeSequence(SeqState& s, bool longOffsets) {                    // :1473-
 
 // :1265-1352 (+ Last7 :1212-1260). dst offsets are relative to the frame's first byte
 // (baseField == vBase == frame start, dictEnd == null: :1912-1921 after :2478-2499).
-u32 execSequence(u8* frameBase, u64 op, u64 oend, const Seq& q, const u8*& lit, const u8* litLimit) {
+// With a dictionary its content is the window's prefix (RefDictContent :2366-2373, CheckContinuity :1912-1921): an offset
+// that reaches beyond the frame's first byte continues at the end of the dictionary content (:1290-1315).
+u32 execSequence(u8* frameBase, u64 op, u64 oend, const Seq& q, const u8*& lit, const u8* litLimit, const u8* dictContent = nullptr, u32 dictContentSize = 0) {
   u64 oLitEnd = op + q.ll, seqLen = (u64)q.ll + q.ml, oMatchEnd = op + seqLen;
   if (oMatchEnd > oend) return ERR(E_dstSize_tooSmall);
   if (lit + q.ll > litLimit) return ERR(E_corruption_detected);
   memcpy(frameBase + op, lit, q.ll); lit += q.ll;
-  if (q.off > oLitEnd) return ERR(E_corruption_detected);
-  u8* o = frameBase + oLitEnd; const u8* m = o - q.off;
-  for (u32 i = 0; i < q.ml; i++) o[i] = m[i];
+  u8* o = frameBase + oLitEnd; u32 ml = q.ml;
+  if (q.off > oLitEnd) {
+    if (q.off > oLitEnd + dictContentSize) return ERR(E_corruption_detected);
+    const u64 back = q.off - oLitEnd;                                   // bytes of the source that lie in the dictionary
+    const u8* m = dictContent + dictContentSize - back;
+    const u32 l1 = back < ml ? (u32)back : ml;
+    memmove(o, m, l1);
+    o += l1; ml -= l1;
+    const u8* m2 = frameBase;                                           // the rest continues at the frame's first byte
+    for (u32 i = 0; i < ml; i++) o[i] = m2[i];
+    return (u32)seqLen;
+  }
+  const u8* m = o - q.off;
+  for (u32 i = 0; i < ml; i++) o[i] = m[i];
   return (u32)seqLen;
 }
 
@@ -684,7 +701,7 @@ u32 decompressSequences(DCtx& d, u8* frameBase, u64 opStart, u64 oend, const u8*
       nbSeq--;
       Seq q = decodeSequence(s, longOff);
       if (d.trace) { d.trace->seqs.push_back(q.ll); d.trace->seqs.push_back(q.ml); d.trace->seqs.push_back(q.off); }
-      u32 one = execSequence(frameBase, op, oend, q, lit, litEnd);
+      u32 one = execSequence(frameBase, op, oend, q, lit, litEnd, d.dictContent, d.dictContentSize);
       if (is_err(one)) return one;
       op += one;
     }
@@ -725,7 +742,7 @@ u32 decompressFrame(DCtx& d, u8* dst, u32 dstCap, const u8** srcp, u32* sizep) {
     u32 r = getFrameHeader(d, ip, fhs);                               // DecodeFrameHeader :628-637
     if (is_err(r)) return r;
     if (r > 0) return ERR(E_srcSize_wrong);
-    if (d.dictID != 0) return ERR(E_dictionary_wrong);               // dctx.dictID == 0 (no dictionary reachable, :2171)
+    if (d.dictID != 0 && d.ctxDictID != d.dictID) return ERR(E_dictionary_wrong);   // :633 (ctxDictID == 0 without a dictionary, :2171)
     if (d.checksumFlag) d.xxh.reset(0);
     ip += fhs; remaining -= fhs;
   }
@@ -763,6 +780,45 @@ u32 decompressFrame(DCtx& d, u8* dst, u32 dstCap, const u8** srcp, u32* sizep) {
   return (u32)op;
 }
 
+// LoadEntropy :2375-2447.  Returns the size of the entropy section or an error.
+// (The reference reads the Huffman table with the double-symbol reader HUF_readDTableX4_wksp; its accept set and
+// header size are those of ReadStats, which the single-symbol reader restated here shares.)
+const u32 MAGIC_DICT = 0xEC30A437u;
+u32 loadEntropy(DCtx& d, const u8* dict, u32 dictSize) {
+  const u8* p = dict; const u8* end = dict + dictSize;
+  if (dictSize <= 8) return ERR(E_dictionary_corrupted);
+  p += 8;
+  { u32 h = hufReadDTableX2(d.huf, p, (u32)(end - p), d.wk); if (is_err(h)) return ERR(E_dictionary_corrupted); p += h; }
+  { s16 norm[MaxOff + 1]; u32 maxV = MaxOff, lg; u32 h = readNCount(norm, &maxV, &lg, p, (u32)(end - p));
+    if (is_err(h)) return ERR(E_dictionary_corrupted);
+    if (maxV > MaxOff || lg > OffFSELog) return ERR(E_dictionary_corrupted);
+    buildFseSeqTable(d.OFspace, norm, maxV, OF_base, OF_bits, lg); p += h; }
+  { s16 norm[MaxML + 1]; u32 maxV = MaxML, lg; u32 h = readNCount(norm, &maxV, &lg, p, (u32)(end - p));
+    if (is_err(h)) return ERR(E_dictionary_corrupted);
+    if (maxV > MaxML || lg > MLFSELog) return ERR(E_dictionary_corrupted);
+    buildFseSeqTable(d.MLspace, norm, maxV, ML_base, ML_bits, lg); p += h; }
+  { s16 norm[MaxLL + 1]; u32 maxV = MaxLL, lg; u32 h = readNCount(norm, &maxV, &lg, p, (u32)(end - p));
+    if (is_err(h)) return ERR(E_dictionary_corrupted);
+    if (maxV > MaxLL || lg > LLFSELog) return ERR(E_dictionary_corrupted);
+    buildFseSeqTable(d.LLspace, norm, maxV, LL_base, LL_bits, lg); p += h; }
+  if (p + 12 > end) return ERR(E_dictionary_corrupted);
+  { u32 contentSize = (u32)(end - (p + 12));
+    for (int i = 0; i < 3; i++) { u32 r = rd32(p); p += 4; if (r == 0 || r >= contentSize) return ERR(E_dictionary_corrupted); d.rep[i] = r; } }
+  return (u32)(p - dict);
+}
+// ZSTD_decompress_insertDictionary :2449-2475 (+ RefDictContent :2366-2373)
+u32 insertDictionary(DCtx& d, const u8* dict, u32 dictSize) {
+  if (dictSize >= 8 && rd32(dict) == MAGIC_DICT) {
+    d.ctxDictID = rd32(dict + 4);
+    u32 e = loadEntropy(d, dict, dictSize);
+    if (is_err(e)) return ERR(E_dictionary_corrupted);
+    dict += e; dictSize -= e;
+    d.litEntropy = d.fseEntropy = 1;
+  }                                                                     // else: pure content mode
+  d.dictContent = dict; d.dictContentSize = dictSize;
+  return 0;
+}
+
 // :2096-2160
 u32 decompressMultiFrame(DCtx& d, u8* dst, u32 dstCap, const u8* src, u32 srcSize) {
   u8* dstStart = dst;
@@ -777,7 +833,8 @@ u32 decompressMultiFrame(DCtx& d, u8* dst, u32 dstCap, const u8* src, u32 srcSiz
       }
       return ERR(E_prefix_unknown);
     }
-    d.begin();
+    d.begin();                                                        // ZSTD_decompressBegin_usingDict :2501-2507: every frame starts from the dictionary
+    if (d.dict && d.dictSize) { u32 e = insertDictionary(d, d.dict, d.dictSize); if (is_err(e)) return ERR(E_dictionary_corrupted); }
     u32 res = decompressFrame(d, dst, dstCap, &src, &srcSize);
     if (is_err(res)) return res;
     dst += res; dstCap -= res;
@@ -786,8 +843,9 @@ u32 decompressMultiFrame(DCtx& d, u8* dst, u32 dstCap, const u8* src, u32 srcSiz
   return (u32)(dst - dstStart);
 }
 
-u32 decompress_impl(u8* dst, u32 dstCap, const u8* src, u32 srcSize, Trace* tr, int* overread) {
+u32 decompress_impl(u8* dst, u32 dstCap, const u8* src, u32 srcSize, Trace* tr, int* overread, const u8* dict = nullptr, u32 dictSize = 0) {
   DCtx* d = new DCtx(); d->trace = tr; d->overread = false;         // fresh context per call, as :2174-2180
+  d->dict = dict; d->dictSize = dictSize;
   static u8 dummy;
   u32 r = decompressMultiFrame(*d, dst ? dst : &dummy, dstCap, src, srcSize);
   if (overread) *overread = d->overread;
@@ -803,6 +861,10 @@ extern "C" {
 // ZStdDecompress.Decompress(byte[] dst, uint dstCapacity, byte[] src, uint srcSize): ZStdDecompress.cs:2182-2186
 uint32_t oracle_decompress(void* dst, uint32_t dstCap, const void* src, uint32_t srcSize) {
   return decompress_impl((u8*)dst, dstCap, (const u8*)src, srcSize, nullptr, nullptr);
+}
+// ZSTD_decompress_usingDict (ZStdDecompress.cs:2162-2167; internal in the reference: its public API passes no dictionary)
+uint32_t oracle_decompress_using_dict(void* dst, uint32_t dstCap, const void* src, uint32_t srcSize, const void* dict, uint32_t dictSize) {
+  return decompress_impl((u8*)dst, dstCap, (const u8*)src, srcSize, nullptr, nullptr, (const u8*)dict, dictSize);
 }
 // same, also reports whether an accepted sequence bitstream was read past its start (diagnostic)
 uint32_t oracle_decompress_diag(void* dst, uint32_t dstCap, const void* src, uint32_t srcSize, int* overread) {

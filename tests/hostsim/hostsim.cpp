@@ -36,10 +36,18 @@ struct Sim {
 };
 
 // mirrors k_huf for one frame; returns first failing block / code through fi
+// the replay's dictionary (hostsim_set_dict): what zstdb200_load_dictionary prepares on the device
+static DictState g_dict; static std::vector<u8> g_dictBytes; static bool g_haveDict = false;
+static const DictState* cur_dict() { return g_haveDict ? &g_dict : nullptr; }
+
 void sim_huf(const u8* src, u32 size, FrameInfo& fi, u8* lit, u64 litCap) {
   alignas(16) static thread_local u16 dt[1 << HUF_TABLE_LOG]; static thread_local HufBuildWk wk; alignas(16) u32 ringBuf[ZB_RING_WORDS];
   static thread_local u8 sideMem[256], slotMem[256]; const u8* side = nullptr;
   u32 pos = fi.body_off, blk = 0; u64 litRun = 0; u32 tableLog = 0; bool haveTable = false;
+  if (const DictState* ds = cur_dict()) if (ds->hasEntropy) {
+    memcpy(dt, ds->huf, sizeof(ds->huf)); tableLog = ds->hufLog; haveTable = true;
+    if (tableLog > HUF_TABLE_LOG) { memcpy(sideMem, ds->hufSide, 256); side = sideMem; }
+  }
   while (true) {
     BlockHdr bh;
     if (read_block_hdr(src + pos, size - pos, bh)) break;
@@ -87,6 +95,10 @@ void sim_huf(const u8* src, u32 size, FrameInfo& fi, u8* lit, u64 litCap) {
 // serial stand-in for k_exec: same checks in the same order, byte-serial copies; no checksum verification
 u32 sim_exec(const u8* src, u32 size, const FrameInfo& fi, u8* dst, u64 cap, const u8* litScratch, const SeqRec* recs, bool* needXxh, u32* trailerOff, u32* nextOff, u32* decoded) {
   u32 pos = fi.body_off, blk = 0; u64 op = 0, litRun = 0, recRun = 0; bool litEntropy = false, dry = false; u32 err = 0;
+  const DictState* ds = cur_dict();
+  const u32 dictContent = ds ? ds->contentSize : 0;
+  const u8* const dictEnd = ds ? g_dictBytes.data() + ds->contentOff + dictContent : nullptr;
+  if (ds && ds->hasEntropy) litEntropy = true;
   while (true) {
     BlockHdr bh;
     err = read_block_hdr(src + pos, size - pos, bh);
@@ -124,11 +136,11 @@ u32 sim_exec(const u8* src, u32 size, const FrameInfo& fi, u8* dst, u64 cap, con
           if (start != op && start <= cap) { fprintf(stderr, "hostsim: record position %llu != %llu\n", (unsigned long long)start, (unsigned long long)op); abort(); }
           if (start + ll + ml > cap) { err = ZE_dstSize_tooSmall; break; }
           if ((u64)rec_lpos(*r) + ll > litSize) { err = ZE_corruption_detected; break; }
-          if ((u64)off > start + ll) { err = ZE_corruption_detected; break; }
+          if ((u64)off > start + ll + dictContent) { err = ZE_corruption_detected; break; }
           if (rec_lpos(*r) != litPos) { fprintf(stderr, "hostsim: literal position mismatch\n"); abort(); }
           if (!dry) for (u32 i = 0; i < ll; i++) dst[op + i] = isRle ? (u8)rleByte : lit[litPos + i];
           op += ll; litPos += ll;
-          if (!dry) for (u32 i = 0; i < ml; i++) dst[op + i] = dst[op + i - off];
+          if (!dry) for (u32 i = 0; i < ml; i++) dst[op + i] = (u64)off > op + i ? dictEnd[(i64)(op + i) - (i64)off] : dst[op + i - off];
           op += ml;
         }
         if (err) break;
@@ -179,7 +191,7 @@ extern "C" uint32_t hostsim_decompress2(uint8_t* dst_in, uint32_t capAll, const 
   u32 start = 0, outBase = 0, out = 0;
   while (true) {
     FrameInfo fi; u32 r = 0;
-    if (!parse_item(src, size, fi, &r, start, outBase)) return r;
+    if (!parse_item(src, size, fi, &r, start, outBase, cur_dict() ? cur_dict()->err : 0, cur_dict() ? cur_dict()->dictID : 0)) return r;
     const u32 cap = capAll - fi.out_base; u8* dst = dst_in ? dst_in + fi.out_base : dummy;
     std::vector<u8> lit((size_t)cap + 64);
     std::vector<SeqRec> recs(seq_capacity(cap) + 40);
@@ -188,9 +200,11 @@ extern "C" uint32_t hostsim_decompress2(uint8_t* dst_in, uint32_t capAll, const 
     SeqTableSet T;
     T.space[KIND_LL] = sim->ll.data(); T.space[KIND_ML] = sim->ml.data(); T.space[KIND_OF] = sim->of.data(); T.stride = 1;
     T.defs[KIND_LL] = sim->defLL; T.defs[KIND_OF] = sim->defOF; T.defs[KIND_ML] = sim->defML;
-    SeqFrameOut res;
     s16 normBuf[53]; u16 nextBuf[53]; alignas(16) u32 ringBuf[ZB_RING_WORDS];
-    seq_decode_frame(src, size, fi.body_off, fi.window, T, recs.data(), seq_capacity(cap), res, sim->llInfo, sim->mlInfo, normBuf, nextBuf, ringBuf);
+    SeqEmitter em; em.init(recs.data(), seq_capacity(cap), sim->llInfo, sim->mlInfo);      // the finishing half, plugged in directly
+    if (cur_dict()) em.set_reps(cur_dict()->rep);
+    seq_decode_frame(src, size, fi.body_off, fi.window, T, em, sim->llInfo, sim->mlInfo, normBuf, nextBuf, ringBuf, cur_dict());
+    const SeqFrameOut res = em.res;
     if (res.err_block != 0xFFFFFFFFu) { fi.seq_err_block = res.err_block; fi.seq_err_code = res.err_code; fi.seq_err_index = res.err_index; }
     bool nx; u32 tr, nextOff = 0, produced = 0;
     out = sim_exec(src, size, fi, dst, cap, lit.data(), recs.data(), &nx, &tr, &nextOff, &produced);
@@ -212,7 +226,7 @@ extern "C" uint32_t hostsim_stages(const uint8_t* src_in, uint32_t size, uint32_
   u8* src = padded.data() + 16;
   memcpy(src, src_in, size);
   FrameInfo fi; u32 r = 0;
-  if (!parse_item(src, size, fi, &r)) return r;
+  if (!parse_item(src, size, fi, &r, 0, 0, cur_dict() ? cur_dict()->err : 0, cur_dict() ? cur_dict()->dictID : 0)) return r;
   std::vector<u8> lit((size_t)cap + 64);
   std::vector<SeqRec> recs(seq_capacity(cap) + 40);
   sim_huf(src, size, fi, lit.data(), (u64)cap + 40);
@@ -220,9 +234,11 @@ extern "C" uint32_t hostsim_stages(const uint8_t* src_in, uint32_t size, uint32_
   SeqTableSet T;
   T.space[KIND_LL] = sim->ll.data(); T.space[KIND_ML] = sim->ml.data(); T.space[KIND_OF] = sim->of.data(); T.stride = 1;
   T.defs[KIND_LL] = sim->defLL; T.defs[KIND_OF] = sim->defOF; T.defs[KIND_ML] = sim->defML;
-  SeqFrameOut res;
   s16 normBuf[53]; u16 nextBuf[53]; alignas(16) u32 ringBuf[ZB_RING_WORDS];
-  seq_decode_frame(src, size, fi.body_off, fi.window, T, recs.data(), seq_capacity(cap), res, sim->llInfo, sim->mlInfo, normBuf, nextBuf, ringBuf);
+  SeqEmitter em; em.init(recs.data(), seq_capacity(cap), sim->llInfo, sim->mlInfo);
+  if (cur_dict()) em.set_reps(cur_dict()->rep);
+  seq_decode_frame(src, size, fi.body_off, fi.window, T, em, sim->llInfo, sim->mlInfo, normBuf, nextBuf, ringBuf, cur_dict());
+  const SeqFrameOut res = em.res;
   memcpy(lit_out, lit.data(), cap);
   u32 n = (u32)std::min<size_t>(max_recs, recs.size());
   memcpy(rec_out, recs.data(), (size_t)n * sizeof(SeqRec));
@@ -338,4 +354,14 @@ extern "C" uint32_t hostsim_compress_warp2(uint8_t* dst, uint32_t cap, const uin
 }
 extern "C" uint32_t hostsim_compress_warp(uint8_t* dst, uint32_t cap, const uint8_t* src_in, uint32_t size, int level, int checksum) {
   return hostsim_compress_warp2(dst, cap, src_in, size, level, checksum, size);
+}
+
+// ---- dictionary of the replay (the device's zstdb200_load_dictionary): size 0 removes it ----
+extern "C" void hostsim_set_dict(const uint8_t* dict, uint32_t size) {
+  g_haveDict = false;
+  if (!dict || size == 0) return;
+  g_dictBytes.assign(dict, dict + size); g_dictBytes.resize(size + 64, 0);
+  static HufBuildWk wk; static HufFseScratch fs; static u8 slot[260]; static s16 norm[64]; static u16 next[64];
+  dict_load(g_dictBytes.data(), size, g_dict, wk, fs, slot, norm, next);
+  g_haveDict = true;
 }

@@ -98,3 +98,60 @@ def compress_chunks(raw, chunk, level=3, checksum=True, threads=8):
     for i in range(n):
         blob[int(offsets[i]):int(offsets[i + 1])] = tmp[i * bound:i * bound + int(sizes[i])]
     return blob, offsets
+
+
+# ---- dictionaries (libzstd + ZDICT): producers of dictionary frames for the 8f-3 tests ----
+_Z.ZDICT_trainFromBuffer.restype = ctypes.c_size_t
+_Z.ZDICT_trainFromBuffer.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint]
+_Z.ZDICT_isError.restype = ctypes.c_uint
+_Z.ZDICT_isError.argtypes = [ctypes.c_size_t]
+_Z.ZSTD_CCtx_loadDictionary.restype = ctypes.c_size_t
+_Z.ZSTD_CCtx_loadDictionary.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+_Z.ZSTD_createDCtx.restype = ctypes.c_void_p
+_Z.ZSTD_freeDCtx.argtypes = [ctypes.c_void_p]
+_Z.ZSTD_decompress_usingDict.restype = ctypes.c_size_t
+_Z.ZSTD_decompress_usingDict.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]
+ZSTD_c_dictIDFlag = 202
+
+
+def train_dict(samples, capacity=16384):
+    """ZDICT_trainFromBuffer over a list of byte strings -> a dictionary with entropy tables (magic 0xEC30A437)."""
+    blob = b"".join(samples)
+    sizes = (ctypes.c_size_t * len(samples))(*[len(s) for s in samples])
+    buf = ctypes.create_string_buffer(capacity)
+    n = _Z.ZDICT_trainFromBuffer(buf, capacity, blob, sizes, len(samples))
+    if _Z.ZDICT_isError(n):
+        raise RuntimeError("ZDICT_trainFromBuffer failed")
+    return buf.raw[:n]
+
+
+def compress_with_dict(data, dictionary, level=3, checksum=True, dict_id_flag=True):
+    data = bytes(data)
+    c = _Z.ZSTD_createCCtx()
+    try:
+        _Z.ZSTD_CCtx_setParameter(c, ZSTD_c_compressionLevel, level)
+        _Z.ZSTD_CCtx_setParameter(c, ZSTD_c_checksumFlag, 1 if checksum else 0)
+        _Z.ZSTD_CCtx_setParameter(c, ZSTD_c_dictIDFlag, 1 if dict_id_flag else 0)
+        r = _Z.ZSTD_CCtx_loadDictionary(c, dictionary, len(dictionary))
+        if _Z.ZSTD_isError(r):
+            raise RuntimeError("ZSTD_CCtx_loadDictionary failed")
+        cap = _Z.ZSTD_compressBound(len(data))
+        buf = ctypes.create_string_buffer(cap)
+        n = _Z.ZSTD_compress2(c, buf, cap, data, len(data))
+        if _Z.ZSTD_isError(n):
+            raise RuntimeError("ZSTD_compress2 failed")
+        return buf.raw[:n]
+    finally:
+        _Z.ZSTD_freeCCtx(c)
+
+
+def decompress_with_dict(frame, cap, dictionary):
+    d = _Z.ZSTD_createDCtx()
+    try:
+        buf = ctypes.create_string_buffer(max(cap, 1))
+        n = _Z.ZSTD_decompress_usingDict(d, buf, cap, bytes(frame), len(frame), dictionary, len(dictionary))
+        if _Z.ZSTD_isError(n):
+            return None
+        return buf.raw[:n]
+    finally:
+        _Z.ZSTD_freeDCtx(d)

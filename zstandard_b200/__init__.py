@@ -28,6 +28,7 @@ ABI = {
     "zstdb200_get_decompressed_size": (_c.c_uint64, [_c.c_void_p, _c.c_uint32]),
     "zstdb200_is_error": (_c.c_int, [_c.c_uint32]),
     "zstdb200_decompress": (_c.c_uint32, [_c.c_void_p, _c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_uint32]),
+    "zstdb200_load_dictionary": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_uint32]),
     "zstdb200_decompress_batch": (_c.c_int, [_c.c_void_p, _vpp, _u32p, _vpp, _u32p, _u32p, _c.c_size_t]),
     "zstdb200_decompress_batch_device": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                                     _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
@@ -166,6 +167,14 @@ class Context:
         if rc != 0:
             raise RuntimeError("zstdb200 batch failed: " + self.last_error())
         return res
+
+    def load_dictionary(self, dictionary):
+        """ZSTD_decompress_usingDict (ZStdDecompress.cs:2162-2167, :2366-2475): later decompress calls start every data frame
+        from this dictionary; None / b"" removes it."""
+        d = bytes(dictionary) if dictionary else b""
+        rc = self._lib.zstdb200_load_dictionary(self._h, d if d else None, len(d))
+        if rc != 0:
+            raise RuntimeError("zstdb200_load_dictionary failed: " + self.last_error())
 
     def decompress_batch(self, srcs, dsts):
         """Decodes srcs[i] into the writable buffer dsts[i]; returns np.uint32 result codes (reference convention)."""

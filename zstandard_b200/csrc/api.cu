@@ -53,6 +53,7 @@ struct Device {
   u32 *d_result = nullptr;
   FrameInfo* d_info = nullptr; u8* d_lit = nullptr; SeqRec* d_seq = nullptr;
   u32* d_more = nullptr;                        // per-stream counters of items with another data frame to decode (DecodeArgs::more)
+  u8* d_dict = nullptr; size_t dictCap = 0; DictState* d_dictState = nullptr; bool dictOn = false;   // zstdb200_load_dictionary
   EncodeScratch enc;                            // encoder arenas (encode_kernels.cuh)
   // pinned host memory
   u8 *h_src = nullptr, *h_dst = nullptr;
@@ -111,6 +112,7 @@ void free_device(Device& d) {
   for (auto& s : d.stream) if (s) cudaStreamSynchronize(s);
   cudaFree(d.d_src); cudaFree(d.d_dst); cudaFree(d.d_desc);
   cudaFree(d.d_info); cudaFree(d.d_lit); cudaFree(d.d_seq); cudaFree(d.d_more); cudaFreeHost(d.h_more);
+  cudaFree(d.d_dict); cudaFree(d.d_dictState);
   encode_free(d.enc);
   cudaFreeHost(d.h_src); cudaFreeHost(d.h_dst); cudaFreeHost(d.h_desc);
   for (auto& s : d.stream) if (s) cudaStreamDestroy(s);
@@ -299,7 +301,7 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     int nl = 0;
     if (j.op == Op::Decompress) {
       DecodeArgs ar{d.d_src, d_srcOff + a, d_srcSize + a, d.d_dst, d_dstOff + a, d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
-                    d.d_info + a, d.d_lit, d.d_seq, 0, d.d_more + (s % nStreams)};
+                    d.d_info + a, d.d_lit, d.d_seq, d.dictOn ? d.d_dictState : nullptr, d.d_dict, 0, d.d_more + (s % nStreams)};
       e = decode_launch(ar, st, &nl);
     } else {
       EncodeArgs ar{d.d_src, d_srcOff + a, d_srcSize + a, d.d_dst, d_dstOff + a, d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
@@ -335,7 +337,7 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     // rare path: some items hold several data frames.  Everything is still resident: decode the remaining frames
     // pass by pass over the whole sub-batch, then fetch results and output again.
     cudaStream_t st = d.stream[0]; int nl = 0;
-    DecodeArgs ar{d.d_src, d_srcOff, d_srcSize, d.d_dst, d_dstOff, d_dstCap, d.d_result, (u32)m, 0, d.d_info, d.d_lit, d.d_seq, 0, nullptr};
+    DecodeArgs ar{d.d_src, d_srcOff, d_srcSize, d.d_dst, d_dstOff, d_dstCap, d.d_result, (u32)m, 0, d.d_info, d.d_lit, d.d_seq, d.dictOn ? d.d_dictState : nullptr, d.d_dict, 0, nullptr};
     e = decode_more_passes(d, ar, 0, st, &nl); *launches += nl;
     if (e) return fail("multi-frame passes", e);
     e = cudaMemcpyAsync(d.h_result, d.d_result, m * 4, cudaMemcpyDeviceToHost, st); if (e) return fail("D2H result", e);
@@ -502,6 +504,27 @@ uint64_t zstdb200_get_decompressed_size(const void* src, uint32_t srcSize) {
   return fcs >= 0xFFFFFFFFFFFFFFFEull ? 0 : fcs;
 }
 
+// ZSTD_decompress_usingDict (ZStdDecompress.cs:2162-2167; dictionary loading :2366-2475): the dictionary becomes part of
+// the context and every later decompress call starts each data frame from it.  dict == NULL or dictSize == 0 removes it.
+int zstdb200_load_dictionary(zstdb200_ctx* ctx, const void* dict, uint32_t dictSize) {
+  if (!ctx) return 1;
+  ctx->err.clear();
+  for (auto& d : ctx->dev) {
+    CK(cudaSetDevice(d.id));
+    if (!dict || dictSize == 0) { d.dictOn = false; continue; }
+    if (dictSize + 64 > d.dictCap) {
+      cudaFree(d.d_dict); d.d_dict = nullptr; d.dictCap = 0;
+      CK(cudaMalloc(&d.d_dict, (size_t)dictSize + 64)); d.dictCap = (size_t)dictSize + 64;
+    }
+    if (!d.d_dictState) CK(cudaMalloc(&d.d_dictState, sizeof(DictState)));
+    CK(cudaMemcpyAsync(d.d_dict, dict, dictSize, cudaMemcpyHostToDevice, d.stream[0]));
+    CK(decode_load_dictionary(d.d_dict, dictSize, d.d_dictState, d.stream[0]));
+    CK(cudaStreamSynchronize(d.stream[0]));
+    d.dictOn = true;
+  }
+  return 0;
+}
+
 int zstdb200_decompress_batch(zstdb200_ctx* ctx, const void* const* src, const uint32_t* srcSize,
                               void* const* dst, const uint32_t* dstCap, uint32_t* result, size_t n) {
   if (!ctx) return 1;
@@ -544,7 +567,7 @@ int zstdb200_decompress_batch_device(zstdb200_ctx* ctx, int device_index, const 
   if (n > ctx->maxItems) { ctx->err = "n exceeds zstdb200_max_items"; return 1; }
   Device& d = ctx->dev[device_index];
   CK(cudaSetDevice(d.id));
-  DecodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, 0, d.d_info, d.d_lit, d.d_seq, 0, nullptr};
+  DecodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, 0, d.d_info, d.d_lit, d.d_seq, d.dictOn ? d.d_dictState : nullptr, d.d_dict, 0, nullptr};
   return decode_device(ctx, d, a, stream ? (cudaStream_t)stream : d.stream[0], nullptr);
 }
 
@@ -562,7 +585,7 @@ int zstdb200_decompress_batch_device_timed(zstdb200_ctx* ctx, int device_index, 
   cudaStream_t st = stream ? (cudaStream_t)stream : d.stream[0];
   cudaEvent_t ev[DECODE_KERNELS + 1];
   for (auto& e : ev) CK(cudaEventCreate(&e));
-  DecodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, 0, d.d_info, d.d_lit, d.d_seq, 0, nullptr};
+  DecodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, 0, d.d_info, d.d_lit, d.d_seq, d.dictOn ? d.d_dictState : nullptr, d.d_dict, 0, nullptr};
   if (decode_device(ctx, d, a, st, ev)) return 1;
   CK(cudaStreamSynchronize(st));
   for (int k = 0; k < DECODE_KERNELS && k < max_kernels; k++) CK(cudaEventElapsedTime(&kernel_ms[k], ev[k], ev[k + 1]));

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(128) k_parse(DecodeArgs a) {
     if ((prev.flags & FI_DONE) || prev.next_off == 0 || is_err(a.result[i])) { a.info[i].flags = FI_DONE; return; }
     start = prev.next_off; outBase = prev.out_base + prev.decoded;
   }
-  bool go = parse_item(a.src_base + a.src_off[i], a.src_size[i], fi, &r, start, outBase);
+  bool go = parse_item(a.src_base + a.src_off[i], a.src_size[i], fi, &r, start, outBase, a.dict ? a.dict->err : 0, a.dict ? a.dict->dictID : 0);
   a.info[i] = fi;
   if (!go) a.result[i] = r;
 }
@@ -74,6 +74,13 @@ __global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
   u8* const slotMem = (u8*)&sm.ring[slot * 4 + 1][0];   // per-symbol rank within its weight: dead once the table is filled
   u32 pos = fi.body_off, blk = 0; u64 litRun = 0;
   u32 tableLog = 0; bool haveTable = false;
+  if (a.dict && a.dict->hasEntropy) {                                              // litEntropy = 1 after ZSTD_decompress_insertDictionary (:2468)
+    const uint4* s4 = reinterpret_cast<const uint4*>(a.dict->huf); uint4* d4 = reinterpret_cast<uint4*>(dt);
+    for (u32 i = sub; i < (sizeof(u16) << HUF_TABLE_LOG) / 16; i += 4) d4[i] = s4[i];
+    tableLog = a.dict->hufLog; haveTable = true;
+    if (tableLog > HUF_TABLE_LOG) { for (u32 i = sub; i < 256; i += 4) sideMem[i] = a.dict->hufSide[i]; side = sideMem; }
+    __syncwarp(gmask);
+  }
   u32 errBlock = 0xFFFFFFFFu, errCode = 0;
   while (true) {
     BlockHdr bh;
@@ -138,6 +145,11 @@ __global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
 // =================================================================================================
 // k_seq : one warp per CTA, one frame per lane, tables bank-interleaved across lanes
 // =================================================================================================
+// The chain half (seq_decode_frame) and the finishing half (SeqEmitter) of sequence decoding run in the same thread.
+// (Measured alternative, round 2: the two halves on two warps of a CTA — two schedulers — joined by a per-lane
+// shared-memory queue.  The chain warp's loop went from 136 to 103 instructions but only from ~400 to ~373 cycles per
+// sequence: it is bound by the dependent chain state -> cell -> extra-bit count -> shift -> state plus the one-warp ALU
+// issue rate, and the queue's back-pressure test adds a divergent branch; 2.06 ms against 1.72 ms for this kernel.)
 struct SeqSmem {
   u16 ll[512][32];       // lane-interleaved: cell[state][lane]
   u16 ml[512][32];
@@ -171,11 +183,13 @@ __global__ void __launch_bounds__(32) k_seq(DecodeArgs a) {
   SeqTableSet T;
   T.space[KIND_LL] = &sm.ll[0][lane]; T.space[KIND_ML] = &sm.ml[0][lane]; T.space[KIND_OF] = &sm.of[0][lane]; T.stride = 32;
   T.defs[KIND_LL] = sm.defLL; T.defs[KIND_OF] = sm.defOF; T.defs[KIND_ML] = sm.defML;
-  SeqFrameOut res;
-  seq_decode_frame(a.src_base + a.src_off[f], a.src_size[f], fi.body_off, fi.window, T, seq_region(a, f, fi), seq_capacity(frame_cap(a, f, fi)), res, sm.llInfo, sm.mlInfo,
-                   Strided<s16>{&sm.norm[0][lane], 32}, Strided<u16>{&sm.next[0][lane], 32}, &sm.ring[lane][0]);
-  if (res.err_block != 0xFFFFFFFFu) {
-    a.info[f].seq_err_block = res.err_block; a.info[f].seq_err_code = res.err_code; a.info[f].seq_err_index = res.err_index;
+  SeqEmitter em;
+  em.init(seq_region(a, f, fi), seq_capacity(frame_cap(a, f, fi)), sm.llInfo, sm.mlInfo);
+  if (a.dict) em.set_reps(a.dict->rep);
+  seq_decode_frame(a.src_base + a.src_off[f], a.src_size[f], fi.body_off, fi.window, T, em, sm.llInfo, sm.mlInfo,
+                   Strided<s16>{&sm.norm[0][lane], 32}, Strided<u16>{&sm.next[0][lane], 32}, &sm.ring[lane][0], a.dict);
+  if (em.res.err_block != 0xFFFFFFFFu) {
+    a.info[f].seq_err_block = em.res.err_block; a.info[f].seq_err_code = em.res.err_code; a.info[f].seq_err_index = em.res.err_index;
   }
 }
 
@@ -371,6 +385,8 @@ __device__ __forceinline__ void warp_match(u8* d, u32 off, u32 len, u32 lane) {
 
 // 16 CTAs of 4 warps per SM (32 registers, spills to local memory included): measured faster than fewer, fatter warps —
 // the kernel lives on occupancy (6 / 8 / 10 / 12 / 16 CTAs: 3.93 / 3.44 / 3.03 / 2.95 / 2.83 ms on the bench workload).
+// DICT: the context has a dictionary (its content is the window's prefix); the common kernel carries none of that code
+template <bool DICT>
 __global__ void __launch_bounds__(EXEC_THREADS, 16) k_exec(DecodeArgs a) {
   const u32 lane = threadIdx.x & 31;
   const u32 f = (blockIdx.x * EXEC_THREADS + threadIdx.x) >> 5;
@@ -383,6 +399,10 @@ __global__ void __launch_bounds__(EXEC_THREADS, 16) k_exec(DecodeArgs a) {
   const SeqRec* recs = seq_region(a, f, fi); const u32 recCap = (u32)seq_capacity(cap);
   u32 pos = fi.body_off, blk = 0, op = 0, litRun = 0, recRun = 0;   // op <= cap < 2^32 throughout: checks are written against cap - op
   bool litEntropy = false, dry = false; u32 err = 0;
+  // the dictionary's content is the window's prefix (RefDictContent :2366-2373): dictEnd[-k] is what offset (produced + k) reaches
+  const u32 dictContent = DICT ? a.dict->contentSize : 0;
+  const u8* const dictEnd = DICT ? a.dict_bytes + a.dict->contentOff + dictContent : nullptr;
+  if (DICT && a.dict->hasEntropy) litEntropy = true;                               // :2468
   while (true) {
     BlockHdr bh;
     err = read_block_hdr(src + pos, size - pos, bh);
@@ -432,7 +452,7 @@ __global__ void __launch_bounds__(EXEC_THREADS, 16) k_exec(DecodeArgs a) {
           const u64 start64 = (u64)blockBase + rec.x;
           const bool e1 = valid && start64 + ll + ml > cap;
           const bool e2 = valid && lpos + ll > litSize;
-          const bool e3 = valid && (u64)off > start64 + ll;
+          const bool e3 = valid && (u64)off > start64 + ll + dictContent;           // :1290-1294 (the prefix includes the dictionary)
           const unsigned bad = __ballot_sync(FULLMASK, e1 | e2 | e3);
           if (bad) {
             const u32 first = (u32)__ffs(bad) - 1;
@@ -484,7 +504,8 @@ __global__ void __launch_bounds__(EXEC_THREADS, 16) k_exec(DecodeArgs a) {
             while (doneMask != 0xFFFFFFFFu) {
               const bool ready = hasM && !((doneMask >> lane) & 1) && ((depMask & ~doneMask) == 0);
               const unsigned R = __ballot_sync(FULLMASK, ready);
-              const bool plain = ready && off >= ml && ml < 128;
+              const bool inDict = DICT && off > blockBase + base + mrel;          // the source begins in the dictionary (:1290-1315)
+              const bool plain = ready && off >= ml && ml < 128 && !inDict;
               const u32 len = plain ? ml : 0, units = (len + 3) >> 2;
               const u32 pincl = warp_incl_scan(units, lane), pexcl = pincl - units;
               const u32 Tt = __shfl_sync(FULLMASK, pincl, 31);
@@ -494,7 +515,14 @@ __global__ void __launch_bounds__(EXEC_THREADS, 16) k_exec(DecodeArgs a) {
               while (big) {
                 const u32 j = (u32)__ffs(big) - 1; big &= big - 1;
                 const u32 mj = __shfl_sync(FULLMASK, mrel, j), oj = __shfl_sync(FULLMASK, off, j), nj = __shfl_sync(FULLMASK, ml, j);
-                warp_match(g + mj, oj, nj, lane);
+                const u32 pj = blockBase + base + mj;                              // the match's output position within the frame
+                if (DICT && oj > pj) {
+                  // `back` bytes come from the end of the dictionary content, the rest continues at the frame's first byte
+                  const u32 back = oj - pj, l1 = back < nj ? back : nj;
+                  warp_copy(g + mj, dictEnd - back, l1, lane);
+                  __syncwarp();
+                  if (nj > l1) warp_match(g + mj + l1, pj + l1, nj - l1, lane);
+                } else warp_match(g + mj, oj, nj, lane);
               }
               __syncwarp();
               doneMask |= R;
@@ -572,6 +600,16 @@ __global__ void __launch_bounds__(128) k_xxh(DecodeArgs a) {
 size_t decode_lit_arena_bytes(u64 max_dst_bytes, u64 max_items) { return (size_t)(max_dst_bytes + 64 * (max_items + 2) + 256); }
 size_t decode_seq_arena_bytes(u64 max_dst_bytes, u64 max_items) { return (size_t)((2 * (max_dst_bytes / 3) + 32 * (max_items + 2) + 64) * sizeof(SeqRec)); }
 
+// k_dict : one thread parses the context's dictionary into a DictState (zb_format.cuh dict_load)
+__global__ void __launch_bounds__(32) k_dict(const u8* dict, u32 size, DictState* ds) {
+  __shared__ HufBuildWk wk; __shared__ HufFseScratch fs; __shared__ u8 slot[260]; __shared__ s16 norm[64]; __shared__ u16 next[64];
+  if (threadIdx.x == 0) dict_load(dict, size, *ds, wk, fs, slot, norm, next);
+}
+cudaError_t decode_load_dictionary(const u8* d_dict_bytes, u32 size, DictState* d_state, cudaStream_t st) {
+  k_dict<<<1, 32, 0, st>>>(d_dict_bytes, size, d_state);
+  return cudaGetLastError();
+}
+
 cudaError_t decode_configure() {
   cudaError_t e = cudaFuncSetAttribute(k_huf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HufSmem));
   if (e != cudaSuccess) return e;
@@ -597,7 +635,8 @@ cudaError_t decode_launch_entropy(const DecodeArgs& a, cudaStream_t st, int* lau
 }
 cudaError_t decode_launch_exec(const DecodeArgs& a, cudaStream_t st, int* launches, cudaEvent_t* marks) {
   if (a.n == 0) return cudaSuccess;
-  k_exec<<<(a.n + (EXEC_THREADS / 32) - 1) / (EXEC_THREADS / 32), EXEC_THREADS, 0, st>>>(a);
+  if (a.dict) k_exec<true><<<(a.n + (EXEC_THREADS / 32) - 1) / (EXEC_THREADS / 32), EXEC_THREADS, 0, st>>>(a);
+  else k_exec<false><<<(a.n + (EXEC_THREADS / 32) - 1) / (EXEC_THREADS / 32), EXEC_THREADS, 0, st>>>(a);
   if (marks) cudaEventRecord(marks[4], st);
   k_xxh<<<(a.n * 4 + 127) / 128, 128, 0, st>>>(a);
   if (marks) cudaEventRecord(marks[5], st);

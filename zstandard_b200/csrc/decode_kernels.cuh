@@ -20,6 +20,8 @@ struct DecodeArgs {
   // Items that hold several data frames (ZStdDecompress.cs:2096-2160) are decoded one data frame per pass: the
   // execute stage counts in *more the items that found another data frame behind the one it finished; the host
   // re-launches the pipeline with pass + 1 until the count stays 0.  Later passes skip every other item.
+  const DictState* dict;   // the context's dictionary prepared by decode_load_dictionary (null: none), and its bytes
+  const u8* dict_bytes;
   u32 pass;            // 0 = first data frame of every item
   u32* more;           // device counter, zeroed by the host before each pass (may be null: multi-frame items end after frame 1)
 };
@@ -27,6 +29,8 @@ struct DecodeArgs {
 size_t decode_lit_arena_bytes(u64 max_dst_bytes, u64 max_items);
 size_t decode_seq_arena_bytes(u64 max_dst_bytes, u64 max_items);
 cudaError_t decode_configure();
+// parses the dictionary at d_dict_bytes (device memory, size bytes) into *d_state on `st` (one small kernel)
+cudaError_t decode_load_dictionary(const u8* d_dict_bytes, u32 size, DictState* d_state, cudaStream_t st);
 // enqueues the whole decode pipeline for one batch on `st`; *launches += number of kernels launched
 cudaError_t decode_launch(const DecodeArgs& a, cudaStream_t st, int* launches, cudaEvent_t* marks = nullptr);
 // the two halves of decode_launch

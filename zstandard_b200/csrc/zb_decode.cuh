@@ -1,7 +1,8 @@
 // zb_decode.cuh — per-thread bodies of the entropy stages of the GPU decoder.
 //
 //   seq_decode_frame : one thread walks one frame's blocks, builds the LL/OF/ML tables in (bank-interleaved)
-//                      shared memory and turns every sequences bitstream into 8-byte records in HBM scratch.
+//                      shared memory and hands every sequence of the bitstreams to a sink; SeqEmitter turns them into
+//                      16-byte records in HBM scratch.
 //   huf_*            : one thread per Huffman stream (4 per frame) decodes literals into HBM scratch from a
 //                      shared-memory decode table built by the frame's first lane.
 //
@@ -125,21 +126,84 @@ ZB_HD void seq_values_ref32(const u8* s, u32 n, i32 P, bool longOffsets, u32 ofB
   llv = llBits ? refbits_read_fast(b, llBits) : 0;                                 // :1542
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Sequence decoding is split in two halves that meet at a narrow interface (a "sink"):
+//   the CHAIN half (seq_decode_frame) owns what is serially dependent from one sequence to the next — the three FSE
+//   states and the bit cursor (DecodeSequence :1473-1553 without its value arithmetic) — and hands every sequence
+//   over as (32 stream bits that begin with its value bits, the three symbols);
+//   the FINISHING half (SeqEmitter) extracts the value bits, applies the repeat-offset rules (:1509-1530), keeps the
+//   running output / literal positions and writes the records.
+// The kernel (k_seq) and the CPU replay (tests/hostsim) plug the emitter in directly.  (Measured in round 2: the halves
+// on two warps of one CTA with a per-lane shared-memory queue between them — see k_seq in decode_kernels.cu; slower.)
+// ---------------------------------------------------------------------------------------------------
+struct SeqEmitter {
+  SeqRec* out; u32 cap; const u32* llInfo; const u32* mlInfo;
+  u32 n;                          // record slots used so far (headers included)
+  u32 hdrSlot, dpos, lpos;        // the current block: its header slot, running output / literal positions
+  u32 rep0, rep1, rep2;           // ZStdInternal.cs:111, ZStdDecompress.cs:2492
+  bool dead;                      // the frame's first entropy-level error has been recorded: later blocks are ignored
+  SeqFrameOut res;
+  ZB_HD void init(SeqRec* o, u64 cap64, const u32* lli, const u32* mli) {
+    out = o; cap = (u32)cap64; llInfo = lli; mlInfo = mli;        // seq_capacity of a u32 capacity fits 32 bits
+    n = 0; hdrSlot = 0; dpos = 0; lpos = 0; rep0 = 1; rep1 = 4; rep2 = 8; dead = false;
+    res.err_block = 0xFFFFFFFFu; res.err_code = 0; res.err_index = 0;
+  }
+  ZB_HD void set_reps(const u32* r) { rep0 = r[0]; rep1 = r[1]; rep2 = r[2]; }          // a dictionary's repeat offsets (:2436-2442)
+  ZB_HD void block_begin() { if (dead) return; hdrSlot = n++; dpos = 0; lpos = 0; }   // the block's header record is written last
+  ZB_HD void emit(u32 ofBits, u32 ofv, u32 llSym, u32 ll, u32 ml) {
+    const u32 offset = rep_resolve(rep0, rep1, rep2, ofBits, ofv, llSym);
+    if (n < cap) rec_store(out + n, dpos, lpos | ((ml >> 15) << 18), offset, ll | (ml << 17));
+    n++; dpos = sat_add32(dpos, ll + ml); lpos = sat_lpos(lpos, ll);
+  }
+  // a sequence of the fast path: hi = 32 stream bits whose top bits are its value bits (fewer than 32 of them), in the
+  // reference's read order offset, matchLength, litLength (:1504, :1534, :1542); iLL / iML = the symbols' info words
+  ZB_HD void fast(u32 hi, u32 llSym, u32 ofBits, u32 iLL, u32 iML) {
+    const u32 llBits = iLL >> 24, mlBits = iML >> 24;
+    const u32 ofv = shr_c(hi, 32 - ofBits);
+    const u32 mlv = shr_c(hi << ofBits, 32 - mlBits);
+    const u32 llv = shr_c(hi << (ofBits + mlBits), 32 - llBits);
+    emit(ofBits, ofv, llSym, (iLL & 0xFFFFFF) + llv, (iML & 0xFFFFFF) + mlv);
+  }
+  // a sequence whose value bits the chain half had to extract itself (stream tail, >= 32 value bits, over-reads)
+  ZB_HD void values(u32 ofv, u32 mlv, u32 llv, u32 llSym, u32 mlSym, u32 ofBits) {
+    emit(ofBits, ofv, llSym, (llInfo[llSym] & 0xFFFFFF) + llv, (mlInfo[mlSym] & 0xFFFFFF) + mlv);
+  }
+  // true once the frame's first entropy-level error is recorded: the chain half stops (nothing it decodes is used)
+  ZB_HD bool stopped() const { return dead; }
+  // decoded = sequences handed over, bad = the bitstream failed after them (:1577, :1582 -> corruption_detected)
+  ZB_HD void block_end(u32 blk, u32 decoded, bool bad) {
+    if (dead) return;
+    // header record: how many records the execute stage may run (those that fit the region)
+    const bool overflow = n > cap;
+    if (hdrSlot < cap) rec_store(out + hdrSlot, (overflow ? cap : n) - hdrSlot - 1, dpos, lpos, 0);
+    if (overflow) { res.err_block = blk; res.err_code = ZE_dstSize_tooSmall; res.err_index = 0; dead = true; }
+    else if (bad) { res.err_block = blk; res.err_code = ZE_corruption_detected; res.err_index = decoded; dead = true; }
+  }
+  // the block failed before its first sequence (count / table headers)
+  ZB_HD void fail(u32 blk, u32 code) { if (dead) return; res.err_block = blk; res.err_code = code; res.err_index = 0xFFFFFFFFu; dead = true; }
+};
+
 // Walks the frame at item `src` (size bytes, first block header at body_off) and decodes every compressed
-// block's sequences.  Stops silently at structural errors that the execute stage will report itself from the
-// same headers; records entropy-level failures in `res`.
+// block's sequences into `sink` (block_begin / fast / values / block_end / fail / stopped, see SeqEmitter).  Stops silently at
+// structural errors that the execute stage will report itself from the same headers.
 // llInfo/mlInfo: per-symbol base | extra bits << 24 (ll_info/ml_info); norm/symbolNext: >= 53 entries of per-thread scratch each;
 // ringMem: ZB_RING_WORDS words of per-thread bitstream read-ahead (BitRing), 16-byte aligned.
-template <class NormT, class NextT>
-ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, SeqTableSet& T, SeqRec* out, u64 cap64, SeqFrameOut& res,
-                            const u32* llInfo, const u32* mlInfo, NormT norm, NextT symbolNext, u32* ringMem) {
-  res.err_block = 0xFFFFFFFFu; res.err_code = 0; res.err_index = 0;
+// dict: the context's dictionary (may be null): its sequence tables are what repeat mode refers to until a block
+// brings its own (fseEntropy = 1 after ZSTD_decompress_insertDictionary, :2468).
+template <class Sink, class NormT, class NextT>
+ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, SeqTableSet& T, Sink& sink,
+                            const u32* llInfo, const u32* mlInfo, NormT norm, NextT symbolNext, u32* ringMem, const DictState* dict = nullptr) {
   u32 pos = body_off, blk = 0;
-  u32 rep0 = 1, rep1 = 4, rep2 = 8;                      // ZStdInternal.cs:111, ZStdDecompress.cs:2492
   bool haveRepeat = false;
-  const u32 cap = (u32)cap64;                            // seq_capacity of a u32 capacity fits 32 bits
-  u32 n = 0;                                             // record slots used so far (headers included)
   for (int k = 0; k < 3; k++) { T.cur[k] = T.space[k]; T.curStride[k] = T.stride; T.log[k] = 0; }
+  if (dict && dict->hasEntropy) {
+    for (int k = 0; k < 3; k++) {
+      const u32 n = 1u << dict->log[k];
+      for (u32 u = 0; u < n; u++) T.space[k][u * T.stride] = dict->cells[k][u];
+      T.log[k] = dict->log[k];
+    }
+    haveRepeat = true;
+  }
   while (true) {
     BlockHdr bh;
     if (read_block_hdr(src + pos, size - pos, bh)) return;
@@ -152,7 +216,7 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, S
       const u8* sp = bp + lh.consumed; u32 ssz = bsz - lh.consumed;
       u32 nbSeq, modes, hdr;
       u32 e = read_seq_count(sp, ssz, &nbSeq, &modes, &hdr);
-      if (e) { res.err_block = blk; res.err_code = e; res.err_index = 0xFFFFFFFFu; return; }
+      if (e) { sink.fail(blk, e); return; }
       if (nbSeq) {
         // tables in the reference's order LL, OF, ML (:1149-1176); any failure is corruption_detected
         const int kinds[3] = {KIND_LL, KIND_OF, KIND_ML};
@@ -170,12 +234,11 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, S
             }
           }
         }
-        if (e) { res.err_block = blk; res.err_code = ZE_corruption_detected; res.err_index = 0xFFFFFFFFu; return; }
+        if (e) { sink.fail(blk, ZE_corruption_detected); return; }
         haveRepeat = true;                                                         // fseEntropy = 1 (:1575)
         // ---- bitstream ----
         BitCursor c;
-        const u32 hdrSlot = n++;                                                   // the block's header record, written last
-        u32 dpos = 0, lpos = 0;                                                    // running output / literal positions within the block
+        sink.block_begin();
         u32 decoded = 0; bool bad = false;
         if (!bc_init(c, sp + hdr, ssz - hdr)) bad = true;                          // :1577 -> corruption_detected
         if (!bad) {
@@ -187,9 +250,8 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, S
             lg = T.log[KIND_OF]; stOF = top_bits(w, lg); w <<= lg; P -= (i32)lg;
             lg = T.log[KIND_ML]; stML = top_bits(w, lg); P -= (i32)lg; }             // :1578-1580 (<= 26 bits)
           u32 i = 0;
-          // ---- fast loop: >= 128 unread bits, so no over-read is possible (a sequence takes <= 89 bits) and
-          //      all six fields come out of 32-bit registers; leaves to the careful loop when a sequence
-          //      carries >= 32 value bits (rare: very long lengths / offsets) ----
+          // ---- fast loop: >= 128 unread bits, so no over-read is possible (a sequence takes <= 89 bits); leaves to
+          //      the careful loop when a sequence carries >= 32 value bits (rare: very long lengths / offsets) ----
           BitRing ring;
           if (nbSeq && P >= 128) ring_init(ring, ringMem, sp + hdr, ssz - hdr);
           while (i < nbSeq && P >= 128) {
@@ -198,21 +260,14 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, S
             const u32 yLL = tLL[stLL * sLLs], yOF = tOF[stOF * sOFs], yML = tML[stML * sMLs];
             const u32 llSym = yLL >> 10, mlSym = yML >> 10, ofBits = yOF >> 10;   // the offset code is its own extra-bit count
             const u32 iLL = llInfo[llSym], iML = mlInfo[mlSym];
-            const u32 llBits = iLL >> 24, mlBits = iML >> 24;
-            const u32 valBits = ofBits + mlBits + llBits;
+            const u32 valBits = ofBits + (iML >> 24) + (iLL >> 24);
             const u32 lLL = yLL & 0x3FF, lOF = yOF & 0x3FF, lML = yML & 0x3FF;
             const u32 nLL = cell_nb(lLL), nML = cell_nb(lML), nOF = cell_nb(lOF);
-            const u32 ofv = shr_c(hi, 32 - ofBits);                                // read order: offset, matchLength, litLength
-            const u32 mlv = shr_c(hi << ofBits, 32 - mlBits);                      // (:1504, :1534, :1542)
-            const u32 llv = shr_c(hi << (ofBits + mlBits), 32 - llBits);
-            const u32 ml = (iML & 0xFFFFFF) + mlv, ll = (iLL & 0xFFFFFF) + llv;
-            // the one rare exit of the loop: >= 32 value bits (the 32-bit extraction above is then wrong) — nothing has
-            // been committed yet, the careful loop redoes this sequence
+            // the one rare exit of the loop: >= 32 value bits (they do not fit the word handed over) — nothing has been
+            // committed yet, the careful loop redoes this sequence
             if (valBits >= 32) break;
+            sink.fast(hi, llSym, ofBits, iLL, iML);
             const u32 h2 = fshl(lo, hi, valBits);                                  // the 32 bits after the value bits
-            const u32 offset = rep_resolve(rep0, rep1, rep2, ofBits, ofv, llSym);
-            if (n < cap) rec_store(out + n, dpos, lpos | ((ml >> 15) << 18), offset, ll | (ml << 17));
-            n++; dpos = sat_add32(dpos, ll + ml); lpos = sat_lpos(lpos, ll);
             stLL = cell_base(lLL) + shr_c(h2, 32 - nLL);                           // state update LL, ML, OF (:1547-1550)
             stML = cell_base(lML) + shr_c(h2 << nLL, 32 - nML);
             stOF = cell_base(lOF) + shr_c(h2 << (nLL + nML), 32 - nOF);
@@ -227,8 +282,7 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, S
             const u64 w0 = bc_window64(c, P);
             const u32 yLL = tLL[stLL * sLLs], yOF = tOF[stOF * sOFs], yML = tML[stML * sMLs];
             const u32 llSym = yLL >> 10, mlSym = yML >> 10, ofBits = yOF >> 10;
-            const u32 iLL = llInfo[llSym], iML = mlInfo[mlSym];
-            const u32 llBits = iLL >> 24, mlBits = iML >> 24;
+            const u32 llBits = llInfo[llSym] >> 24, mlBits = mlInfo[mlSym] >> 24;
             const u32 lLL = yLL & 0x3FF, lOF = yOF & 0x3FF, lML = yML & 0x3FF;
             const u32 nLL = cell_nb(lLL), nML = cell_nb(lML), nOF = cell_nb(lOF);
             const u32 valBits = ofBits + mlBits + llBits, stBits = nLL + nML + nOF;
@@ -239,10 +293,7 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, S
             const i32 Pv = P - (i32)valBits;
             if (Pv < 0) seq_values_ref32(sp + hdr, ssz - hdr, P, window > (1ull << 25), ofBits, mlBits, llBits, ofv, mlv, llv);   // over-read: the reference's container garbage
             else if (valBits + stBits > 64) w = bc_window64(c, Pv);                // rare: more than 64 bits in one sequence
-            const u32 offset = rep_resolve(rep0, rep1, rep2, ofBits, ofv, llSym);
-            const u32 ml = (iML & 0xFFFFFF) + mlv, ll = (iLL & 0xFFFFFF) + llv;
-            if (n < cap) rec_store(out + n, dpos, lpos | ((ml >> 15) << 18), offset, ll | (ml << 17));
-            n++; dpos = sat_add32(dpos, ll + ml); lpos = sat_lpos(lpos, ll);
+            sink.values(ofv, mlv, llv, llSym, mlSym, ofBits);
             decoded++;
             // past the last sequence these bits do not exist (the stream ends after its value bits)
             stLL = cell_base(lLL) + top_bits(w, nLL); w <<= nLL;
@@ -251,11 +302,8 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, S
             P = Pv - (i32)stBits;
           }
         }
-        // header record: how many records the execute stage may run (those that fit the region)
-        const bool overflow = n > cap;
-        if (hdrSlot < cap) rec_store(out + hdrSlot, (overflow ? cap : n) - hdrSlot - 1, dpos, lpos, 0);
-        if (overflow) { res.err_block = blk; res.err_code = ZE_dstSize_tooSmall; res.err_index = 0; return; }
-        if (bad) { res.err_block = blk; res.err_code = ZE_corruption_detected; res.err_index = decoded; return; }
+        sink.block_end(blk, decoded, bad);
+        if (bad || sink.stopped()) return;
       }
     }
     pos += bh.csize; blk++;

@@ -16,7 +16,9 @@ namespace zb {
 // returns false when the item's result is already final (*result set).
 // start / out_base: where in the item to look and how many bytes its earlier data frames produced (0, 0 on the
 // first pass; the execute stage's next_off and running total on later passes of a multi-frame item).
-ZB_HD bool parse_item(const u8* src, u32 size, FrameInfo& fi, u32* result, u32 start = 0, u32 out_base = 0) {
+// dictErr / ctxDictID: state of the context's dictionary (ZSTD_decompressBegin_usingDict :2501-2507 runs before every
+// data frame and fails it with dictionary_corrupted; DecodeFrameHeader :633 compares the frame's dictionary id).
+ZB_HD bool parse_item(const u8* src, u32 size, FrameInfo& fi, u32* result, u32 start = 0, u32 out_base = 0, u32 dictErr = 0, u32 ctxDictID = 0) {
   fi.flags = 0; fi.body_off = 0; fi.fcs = 0; fi.window = 0;
   fi.huf_err_block = 0xFFFFFFFFu; fi.huf_err_code = 0; fi.seq_err_block = 0xFFFFFFFFu; fi.seq_err_code = 0; fi.seq_err_index = 0;
   fi.trailer_off = 0; fi.decoded = 0; fi.out_base = out_base; fi.next_off = 0;
@@ -32,6 +34,7 @@ ZB_HD bool parse_item(const u8* src, u32 size, FrameInfo& fi, u32* result, u32 s
     if (rem < skip) { *result = zerr(ZE_srcSize_wrong); fi.flags = FI_DONE; return false; }
     pos += skip;
   }
+  if (dictErr) { *result = zerr(dictErr); fi.flags = FI_DONE; return false; }
   const u8* ip = src + pos; u32 rem = size - pos;
   u32 e = 0;
   if (rem < 6 + 3) e = ZE_srcSize_wrong;                                           // :2019
@@ -58,7 +61,7 @@ ZB_HD bool parse_item(const u8* src, u32 size, FrameInfo& fi, u32* result, u32 s
       else if (fcsId == 2) { fcs = ld32(ip + p); known = true; }
       else { fcs = ld64(ip + p); known = true; }
       if (single) window = fcs;
-      if (dictID != 0) e = ZE_dictionary_wrong;                                    // :633 (no dictionary is reachable, :2171)
+      if (dictID != 0 && dictID != ctxDictID) e = ZE_dictionary_wrong;             // :633 (ctxDictID = 0 without a dictionary, :2171)
       fi.fcs = fcs; fi.window = window;
       fi.flags = ((fhd >> 2) & 1 ? FI_CHECKSUM : 0) | (known ? FI_FCS_KNOWN : 0);
       fi.body_off = pos + fhs;
@@ -427,6 +430,58 @@ ZB_HD void huf_fill_table(u16* dt, u8* side, const HufBuildWk& wk, const u8* slo
     else if (wv == 1) { side[start] = (u8)n; dt[start >> 1] = (u16)(12u << 8); }
     else huf_fill_cells(dt, start / 2, len / 2, cell);
   }
+}
+
+// =====================================================================================================
+// Dictionary (ZSTD_decompress_insertDictionary :2449-2475, LoadEntropy :2375-2447, RefDictContent :2366-2373)
+// =====================================================================================================
+// Prepared once per context; every data frame then starts from it (ZSTD_decompressBegin_usingDict :2501-2507): the
+// content is the window's prefix, and — for a dictionary with entropy tables — the Huffman table, the three sequence
+// tables and the repeat offsets are what "repeat" / "treeless" modes of the first block refer to.
+static const u32 MAGIC_DICT = 0xEC30A437u;
+struct DictState {
+  u32 present;            // 0: no dictionary
+  u32 err;                // ZE_dictionary_corrupted when the entropy section is malformed: every data frame fails with it
+  u32 dictID, hasEntropy;
+  u32 rep[3];
+  u32 hufLog;
+  u32 log[3];             // KIND_LL, KIND_OF, KIND_ML
+  u32 contentOff, contentSize;
+  u32 pad;
+  alignas(16) u16 cells[3][512];      // decode tables in the kernels' cell format (seq_cell), stride 1
+  alignas(16) u16 huf[1u << HUF_TABLE_LOG];
+  alignas(16) u8 hufSide[256];
+};
+// One thread.  norm / next: 53 entries each; slot: 256 bytes.
+ZB_HD void dict_load(const u8* dict, u32 size, DictState& ds, HufBuildWk& wk, HufFseScratch& fs, u8* slot, s16* norm, u16* next) {
+  ds.present = 1; ds.err = 0; ds.dictID = 0; ds.hasEntropy = 0; ds.rep[0] = 1; ds.rep[1] = 4; ds.rep[2] = 8; ds.hufLog = 0;
+  ds.log[0] = ds.log[1] = ds.log[2] = 0; ds.contentOff = 0; ds.contentSize = size; ds.pad = 0;
+  if (size < 8 || ld32(dict) != MAGIC_DICT) return;                                // pure content mode (:2451-2458)
+  ds.dictID = ld32(dict + 4);
+  ds.err = ZE_dictionary_corrupted;                                                // until the whole entropy section has been accepted
+  if (size <= 8) return;
+  u32 p = 8;
+  {
+    u32 hdr = 0, tl = 0, nbSym = 0;
+    if (huf_read_weights(dict + p, size - p, wk, fs, slot, &hdr, &tl, &nbSym)) return;
+    huf_fill_table(ds.huf, ds.hufSide, wk, slot, tl, nbSym, 0, 1);
+    ds.hufLog = tl; p += hdr;
+  }
+  const int order[3] = {KIND_OF, KIND_ML, KIND_LL};
+  for (int k = 0; k < 3; k++) {
+    const int kind = order[k];
+    const u32 maxSym = kind == KIND_LL ? MaxLL : (kind == KIND_ML ? MaxML : MaxOff);
+    const u32 maxLog = kind == KIND_LL ? LLFSELog : (kind == KIND_ML ? MLFSELog : OffFSELog);
+    u32 maxSV = maxSym, tl = 0, h = 0;
+    if (read_ncount(norm, &maxSV, &tl, dict + p, size - p, &h)) return;
+    if (maxSV > maxSym || tl > maxLog) return;
+    build_seq_table(ds.cells[kind], 1, norm, maxSV, tl, next);
+    ds.log[kind] = tl; p += h;
+  }
+  if (p + 12 > size) return;
+  const u32 contentSize = size - (p + 12);
+  for (int i = 0; i < 3; i++) { const u32 r = ld32(dict + p); p += 4; if (r == 0 || r >= contentSize) return; ds.rep[i] = r; }
+  ds.contentOff = p; ds.contentSize = contentSize; ds.hasEntropy = 1; ds.err = 0;
 }
 
 }  // namespace zb
