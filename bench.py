@@ -2,7 +2,8 @@
 """bench.py — headline benchmark of libzstdb200 (BASELINE.json: GB/s uncompressed, 64 KiB frames).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload decode64k|compress128k]
-                    [--corpus log|tick|random|mixed] [--chunk BYTES] [--level 1..3] [--bytes N]
+                    [--corpus log|tick|random|mixed] [--chunk BYTES] [--level 1..3] [--bytes N] [--dictionary BYTES]
+                    [--no-extras] [--no-cpu-baseline]
 
 One process per GPU (under torchrun for N > 1: RANK/LOCAL_RANK/WORLD_SIZE from the env).  Frames are independent,
 so ranks shard the work with no data-path collective ("scaling": "weak": every rank processes --bytes of its own
@@ -17,6 +18,12 @@ Reported:
   e2e           the same work through the host-buffer C-ABI call (pinned host memory -> H2D -> kernels -> D2H)
   roofline      algorithmic bytes (bytes in + bytes out of the codec) / duration of the dominant kernel; `traffic` = that
                 kernel's DRAM bytes per launch from the committed ncu capture of this command (profiles/traffic.json)
+The default line (decode64k, log text, no --chunk) also carries
+  compress        BASELINE.json configs[2]: levels 1-3 on the same corpus in 128 KiB chunks — value, e2e, our / libzstd ratio,
+                  per-kernel ms, roofline fractions (the reference has no compressor: the ratio band is unpinned by it)
+  e2e_pageable    the same C-ABI call on pageable caller memory (what a managed byte[] is): one array pair / one array per frame
+  single_call_us  median latency of zstdb200_decompress on one 64 KiB frame
+  e2e_single_ctx  (N > 1, under torchrun) rank 0 alone driving ONE context over all N devices on N x the workload
 The other BASELINE.json configs are the same two workloads with other shapes: --corpus mixed (configs[3]), --corpus tick
 --chunk 4096..1048576 (configs[4]); profiles/ holds the lines measured for them.
   cpu_baseline  decode: the oracle (C++ port of the reference decoder; the C# reference cannot run in this image), with
@@ -52,6 +59,8 @@ def parse_args():
     ap.add_argument("--corpus", default="log", choices=["log", "tick", "random", "mixed"])
     ap.add_argument("--level", type=int, default=3)
     ap.add_argument("--chunk", type=int, default=0, help="frame / chunk size in bytes (default: the workload's 64 KiB / 128 KiB)")
+    ap.add_argument("--dictionary", type=int, default=0, help="decode only: frames compressed with a dictionary of this many bytes trained "
+                    "(ZDICT) on the head of the corpus, decoded through zstdb200_load_dictionary (SURVEY 8f-3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the compress block, the pageable / single-call / single-context measurements")
     return ap.parse_args()
@@ -126,8 +135,13 @@ def prepare(args, rank, workload=None, level=None, raw=None):
     n = (total + chunk - 1) // chunk
     raw_off = np.arange(n + 1, dtype=np.uint64) * chunk
     raw_off[-1] = total
-    w = {"raw": raw, "chunk": chunk, "n": n, "total": total, "kind": workload, "level": level}
-    blob, off = zstd_ref.compress_chunks(raw, chunk, level=level, checksum=True, threads=max(1, os.cpu_count() or 1))
+    w = {"raw": raw, "chunk": chunk, "n": n, "total": total, "kind": workload, "level": level, "dictionary": None}
+    if args.dictionary and workload == "decode64k":
+        head = raw[:min(total, 16 << 20)].tobytes()
+        w["dictionary"] = zstd_ref.train_dict([head[i:i + chunk] for i in range(0, len(head), chunk)][:4096], args.dictionary)
+        plain, poff = zstd_ref.compress_chunks(raw, chunk, level=level, checksum=True, threads=max(1, os.cpu_count() or 1))
+        w["plain_compressed_bytes"] = int(poff[-1])
+    blob, off = zstd_ref.compress_chunks(raw, chunk, level=level, checksum=True, threads=max(1, os.cpu_count() or 1), dictionary=w["dictionary"])
     w["ref_compressed_bytes"] = int(off[-1])
     if workload == "decode64k":
         w.update(src=blob, src_off=off, dst_cap=np.diff(raw_off).astype(np.uint32), dst_stride=chunk)
@@ -144,7 +158,11 @@ def workload_config(args, w):
     else:
         what = (f"compress{w['chunk'] // 1024}k: batched level-{w['level']} compression of {w['total']} B/GPU of {args.corpus} text in "
                 f"{w['chunk'] // 1024} KiB chunks, one frame each, with XXH64 checksums")
-    return {"workload": what, "frames_per_gpu": w["n"], "libzstd_compressed_bytes_per_gpu": w["ref_compressed_bytes"],
+    extra = {}
+    if w.get("dictionary"):
+        what += f", compressed with a {len(w['dictionary'])}-byte trained dictionary (ZSTD_decompress_usingDict path)"
+        extra = {"dictionary_bytes": len(w["dictionary"]), "libzstd_ratio_without_dictionary": round(w["total"] / w["plain_compressed_bytes"], 4)}
+    return {**extra, "workload": what, "frames_per_gpu": w["n"], "libzstd_compressed_bytes_per_gpu": w["ref_compressed_bytes"],
             "libzstd_ratio": round(w["total"] / w["ref_compressed_bytes"], 4),
             "l2": "inputs+outputs per step exceed the 126 MB L2 (no flush needed)", "sharding": "by frame, no collective"}
 
@@ -458,6 +476,9 @@ def main():
     world = g.world
     w = prepare(args, g.rank)
     decode = w["kind"] == "decode64k"
+    if w.get("dictionary"):
+        g.ctx.load_dictionary(w["dictionary"])
+        args.no_cpu_baseline = True          # the all-core oracle arm has no dictionary entry point
     sampler = ClockSampler(g.local)
     m = measure(g, args, w, args.steps, args.warmup, sampler=sampler, extras=not args.no_extras)
     sampler.stop_flag = True      # clocks are sampled through both timed regions (device-resident and host-buffer)
@@ -471,7 +492,7 @@ def main():
 
     # ---------------- the other direction of BASELINE.json's metric (configs[2]): compression at levels 1-3 ----------------
     compress = None
-    if decode and args.corpus == "log" and not args.chunk and not args.no_extras:
+    if decode and args.corpus == "log" and not args.chunk and not args.no_extras and not args.dictionary:
         compress = {}
         for lvl in (1, 2, 3):
             wc = prepare(args, g.rank, workload="compress128k", level=lvl, raw=w["raw"])

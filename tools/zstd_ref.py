@@ -26,6 +26,8 @@ _Z.ZSTD_getFrameContentSize.restype = ctypes.c_uint64
 _Z.ZSTD_getFrameContentSize.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
 _Z.ZSTD_versionNumber.restype = ctypes.c_uint
 
+_Z.ZSTD_CCtx_loadDictionary.restype = ctypes.c_size_t
+_Z.ZSTD_CCtx_loadDictionary.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
 ZSTD_c_compressionLevel = 100
 ZSTD_c_windowLog = 101
 ZSTD_c_contentSizeFlag = 200
@@ -67,8 +69,8 @@ def decompress(frame, cap):
     return buf.raw[:n]
 
 
-def compress_chunks(raw, chunk, level=3, checksum=True, threads=8):
-    """Compress raw (np.uint8 array) as independent frames of `chunk` bytes.
+def compress_chunks(raw, chunk, level=3, checksum=True, threads=8, dictionary=None):
+    """Compress raw (np.uint8 array) as independent frames of `chunk` bytes (each with `dictionary` when given).
 
     Returns (blob np.uint8, offsets np.uint64[n+1]) with frame i = blob[offsets[i]:offsets[i+1]]."""
     raw = np.ascontiguousarray(raw, dtype=np.uint8)
@@ -81,6 +83,8 @@ def compress_chunks(raw, chunk, level=3, checksum=True, threads=8):
         c = _Z.ZSTD_createCCtx()
         _Z.ZSTD_CCtx_setParameter(c, ZSTD_c_compressionLevel, level)
         _Z.ZSTD_CCtx_setParameter(c, ZSTD_c_checksumFlag, 1 if checksum else 0)
+        if dictionary:
+            assert not _Z.ZSTD_isError(_Z.ZSTD_CCtx_loadDictionary(c, dictionary, len(dictionary)))   # sticks to the context
         for i in range(t, n, threads):
             lo = i * chunk
             ln = min(chunk, len(raw) - lo)

@@ -45,6 +45,7 @@ struct Device {
   int id = 0;
   cudaStream_t stream[NSTREAMS] = {};
   cudaEvent_t descEv = nullptr;                 // descriptors of the current sub-batch are on the device
+  std::vector<cudaEvent_t> sliceEv;             // "this slice's output is in the pinned staging" (grown on demand)
   // device memory
   u8 *d_src = nullptr, *d_dst = nullptr;       // staging for the host-pointer API
   // descriptors of one sub-batch of m items, packed so that they travel in ONE copy: [srcOff m x 8][dstOff m x 8][srcSize m x 4][dstCap m x 4]
@@ -117,6 +118,7 @@ void free_device(Device& d) {
   cudaFreeHost(d.h_src); cudaFreeHost(d.h_dst); cudaFreeHost(d.h_desc);
   for (auto& s : d.stream) if (s) cudaStreamDestroy(s);
   if (d.descEv) cudaEventDestroy(d.descEv);
+  for (auto& ev : d.sliceEv) cudaEventDestroy(ev);
 }
 
 struct Range { size_t lo, hi; };
@@ -282,6 +284,8 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     }
   }
   static const bool trace = getenv("ZSTDB200_TRACE") != nullptr;   // per-slice timeline on stderr (tuning aid)
+  const bool eager = !dstDirect && j.op == Op::Decompress && slices.size() > 1;
+  if (eager) while (d.sliceEv.size() < slices.size()) { cudaEvent_t ev; e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming); if (e) return fail("event create", e); d.sliceEv.push_back(ev); }
   std::vector<cudaEvent_t> tev;
   if (trace) { tev.resize(1 + 3 * slices.size()); for (auto& x : tev) cudaEventCreate(&x); cudaEventRecord(tev[0], d.stream[0]); }
   for (size_t s = 0; s < slices.size(); s++) {
@@ -317,7 +321,19 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
       e = cudaMemcpyAsync(hostDst, d.d_dst + outLo, outHi - outLo, cudaMemcpyDeviceToHost, st); if (e) return fail("D2H dst", e);
     }
     if (trace) cudaEventRecord(tev[3 + 3 * s], st);
+    if (eager) { e = cudaEventRecord(d.sliceEv[s], st); if (e) return fail("event", e); }
   }
+  // Pageable destinations of a decode: scatter every slice out of the pinned staging as soon as its copy has landed,
+  // while the later slices are still in flight (the whole capacity of each item is copied: the result codes only arrive
+  // at the end; bytes past result[i] are unspecified, include/zstdb200.h).
+  if (eager)
+    for (size_t s = 0; s < slices.size(); s++) {
+      e = cudaEventSynchronize(d.sliceEv[s]); if (e) return fail("event sync", e);
+      const size_t a = slices[s].lo, b = slices[s].hi;
+      parallel_for(b - a, d.h_dstOff[b - 1] + d.h_dstCap[b - 1] - d.h_dstOff[a], [&](size_t x, size_t y) {
+        for (size_t k = a + x; k < a + y; k++) if (d.h_dstCap[k]) memcpy(j.dst[lo + k], d.h_dst + d.h_dstOff[k], d.h_dstCap[k]);
+      });
+    }
   // a single slice ran on stream 0 alone: its results ride the same stream and one synchronisation ends the call
   if (slices.size() > 1) for (auto& st : d.stream) { e = cudaStreamSynchronize(st); if (e) return fail("stream sync", e); }
   if (trace) {
@@ -346,8 +362,9 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     e = cudaStreamSynchronize(st); if (e) return fail("stream sync", e);
   }
   for (size_t k = 0; k < m; k++) j.result[lo + k] = d.h_result[k];
-  // staged output: copy what was produced; on error the reference leaves dst partially written, we copy nothing
-  if (!dstDirect) parallel_for(m, d.h_dstOff[m - 1] + d.h_dstCap[m - 1], [&](size_t x, size_t y) {
+  // staged output not scattered yet (compress: frames are much smaller than their capacity; single-slice calls; items
+  // that needed further passes): copy what was produced; on error the reference leaves dst partially written, we copy nothing
+  if (!dstDirect && (!eager || anyMore)) parallel_for(m, d.h_dstOff[m - 1] + d.h_dstCap[m - 1], [&](size_t x, size_t y) {
     for (size_t k = x; k < y; k++) {
       const size_t i = lo + k; const u32 r = d.h_result[k];
       if (!is_err(r) && r) memcpy(j.dst[i], d.h_dst + d.h_dstOff[k], std::min<u32>(r, j.dstCap[i]));

@@ -221,9 +221,10 @@ struct HufEnc { HufCode code[256]; u8 weight[256]; u32 maxSym; u32 tableLog; };
 // hash-table logs of the warp-parallel match finder (k_enc_match and its lock-step emulation in tests/hostsim)
 // Table sizes of the match stage (log2 of u16 entries).  big: the launch holds chunks above one block (128 KiB): there a
 // table of 2^12 entries forgets a position after ~4 KiB of input and the ratio falls out of the 3 % band against
-// libzstd (tick records, 256 KiB: -3.7 %, 1 MiB: -4.1 %); 2^13 entries keep it inside (-2.0 % / -2.2 %) at about half the
-// resident warps.
-ZB_HD u32 enc_hlog_long(int level, bool big) { return big ? 13 : (level == 2 ? 13 : (level >= 3 ? 11 : 12)); }
+// libzstd (tick records, level 1 at 256 KiB: -3.7 %, level 3 at 1 MiB: -4.1 %).  Level 1 then takes 2^13 entries (-2.0 %),
+// level 3 a short table of 2^13 beside a long one of 2^12 (-0.7 % / -2.4 %; 24 KB, which still leaves 9 one-warp CTAs per
+// SM: a GiB of 1 MiB chunks is 1 024 chunks and must not need a second wave).
+ZB_HD u32 enc_hlog_long(int level, bool big) { return big ? (level >= 3 ? 12 : 13) : (level == 2 ? 13 : (level >= 3 ? 11 : 12)); }
 ZB_HD u32 enc_hlog_short(int /*level*/, bool big) { return big ? 13 : 12; }
 
 struct HufBuildScratch { u32 nodeCount[512]; u16 parent[512]; u16 order[256]; u8 depth[512]; };
