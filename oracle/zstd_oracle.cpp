@@ -23,9 +23,11 @@
 //    X2 or the double-symbol X4 by a static cost model
 //    (HufDecompress.cs:1082-1095) — both emit identical bytes and apply the
 //    same end-of-stream check.
-//  * The long-offset prefetching sequence loop (ZStdDecompress.cs:1620-1787),
-//    used only for windows > 16 MiB, is not restated; the regular loop
-//    (:1555-1608) gives the same bytes.
+//  * The long-offset sequence loop (ZStdDecompress.cs:1620-1787, taken for
+//    windows > 16 MiB whose offset table has >= 20/256 long-offset cells) is
+//    restated without its prefetches: same bytes as the regular loop, but it
+//    executes four sequences behind the decoder, which changes the result
+//    code of some damaged blocks — that ordering IS restated.
 //  * Wildcopy over-writes past a sequence's end (Mem.cs:55-61) are not
 //    reproduced: dst[0..ret) is identical, bytes beyond ret are untouched.
 
@@ -630,15 +632,17 @@ struct SeqState { BitReader bs; u32 sLL, sOF, sML; const SeqTable *tLL, *tOF, *t
 inline void initSeqFse(u32& st, BitReader& b, const SeqTable* t) { st = b.read(t->tableLog); b.reload(); }      // :1443-1452
 inline void updateSeqFse(u32& st, BitReader& b, const SeqTable* t) { const SeqCell& c = t->cell[st]; u32 low = b.read(c.nbBits); st = c.nextState + low; } // :1454-1460
 
-Seq decodeSequence(SeqState& s, bool longOffsets) {                    // :1473-1553 (MEM_32bits() == true)
+// longVariant: DecodeSequenceLong :1620-1706 — identical but for how an offset's bits are split around the reload when
+// the frame is in the long-offset regime: a fixed 24 (STREAM_ACCUMULATOR_MIN_32 - 1) first, whatever ofBits is (:1642-1647).
+Seq decodeSequence(SeqState& s, bool longOffsets, bool longVariant = false) {   // :1473-1553 (MEM_32bits() == true)
   Seq q;
   const SeqCell &cl = s.tLL->cell[s.sLL], &cm = s.tML->cell[s.sML], &co = s.tOF->cell[s.sOF];
   u32 llBits = cl.nbAdd, mlBits = cm.nbAdd, ofBits = co.nbAdd;
   u32 llBase = cl.base, mlBase = cm.base, ofBase = co.base;
   u32 offset;
   if (ofBits == 0) offset = 0;
-  else if (longOffsets && ofBits >= ACC_MIN_32) {
-    u32 extra = ofBits - std::min(ofBits, 32 - s.bs.consumed);
+  else if (longOffsets && (longVariant || ofBits >= ACC_MIN_32)) {
+    u32 extra = ofBits - std::min(ofBits, longVariant ? ACC_MIN_32 - 1 : 32 - s.bs.consumed);
     offset = ofBase + (s.bs.readFast(ofBits - extra) << extra);
     s.bs.reload();
     if (extra) offset += s.bs.readFast(extra);
@@ -715,6 +719,57 @@ u32 decompressSequences(DCtx& d, u8* frameBase, u64 opStart, u64 oend, const u8*
   return (u32)(op - opStart);
 }
 
+// ZSTD_decompressSequencesLong_body :1708-1787: the same sequences, decoded four ahead of their execution.  What that
+// changes for a caller is the result code of a damaged block: when the bitstream runs out after D sequences only the
+// first D - 4 have been executed (none when D < min(nbSeq, 4)), so an error one of the last four would have raised is
+// replaced by corruption_detected.
+u32 decompressSequencesLong(DCtx& d, u8* frameBase, u64 opStart, u64 oend, const u8* seqStart, u32 seqSize, int nbSeq, bool longOff) {
+  u64 op = opStart; const u8* lit = d.litPtr; const u8* litEnd = lit + d.litSize;
+  if (nbSeq) {
+    const int STORED = 4, MASK = STORED - 1, ADVANCED = 4;
+    Seq queue[STORED];
+    const int seqAdvance = std::min(nbSeq, ADVANCED);
+    SeqState s; d.fseEntropy = 1;
+    for (int i = 0; i < 3; i++) s.prev[i] = d.rep[i];
+    { u32 e = s.bs.init(seqStart, seqSize); if (is_err(e)) return ERR(E_corruption_detected); }
+    s.tLL = d.LL; s.tOF = d.OF; s.tML = d.ML;
+    initSeqFse(s.sLL, s.bs, d.LL); initSeqFse(s.sOF, s.bs, d.OF); initSeqFse(s.sML, s.bs, d.ML);
+    int seqNb = 0;
+    for (; (s.bs.reload() <= BS_completed) && seqNb < seqAdvance; seqNb++) {         // :1748-1752
+      queue[seqNb] = decodeSequence(s, longOff, true);
+      if (d.trace) { d.trace->seqs.push_back(queue[seqNb].ll); d.trace->seqs.push_back(queue[seqNb].ml); d.trace->seqs.push_back(queue[seqNb].off); }
+    }
+    if (seqNb < seqAdvance) return ERR(E_corruption_detected);
+    for (; (s.bs.reload() <= BS_completed) && seqNb < nbSeq; seqNb++) {              // :1755-1763
+      Seq q = decodeSequence(s, longOff, true);
+      if (d.trace) { d.trace->seqs.push_back(q.ll); d.trace->seqs.push_back(q.ml); d.trace->seqs.push_back(q.off); }
+      u32 one = execSequence(frameBase, op, oend, queue[(seqNb - ADVANCED) & MASK], lit, litEnd, d.dictContent, d.dictContentSize);
+      if (is_err(one)) return one;
+      queue[seqNb & MASK] = q;
+      op += one;
+    }
+    if (seqNb < nbSeq) return ERR(E_corruption_detected);
+    for (seqNb -= seqAdvance; seqNb < nbSeq; seqNb++) {                               // :1766-1772
+      u32 one = execSequence(frameBase, op, oend, queue[seqNb & MASK], lit, litEnd, d.dictContent, d.dictContentSize);
+      if (is_err(one)) return one;
+      op += one;
+    }
+    for (int i = 0; i < 3; i++) d.rep[i] = s.prev[i];
+    if (s.bs.overread) d.overread = true;
+  }
+  u64 last = (u64)(litEnd - lit);
+  if (last > oend - op) return ERR(E_dstSize_tooSmall);
+  memcpy(frameBase + op, lit, last); op += last;
+  return (u32)(op - opStart);
+}
+
+// GetLongOffsetsShare :1845-1865: cells of the offset table with more than 22 extra bits, scaled to a table of 2^OffFSELog
+u32 longOffsetsShare(const SeqTable* t) {
+  u32 total = 0;
+  for (u32 u = 0; u < (1u << t->tableLog); u++) total += t->cell[u].nbAdd > 22;
+  return total << (OffFSELog - t->tableLog);
+}
+
 // :1868-1909
 u32 decompressBlock(DCtx& d, u8* frameBase, u64 op, u64 oend, const u8* src, u32 srcSize) {
   bool longOff = d.windowSize > (1ull << ACC_MIN_32);
@@ -726,7 +781,10 @@ u32 decompressBlock(DCtx& d, u8* frameBase, u64 op, u64 oend, const u8* src, u32
   if (is_err(sh)) return sh;
   src += sh; srcSize -= sh;
   if (d.trace) { d.trace->lits.insert(d.trace->lits.end(), d.litPtr, d.litPtr + d.litSize); }
-  u32 r = decompressSequences(d, frameBase, op, oend, src, srcSize, nbSeq, longOff);
+  // :1898-1905 (MEM_64bits() == false: minShare 20)
+  const bool longVariant = d.windowSize > (1u << 24) && nbSeq > 0 && longOffsetsShare(d.OF) >= 20;
+  u32 r = longVariant ? decompressSequencesLong(d, frameBase, op, oend, src, srcSize, nbSeq, longOff)
+                      : decompressSequences(d, frameBase, op, oend, src, srcSize, nbSeq, longOff);
   if (d.trace) { d.trace->blockInfo.push_back(2); d.trace->blockInfo.push_back((u32)nbSeq); d.trace->blockInfo.push_back(d.litSize); d.trace->blockInfo.push_back(r); }
   return r;
 }

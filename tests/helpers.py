@@ -150,6 +150,25 @@ def mutate(rng, frame):
     return bytes(b)
 
 
+def large_window_frames(seed=5, count=60):
+    """libzstd frames whose header declares a window above 16 MiB (descriptors 0x71: 18 MiB, 0x78: 32 MiB, 0x80: 64 MiB,
+    0x8b: 88 MiB) over ordinary small contents — a declared window may always be larger than needed.  Above 16 MiB the
+    reference switches blocks whose offset table has enough long-offset cells (the predefined table does) to the
+    sequence loop that runs four sequences ahead (ZStdDecompress.cs:1898-1905); above 32 MiB offsets of 25+ bits
+    are read in two parts (:1494-1501 / :1642-1647)."""
+    from tools import zstd_ref
+    rng = random.Random(seed)
+    out = []
+    for t in range(count):
+        n = rng.choice([60, 200, 700, 1500, 4000, 20000, 70000])
+        data = sample_payload(rng, t % 6, n)
+        frame = bytearray(zstd_ref.compress(data, rng.choice(LEVELS), checksum=rng.random() < 0.5, content_size=False))
+        assert not (frame[4] & 0x20)                  # not single-segment: byte 5 is the window descriptor
+        frame[5] = rng.choice([0x71, 0x78, 0x80, 0x8b])
+        out.append((bytes(frame), data))
+    return out
+
+
 def skippable(payload, nibble=0):
     return (0x184D2A50 + nibble).to_bytes(4, "little") + len(payload).to_bytes(4, "little") + payload
 

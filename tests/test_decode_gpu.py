@@ -403,6 +403,31 @@ def test_long_offset_regime_window_above_32_mib(gpu_ctx, oracle):
             assert d[:want].tobytes() == out
 
 
+def test_large_window_frames_use_the_look_ahead_sequence_loop(gpu_ctx, oracle):
+    """Declared windows above 16 MiB: the reference runs blocks with enough long-offset cells through the loop that
+    executes four sequences behind the decoder (ZStdDecompress.cs:1898-1905, :1708-1787) — same bytes, but a damaged
+    block reports what THAT loop would have reached."""
+    rng = random.Random(32)
+    items = []
+    for frame, data in helpers.large_window_frames(seed=6, count=80):
+        items.append((frame, len(data)))
+        for _ in range(30):
+            b = bytearray(helpers.mutate(rng, frame))
+            if len(b) > 5:
+                b[:6] = frame[:6]
+            items.append((bytes(b), max(0, len(data) + rng.choice([0, 0, 5, -1, -7, -40, -len(data) // 3, 1000]))))
+    res, dsts = _gpu_decode(gpu_ctx, items)
+    n_err = 0
+    for (frame, cap), r, d in zip(items, res, dsts):
+        ro, oo, _ = oracle.decompress(frame, cap)
+        assert int(r) == ro, (frame.hex()[:80], cap, hex(ro), hex(int(r)))
+        if helpers.is_err(ro):
+            n_err += 1
+        else:
+            assert d[:ro].tobytes() == oo
+    assert n_err > 400
+
+
 def test_capacity_larger_than_the_context_arena():
     """The reference accepts any dstCapacity (ZStdDecompress.cs:2182-2191): a small frame decoded into a large reusable
     scratch buffer must not be refused because the buffer is larger than the context's max_batch_bytes; a frame that

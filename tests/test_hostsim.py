@@ -126,3 +126,25 @@ def test_maximum_match_length_records(hostsim, oracle):
         assert want == len(data) and out == data
         r, got = hostsim.decompress(frame, len(data), oracle)
         assert r == want and got == data
+
+
+def test_large_window_frames_use_the_look_ahead_sequence_loop(hostsim, oracle):
+    """Windows above 16 MiB: same bytes, and on damaged frames the result code of the loop that executes four
+    sequences behind the decoder (DecompressSequencesLong, ZStdDecompress.cs:1708-1787)."""
+    rng = random.Random(31)
+    n_long_fail = 0
+    for frame, data in helpers.large_window_frames():
+        ro, oo, _ = oracle.decompress(frame, len(data))
+        assert ro == len(data) and oo == data
+        rh, oh = hostsim.decompress(frame, len(data), oracle)
+        assert rh == ro and oh == oo
+        for _ in range(30):
+            b = bytearray(helpers.mutate(rng, frame))
+            if len(b) > 5:
+                b[:6] = frame[:6]                     # keep the header: the mutations are for the blocks
+            cap = max(0, len(data) + rng.choice([0, 0, 5, -1, -7, -40, -len(data) // 3, 1000]))
+            ro, oo, _ = oracle.decompress(bytes(b), cap)
+            rh, oh = hostsim.decompress(bytes(b), cap, oracle)
+            assert ro == rh and oo == oh, (bytes(b).hex()[:80], cap, hex(ro), hex(rh))
+            n_long_fail += helpers.is_err(ro)
+    assert n_long_fail > 300

@@ -74,6 +74,13 @@ struct zstdb200_ctx {
 
 namespace {
 
+// Events of the *_timed entry points; destroyed on every return path.
+template <int N> struct EventSet {
+  cudaEvent_t ev[N] = {};
+  ~EventSet() { for (auto e : ev) if (e) cudaEventDestroy(e); }
+  cudaError_t create() { for (auto& e : ev) { cudaError_t r = cudaEventCreate(&e); if (r != cudaSuccess) return r; } return cudaSuccess; }
+};
+
 #define CK(call)                                                                                   \
   do {                                                                                             \
     cudaError_t e_ = (call);                                                                       \
@@ -600,13 +607,12 @@ int zstdb200_decompress_batch_device_timed(zstdb200_ctx* ctx, int device_index, 
   Device& d = ctx->dev[device_index];
   CK(cudaSetDevice(d.id));
   cudaStream_t st = stream ? (cudaStream_t)stream : d.stream[0];
-  cudaEvent_t ev[DECODE_KERNELS + 1];
-  for (auto& e : ev) CK(cudaEventCreate(&e));
+  EventSet<DECODE_KERNELS + 1> es; CK(es.create());
+  cudaEvent_t* ev = es.ev;
   DecodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, 0, d.d_info, d.d_lit, d.d_seq, d.dictOn ? d.d_dictState : nullptr, d.d_dict, 0, nullptr};
   if (decode_device(ctx, d, a, st, ev)) return 1;
   CK(cudaStreamSynchronize(st));
   for (int k = 0; k < DECODE_KERNELS && k < max_kernels; k++) CK(cudaEventElapsedTime(&kernel_ms[k], ev[k], ev[k + 1]));
-  for (auto& e : ev) cudaEventDestroy(e);
   return 0;
 }
 const char* zstdb200_decode_kernel_name(int k) { return (k >= 0 && k < DECODE_KERNELS) ? kDecodeKernelNames[k] : ""; }
@@ -675,8 +681,8 @@ int zstdb200_compress_batch_device_timed(zstdb200_ctx* ctx, int device_index, in
   Device& d = ctx->dev[device_index];
   CK(cudaSetDevice(d.id));
   cudaStream_t st = stream ? (cudaStream_t)stream : d.stream[0];
-  cudaEvent_t ev[ENCODE_KERNELS + 1];
-  for (auto& e : ev) CK(cudaEventCreate(&e));
+  EventSet<ENCODE_KERNELS + 1> es; CK(es.create());
+  cudaEvent_t* ev = es.ev;
   u32 maxSrc = 0;
   if (device_max_u32(ctx, d, src_size, n, st, &maxSrc)) return 1;
   EncodeArgs a{(const u8*)src_base, src_off, src_size, (u8*)dst_base, dst_off, dst_cap, result, (u32)n, 0, level, checksum, maxSrc, ENC_EXCLUSIVE};
@@ -685,7 +691,6 @@ int zstdb200_compress_batch_device_timed(zstdb200_ctx* ctx, int device_index, in
   ctx->launches += nl;
   CK(cudaStreamSynchronize(st));
   for (int k = 0; k < ENCODE_KERNELS && k < max_kernels; k++) CK(cudaEventElapsedTime(&kernel_ms[k], ev[k], ev[k + 1]));
-  for (auto& e : ev) cudaEventDestroy(e);
   return 0;
 }
 const char* zstdb200_encode_kernel_name(int k) { return (k >= 0 && k < ENCODE_KERNELS) ? kEncodeKernelNames[k] : ""; }

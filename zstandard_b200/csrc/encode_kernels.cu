@@ -610,10 +610,13 @@ static cudaError_t encode_lazy_alloc(EncodeScratch& s) {
   if (s.lit) return cudaSuccess;
   const size_t B = s.maxBytes, N = s.maxItems + 2;
   cudaError_t e;
-  if ((e = cudaMalloc(&s.lit, B + 64 * N + 256)) != cudaSuccess) return e;
-  if ((e = cudaMalloc(&s.seq, (B / 4 + 64 * ((B >> 17) + 1) + 128 * N + 64) * 8)) != cudaSuccess) return e;
-  if ((e = cudaMalloc(&s.meta, ((B >> 17) + N + 8) * sizeof(BlockMeta))) != cudaSuccess) return e;
-  if ((e = cudaMalloc(&s.slots, (size_t)kPoolSlots * slot_bytes())) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&s.lit, B + 64 * N + 256)) != cudaSuccess ||
+      (e = cudaMalloc(&s.seq, (B / 4 + 64 * ((B >> 17) + 1) + 128 * N + 64) * 8)) != cudaSuccess ||
+      (e = cudaMalloc(&s.meta, ((B >> 17) + N + 8) * sizeof(BlockMeta))) != cudaSuccess ||
+      (e = cudaMalloc(&s.slots, (size_t)kPoolSlots * slot_bytes())) != cudaSuccess) {
+    encode_free(s);   // a later call retries from scratch instead of running on a half-built arena
+    return e;
+  }
   int dev = 0; cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&s.sms, cudaDevAttrMultiProcessorCount, dev);
   // as many entropy-stage warps as are resident at once: every warp then takes the same number of frames (+-1)

@@ -110,12 +110,13 @@ ZB_HD void refbits_reload(RefBits& b) {                                         
   refbits_load(b);
 }
 // value bits of one sequence in the reference's read order and reload schedule (DecodeSequence :1487-1545, MEM_32bits)
-ZB_HD void seq_values_ref32(const u8* s, u32 n, i32 P, bool longOffsets, u32 ofBits, u32 mlBits, u32 llBits, u32& ofv, u32& mlv, u32& llv) {
+// longVariant: the block runs DecodeSequenceLong (:1620-1706), which splits an offset at a fixed 24 bits (:1642-1647)
+ZB_HD void seq_values_ref32(const u8* s, u32 n, i32 P, bool longOffsets, bool longVariant, u32 ofBits, u32 mlBits, u32 llBits, u32& ofv, u32& mlv, u32& llv) {
   RefBits b; refbits_at(b, s, n, P);
   ofv = 0;
   if (ofBits) {
-    if (longOffsets && ofBits >= 25) {                                             // :1494-1501
-      const u32 room = 32 - b.bc, extra = ofBits - (ofBits < room ? ofBits : room);
+    if (longOffsets && (longVariant || ofBits >= 25)) {                            // :1494-1501
+      const u32 room = longVariant ? 24 : 32 - b.bc, extra = ofBits - (ofBits < room ? ofBits : room);
       ofv = refbits_read_fast(b, ofBits - extra) << (extra & 31);
       refbits_reload(b);
       if (extra) ofv += refbits_read_fast(b, extra);
@@ -170,14 +171,17 @@ struct SeqEmitter {
   }
   // true once the frame's first entropy-level error is recorded: the chain half stops (nothing it decodes is used)
   ZB_HD bool stopped() const { return dead; }
-  // decoded = sequences handed over, bad = the bitstream failed after them (:1577, :1582 -> corruption_detected)
-  ZB_HD void block_end(u32 blk, u32 decoded, bool bad) {
+  // bad = the bitstream failed (:1577, :1582 -> corruption_detected); runnable = how many of the block's sequences the
+  // reference has executed by then (all that were decoded in the regular loop, four fewer in the look-ahead loop)
+  ZB_HD void block_end(u32 blk, u32 runnable, bool bad) {
     if (dead) return;
     // header record: how many records the execute stage may run (those that fit the region)
     const bool overflow = n > cap;
-    if (hdrSlot < cap) rec_store(out + hdrSlot, (overflow ? cap : n) - hdrSlot - 1, dpos, lpos, 0);
+    u32 count = (overflow ? cap : n) - hdrSlot - 1;
+    if (bad && runnable < count) count = runnable;
+    if (hdrSlot < cap) rec_store(out + hdrSlot, count, dpos, lpos, 0);
     if (overflow) { res.err_block = blk; res.err_code = ZE_dstSize_tooSmall; res.err_index = 0; dead = true; }
-    else if (bad) { res.err_block = blk; res.err_code = ZE_corruption_detected; res.err_index = decoded; dead = true; }
+    else if (bad) { res.err_block = blk; res.err_code = ZE_corruption_detected; res.err_index = runnable; dead = true; }
   }
   // the block failed before its first sequence (count / table headers)
   ZB_HD void fail(u32 blk, u32 code) { if (dead) return; res.err_block = blk; res.err_code = code; res.err_index = 0xFFFFFFFFu; dead = true; }
@@ -236,6 +240,14 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, S
         }
         if (e) { sink.fail(blk, ZE_corruption_detected); return; }
         haveRepeat = true;                                                         // fseEntropy = 1 (:1575)
+        // Windows above 16 MiB whose offset table has >= 20/256 cells of more than 22 extra bits run the sequence loop
+        // that decodes four sequences ahead of their execution (:1898-1905, GetLongOffsetsShare :1845-1865)
+        bool longVariant = false;
+        if (window > (1u << 24)) {
+          const u32 lg = T.log[KIND_OF]; u32 total = 0;
+          for (u32 u = 0; u < (1u << lg); u++) total += (T.cur[KIND_OF][u * T.curStride[KIND_OF]] >> 10) > 22;
+          longVariant = (total << (8 - lg)) >= 20;
+        }
         // ---- bitstream ----
         BitCursor c;
         sink.block_begin();
@@ -291,7 +303,7 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, S
             u32 mlv = top_bits(w, mlBits); w <<= mlBits;
             u32 llv = top_bits(w, llBits); w <<= llBits;
             const i32 Pv = P - (i32)valBits;
-            if (Pv < 0) seq_values_ref32(sp + hdr, ssz - hdr, P, window > (1ull << 25), ofBits, mlBits, llBits, ofv, mlv, llv);   // over-read: the reference's container garbage
+            if (Pv < 0) seq_values_ref32(sp + hdr, ssz - hdr, P, window > (1ull << 25), longVariant, ofBits, mlBits, llBits, ofv, mlv, llv);   // over-read: the reference's container garbage
             else if (valBits + stBits > 64) w = bc_window64(c, Pv);                // rare: more than 64 bits in one sequence
             sink.values(ofv, mlv, llv, llSym, mlSym, ofBits);
             decoded++;
@@ -302,6 +314,8 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, S
             P = Pv - (i32)stBits;
           }
         }
+        // the look-ahead loop has executed all but the last four sequences when the stream runs out (:1748-1764)
+        if (bad && longVariant) decoded = decoded > 4 ? decoded - 4 : 0;
         sink.block_end(blk, decoded, bad);
         if (bad || sink.stopped()) return;
       }
