@@ -65,7 +65,7 @@ class HostSim:
         d = os.path.join(ROOT, "tests", "hostsim")
         path = os.path.join(d, "_build", "libhostsim.so")
         deps = [os.path.join(d, "hostsim.cpp")] + [os.path.join(ROOT, "zstandard_b200", "csrc", f)
-                                                  for f in ("zb_common.cuh", "zb_format.cuh", "zb_decode.cuh", "zb_encode.cuh")] + [os.path.join(d, "serial_encoder.h")]
+                                                  for f in ("zb_common.cuh", "zb_format.cuh", "zb_decode.cuh", "zb_blocks.cuh", "zb_encode.cuh")] + [os.path.join(d, "serial_encoder.h")]
         if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(p) for p in deps):
             os.makedirs(os.path.dirname(path), exist_ok=True)
             subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-static-libstdc++", "-static-libgcc",
@@ -78,7 +78,16 @@ class HostSim:
         h.hostsim_decompress2.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint32,
                                           ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_int),
                                           ctypes.POINTER(ctypes.c_uint32), ctypes.c_void_p]
+        h.hostsim_set_par.argtypes = [ctypes.c_int]
+        h.hostsim_par_frames.restype = ctypes.c_int
         self.lib = h
+
+    def set_par(self, on):
+        """0: every frame on the frame-serial replay; 1 (default): sound multi-block frames take the block-parallel one."""
+        self.lib.hostsim_set_par(int(on))
+
+    def par_frames(self):
+        return self.lib.hostsim_par_frames()
 
     def decompress(self, frame, cap, oracle):
         """One item through the replayed stages, one pass per data frame; the oracle's XXH64 stands in for k_xxh."""

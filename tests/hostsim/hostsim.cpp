@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <vector>
 #include "../../zstandard_b200/csrc/zb_decode.cuh"
+#include "../../zstandard_b200/csrc/zb_blocks.cuh"
 #include "../../zstandard_b200/csrc/zb_encode.cuh"
 #include "serial_encoder.h"
 
@@ -175,6 +176,137 @@ u32 sim_exec(const u8* src, u32 size, const FrameInfo& fi, u8* dst, u64 cap, con
   return err ? zerr(err) : (tailErr ? zerr(tailErr) : fi.out_base + (u32)op);
 }
 
+// ---- block-parallel path (zb_blocks.cuh): k_huf_blk / k_seq_blk / k_exec_big, one unit at a time ----
+static int g_par = 1;            // hostsim_set_par: 0 = every frame on the frame-serial replay
+static int g_parFrames = 0;      // data frames that took the block-parallel replay (hostsim_par_frames)
+
+// mirrors k_huf_blk for one unit
+void sim_huf_unit(const u8* src, BlockUnit& u, const BlockUnit* frameUnits, u8* litRegion) {
+  alignas(16) static thread_local u16 dt[1 << HUF_TABLE_LOG]; static thread_local HufBuildWk wk; alignas(16) u32 ringBuf[ZB_RING_WORDS];
+  static thread_local u8 sideMem[256], slotMem[256]; const u8* side = nullptr;
+  const u8* bp = src + u.body;
+  LitHdr lh; bool needs;
+  read_lit_hdr(bp, u.csize, lh, &needs);
+  if (lh.type < 2) return;
+  u8* lit = litRegion + u.lit_off;
+  bool ok = true; u32 tableLog = 0;
+  const u8* body = bp + lh.lhSize; u32 bodySize = lh.litCSize;
+  if (lh.type == 3 && u.huf_def == DEF_DICT) {
+    const DictState* ds = cur_dict();
+    memcpy(dt, ds->huf, sizeof(ds->huf)); tableLog = ds->hufLog;
+    if (tableLog > HUF_TABLE_LOG) { memcpy(sideMem, ds->hufSide, 256); side = sideMem; }
+  } else {
+    const u8* tb = body; u32 tbSize = bodySize;
+    if (lh.type == 3) {
+      const BlockUnit& d = frameUnits[u.huf_def];
+      LitHdr lhD; bool n2;
+      read_lit_hdr(src + d.body, d.csize, lhD, &n2);
+      tb = src + d.body + lhD.lhSize; tbSize = lhD.litCSize;
+    } else if (!lh.single && (lh.litSize == 0 || bodySize == 0)) ok = false;
+    u32 hdr = 0, nbSym = 0, tl = 0;
+    if (ok) {
+      u32 e = huf_read_weights(tb, tbSize, wk, *reinterpret_cast<HufFseScratch*>(dt), slotMem, &hdr, &tl, &nbSym);
+      if (!e && hdr >= tbSize) e = ZE_srcSize_wrong;
+      if (e) ok = false;
+    }
+    if (ok) {
+      for (u32 sub = 0; sub < 4; sub++) huf_fill_table(dt, sideMem, wk, slotMem, tl, nbSym, sub, 4);
+      tableLog = tl; side = tl > HUF_TABLE_LOG ? sideMem : nullptr;
+      if (lh.type == 2) { body += hdr; bodySize -= hdr; }
+    }
+  }
+  if (ok) {
+    if (lh.single) ok = huf_decode_stream(body, bodySize, lit, lh.litSize, dt, tableLog, ringBuf, side);
+    else for (u32 sub = 0; sub < 4; sub++) {
+      HufStream st; bool good = huf_split4(body, bodySize, lh.litSize, sub, st);
+      if (good) good = huf_decode_stream(st.src, st.len, lit + st.outOfs, st.count, dt, tableLog, ringBuf, side);
+      if (!good) ok = false;
+    }
+  }
+  if (!ok) u.huf_err = ZE_corruption_detected;
+}
+
+// serial stand-in for k_exec_big: the same checks in block order, symbolic offsets resolved against the running history
+u32 sim_exec_par(const u8* src, u32 size, const FrameInfo& fi, const BlockUnit* units, u8* dst, u64 cap, const u8* litScratch, const SeqRec* recs, bool* needXxh, u32* trailerOff, u32* nextOff, u32* decoded) {
+  u32 pos = fi.body_off, cblk = 0; u64 op = 0; u32 err = 0;
+  const DictState* ds = cur_dict();
+  const u32 dictContent = ds ? ds->contentSize : 0;
+  const u8* const dictEnd = ds ? g_dictBytes.data() + ds->contentOff + dictContent : nullptr;
+  u32 R[3] = {1, 4, 8};
+  if (ds) { R[0] = ds->rep[0]; R[1] = ds->rep[1]; R[2] = ds->rep[2]; }
+  while (true) {
+    BlockHdr bh;
+    err = read_block_hdr(src + pos, size - pos, bh);
+    if (err) break;
+    pos += 3;
+    if (bh.type == 0) { if (bh.csize > cap - op) { err = ZE_dstSize_tooSmall; break; } memcpy(dst + op, src + pos, bh.csize); op += bh.csize; }
+    else if (bh.type == 1) { if (bh.orig > cap - op) { err = ZE_dstSize_tooSmall; break; } memset(dst + op, src[pos], bh.orig); op += bh.orig; }
+    else {
+      const BlockUnit& bu = units[cblk++];
+      if (bu.body != pos || bu.csize != bh.csize) { fprintf(stderr, "hostsim: unit / block mismatch\n"); abort(); }
+      const u8* bp = src + pos; const u32 bsz = bh.csize;
+      LitHdr lh; bool needs;
+      read_lit_hdr(bp, bsz, lh, &needs);
+      const u8* lit = nullptr; u32 rleByte = 0; bool isRle = false;
+      if (lh.type >= 2) { if (bu.huf_err) { err = bu.huf_err; break; } lit = litScratch + bu.lit_off; }
+      else if (lh.type == 0) lit = bp + lh.lhSize;
+      else { isRle = true; rleByte = bp[lh.lhSize]; }
+      const u32 litSize = lh.litSize;
+      const u8* sp = bp + lh.consumed; const u32 ssz = bsz - lh.consumed;
+      u32 nbSeq, modes, hdr;
+      read_seq_count(sp, ssz, &nbSeq, &modes, &hdr);
+      if (bu.seq_err_code && bu.seq_err_index == 0xFFFFFFFFu) { err = bu.seq_err_code; break; }
+      u64 litPos = 0;
+      if (nbSeq) {
+        const u32 nRecs = recs[bu.rec_off].x;
+        const SeqRec* r = recs + bu.rec_off + 1;
+        const u64 blockBase = op;
+        for (u32 k = 0; k < nRecs; k++, r++) {
+          const u32 ll = rec_ll(*r), ml = rec_ml(*r), off = repsym_resolve(r->z, rec_tag(*r), R);
+          const u64 start = blockBase + r->x;
+          if (start != op && start <= cap) { fprintf(stderr, "hostsim: record position %llu != %llu\n", (unsigned long long)start, (unsigned long long)op); abort(); }
+          if (start + ll + ml > cap) { err = ZE_dstSize_tooSmall; break; }
+          if ((u64)rec_lpos(*r) + ll > litSize) { err = ZE_corruption_detected; break; }
+          if ((u64)off > start + ll + dictContent) { err = ZE_corruption_detected; break; }
+          for (u32 i = 0; i < ll; i++) dst[op + i] = isRle ? (u8)rleByte : lit[litPos + i];
+          op += ll; litPos += ll;
+          for (u32 i = 0; i < ml; i++) dst[op + i] = (u64)off > op + i ? dictEnd[(i64)(op + i) - (i64)off] : dst[op + i - off];
+          op += ml;
+        }
+        if (err) break;
+        if (bu.seq_err_code) { err = bu.seq_err_code; break; }
+        op = blockBase + recs[bu.rec_off].y; litPos = recs[bu.rec_off].z;
+        const u32 n0 = repsym_resolve(bu.rep[0], bu.rep_sym & 7, R), n1 = repsym_resolve(bu.rep[1], (bu.rep_sym >> 3) & 7, R), n2 = repsym_resolve(bu.rep[2], (bu.rep_sym >> 6) & 7, R);
+        R[0] = n0; R[1] = n1; R[2] = n2;
+      }
+      u64 lastLL = litSize - litPos;
+      if (lastLL > cap - op) { err = ZE_dstSize_tooSmall; break; }
+      for (u64 i = 0; i < lastLL; i++) dst[op + i] = isRle ? (u8)rleByte : lit[litPos + i];
+      op += lastLL;
+    }
+    pos += bh.csize;
+    if (bh.last) break;
+  }
+  *needXxh = false; *trailerOff = 0;
+  if (!err) {
+    if ((fi.flags & FI_FCS_KNOWN) && op != fi.fcs) err = ZE_corruption_detected;
+    else if (fi.flags & FI_CHECKSUM) { if (size - pos < 4) err = ZE_checksum_wrong; else { *trailerOff = pos; pos += 4; *needXxh = true; } }
+  }
+  u32 tailErr = 0; *decoded = (u32)op;
+  if (!err) while (true) {
+    u32 rem = size - pos;
+    if (rem < 5) { if (rem) tailErr = ZE_srcSize_wrong; break; }
+    u32 magic = ld32(src + pos);
+    if (magic == MAGIC) { *nextOff = pos; break; }
+    if ((magic & 0xFFFFFFF0u) != MAGIC_SKIP) { tailErr = ZE_prefix_unknown; break; }
+    if (rem < 8) { tailErr = ZE_srcSize_wrong; break; }
+    u32 skip = ld32(src + pos + 4) + 8u;
+    if (rem < skip) { tailErr = ZE_srcSize_wrong; break; }
+    pos += skip;
+  }
+  return err ? zerr(err) : (tailErr ? zerr(tailErr) : fi.out_base + (u32)op);
+}
+
 }  // namespace
 
 // One pass per data frame of the item, as the host loop around the kernels does (api.cu, decode_more_passes).
@@ -195,19 +327,36 @@ extern "C" uint32_t hostsim_decompress2(uint8_t* dst_in, uint32_t capAll, const 
     const u32 cap = capAll - fi.out_base; u8* dst = dst_in ? dst_in + fi.out_base : dummy;
     std::vector<u8> lit((size_t)cap + 64);
     std::vector<SeqRec> recs(seq_capacity(cap) + 40);
-    sim_huf(src, size, fi, lit.data(), (u64)cap + 40);
     static thread_local Sim* sim = nullptr; if (!sim) sim = new Sim();
     SeqTableSet T;
     T.space[KIND_LL] = sim->ll.data(); T.space[KIND_ML] = sim->ml.data(); T.space[KIND_OF] = sim->of.data(); T.stride = 1;
     T.defs[KIND_LL] = sim->defLL; T.defs[KIND_OF] = sim->defOF; T.defs[KIND_ML] = sim->defML;
     s16 normBuf[53]; u16 nextBuf[53]; alignas(16) u32 ringBuf[ZB_RING_WORDS];
+    bool nx; u32 tr, nextOff = 0, produced = 0;
+    // k_parse's decision: structurally sound multi-block frames become units (zb_blocks.cuh)
+    const u32 maxU = cap / PAR_UNIT_BYTES + PAR_UNIT_SLACK;
+    const u32 nu = g_par ? par_walk(src, size, fi.body_off, (u64)cap + 40, seq_capacity(cap), cur_dict(), maxU, nullptr, 0) : 0;
+    if (nu) {
+      g_parFrames++;
+      std::vector<BlockUnit> units(nu);
+      par_walk(src, size, fi.body_off, (u64)cap + 40, seq_capacity(cap), cur_dict(), maxU, units.data(), 0);
+      for (u32 w = 0; w < nu; w++) sim_huf_unit(src, units[w], units.data(), lit.data());
+      for (u32 w = 0; w < nu; w++) {
+        UnitEmitter em; em.init(recs.data() + units[w].rec_off, sim->llInfo, sim->mlInfo);
+        seq_decode_unit(src, units[w], units.data(), fi.window, T, em, sim->llInfo, sim->mlInfo, normBuf, nextBuf, ringBuf, cur_dict());
+        if (em.dead) { units[w].seq_err_code = em.err_code; units[w].seq_err_index = em.err_index; }
+        else if (em.n) { units[w].rep[0] = em.h.v0; units[w].rep[1] = em.h.v1; units[w].rep[2] = em.h.v2; units[w].rep_sym = em.h.t0 | (em.h.t1 << 3) | (em.h.t2 << 6); }
+      }
+      out = sim_exec_par(src, size, fi, units.data(), dst, cap, lit.data(), recs.data(), &nx, &tr, &nextOff, &produced);
+    } else {
+    sim_huf(src, size, fi, lit.data(), (u64)cap + 40);
     SeqEmitter em; em.init(recs.data(), seq_capacity(cap), sim->llInfo, sim->mlInfo);      // the finishing half, plugged in directly
     if (cur_dict()) em.set_reps(cur_dict()->rep);
     seq_decode_frame(src, size, fi.body_off, fi.window, T, em, sim->llInfo, sim->mlInfo, normBuf, nextBuf, ringBuf, cur_dict());
     const SeqFrameOut res = em.res;
     if (res.err_block != 0xFFFFFFFFu) { fi.seq_err_block = res.err_block; fi.seq_err_code = res.err_code; fi.seq_err_index = res.err_index; }
-    bool nx; u32 tr, nextOff = 0, produced = 0;
     out = sim_exec(src, size, fi, dst, cap, lit.data(), recs.data(), &nx, &tr, &nextOff, &produced);
+    }
     *need_xxh = nx; *trailer_off = tr; *last_base = fi.out_base;
     // k_xxh runs whenever the frame itself decoded (even if what follows it in the item is malformed) and overrides the result
     if (nx && xxh && dst_in && (u32)xxh(dst, produced, 0) != ld32(src + tr)) return zerr(ZE_checksum_wrong);
@@ -215,6 +364,8 @@ extern "C" uint32_t hostsim_decompress2(uint8_t* dst_in, uint32_t capAll, const 
     start = nextOff; outBase = out;
   }
 }
+extern "C" void hostsim_set_par(int on) { g_par = on; }
+extern "C" int hostsim_par_frames() { return g_parFrames; }
 extern "C" uint32_t hostsim_decompress(uint8_t* dst, uint32_t cap, const uint8_t* src_in, uint32_t size, uint32_t* trailer_off, int* need_xxh) {
   uint32_t lastBase;
   return hostsim_decompress2(dst, cap, src_in, size, trailer_off, need_xxh, &lastBase, nullptr);

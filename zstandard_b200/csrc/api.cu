@@ -54,6 +54,7 @@ struct Device {
   u32 *d_result = nullptr;
   FrameInfo* d_info = nullptr; u8* d_lit = nullptr; SeqRec* d_seq = nullptr;
   u32* d_more = nullptr;                        // per-stream counters of items with another data frame to decode (DecodeArgs::more)
+  BlockUnit* d_units = nullptr; u32* d_parList = nullptr; u32* d_cnt = nullptr;   // block-parallel path of multi-block frames (DecodeArgs::units / par_list / cnt, 2 counters per stream)
   u8* d_dict = nullptr; size_t dictCap = 0; DictState* d_dictState = nullptr; bool dictOn = false;   // zstdb200_load_dictionary
   EncodeScratch enc;                            // encoder arenas (encode_kernels.cuh)
   // pinned host memory
@@ -107,6 +108,9 @@ int alloc_device(zstdb200_ctx* ctx, Device& d) {
   CK(cudaMalloc(&d.d_info, items * sizeof(FrameInfo)));
   CK(cudaMalloc(&d.d_lit, decode_lit_arena_bytes(ctx->dstSpan, items)));
   CK(cudaMalloc(&d.d_seq, decode_seq_arena_bytes(ctx->dstSpan, items)));
+  CK(cudaMalloc(&d.d_units, decode_unit_arena_count(ctx->dstSpan, items) * sizeof(BlockUnit)));
+  CK(cudaMalloc(&d.d_parList, (items + 1) * 4));
+  CK(cudaMalloc(&d.d_cnt, NSTREAMS * 2 * 4));
   CK(cudaMallocHost(&d.h_src, ctx->srcCap + 256)); CK(cudaMallocHost(&d.h_dst, ctx->srcCap + 256));
   CK(cudaMallocHost(&d.h_desc, items * 24 + 64));
   CK(decode_configure());
@@ -120,6 +124,7 @@ void free_device(Device& d) {
   for (auto& s : d.stream) if (s) cudaStreamSynchronize(s);
   cudaFree(d.d_src); cudaFree(d.d_dst); cudaFree(d.d_desc);
   cudaFree(d.d_info); cudaFree(d.d_lit); cudaFree(d.d_seq); cudaFree(d.d_more); cudaFreeHost(d.h_more);
+  cudaFree(d.d_units); cudaFree(d.d_parList); cudaFree(d.d_cnt);
   cudaFree(d.d_dict); cudaFree(d.d_dictState);
   encode_free(d.enc);
   cudaFreeHost(d.h_src); cudaFreeHost(d.h_dst); cudaFreeHost(d.h_desc);
@@ -192,6 +197,14 @@ std::vector<Range> make_subbatches(size_t n, size_t maxIn, size_t maxOut, size_t
 }
 
 enum class Op { Decompress, Compress };
+
+// Switches a launch to the block-parallel path for multi-block frames (zb_blocks.cuh); ZSTDB200_PAR=0 keeps every frame
+// on the frame-serial kernels (A/B measurements).  slot: the stream slot the launch runs on (its pair of counters).
+void with_units(Device& d, DecodeArgs& a, u32 slot) {
+  static const bool on = env_int("ZSTDB200_PAR", 1, 0, 1) != 0;
+  if (!on) return;
+  a.units = d.d_units; a.par_list = d.d_parList; a.cnt = d.d_cnt + 2 * slot;
+}
 
 // Items that hold more than one data frame (DecompressMultiFrame, ZStdDecompress.cs:2096-2160): after the first pass
 // the execute stage has counted them in *more; every further pass decodes the next data frame of each of them.
@@ -313,6 +326,7 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     if (j.op == Op::Decompress) {
       DecodeArgs ar{d.d_src, d_srcOff + a, d_srcSize + a, d.d_dst, d_dstOff + a, d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
                     d.d_info + a, d.d_lit, d.d_seq, d.dictOn ? d.d_dictState : nullptr, d.d_dict, 0, d.d_more + (s % nStreams)};
+      with_units(d, ar, (u32)(s % nStreams));
       e = decode_launch(ar, st, &nl);
     } else {
       EncodeArgs ar{d.d_src, d_srcOff + a, d_srcSize + a, d.d_dst, d_dstOff + a, d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
@@ -361,6 +375,7 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     // pass by pass over the whole sub-batch, then fetch results and output again.
     cudaStream_t st = d.stream[0]; int nl = 0;
     DecodeArgs ar{d.d_src, d_srcOff, d_srcSize, d.d_dst, d_dstOff, d_dstCap, d.d_result, (u32)m, 0, d.d_info, d.d_lit, d.d_seq, d.dictOn ? d.d_dictState : nullptr, d.d_dict, 0, nullptr};
+    with_units(d, ar, 0);
     e = decode_more_passes(d, ar, 0, st, &nl); *launches += nl;
     if (e) return fail("multi-frame passes", e);
     e = cudaMemcpyAsync(d.h_result, d.d_result, m * 4, cudaMemcpyDeviceToHost, st); if (e) return fail("D2H result", e);
@@ -573,6 +588,7 @@ uint32_t zstdb200_decompress(zstdb200_ctx* ctx, void* dst, uint32_t dstCapacity,
 static int decode_device(zstdb200_ctx* ctx, Device& d, const DecodeArgs& a, cudaStream_t user, cudaEvent_t* marks) {
   int nl = 0;
   DecodeArgs b = a; b.pass = 0; b.more = d.d_more;
+  with_units(d, b, 0);
   CK(cudaMemsetAsync(b.more, 0, 4, user));
   CK(decode_launch(b, user, &nl, marks));
   CK(cudaMemcpyAsync(d.h_more, b.more, 4, cudaMemcpyDeviceToHost, user));

@@ -27,6 +27,10 @@ __device__ __forceinline__ u8* lit_region(const DecodeArgs& a, u32 f, const Fram
 __device__ __forceinline__ u64 lit_capacity(u32 cap) { return (u64)cap + 40; }
 __device__ __forceinline__ SeqRec* seq_region(const DecodeArgs& a, u32 f, const FrameInfo& fi) { return a.seq_arena + 2 * (frame_dst_off(a, f, fi) / 3) + 32ull * (a.item_base + f); }
 
+// first unit of this launch's range of the unit arena: a frame may list cap / PAR_UNIT_BYTES + PAR_UNIT_SLACK units, so the
+// ranges of the slices that share the arena follow from dst_off / item_base like the other scratch regions and cannot meet
+__device__ __forceinline__ u64 unit_slice_base(const DecodeArgs& a) { return a.dst_off[0] / PAR_UNIT_BYTES + (u64)PAR_UNIT_SLACK * a.item_base; }
+
 // =================================================================================================
 // k_parse
 // =================================================================================================
@@ -40,7 +44,19 @@ __global__ void __launch_bounds__(128) k_parse(DecodeArgs a) {
     if ((prev.flags & FI_DONE) || prev.next_off == 0 || is_err(a.result[i])) { a.info[i].flags = FI_DONE; return; }
     start = prev.next_off; outBase = prev.out_base + prev.decoded;
   }
-  bool go = parse_item(a.src_base + a.src_off[i], a.src_size[i], fi, &r, start, outBase, a.dict ? a.dict->err : 0, a.dict ? a.dict->dictID : 0);
+  const u8* src = a.src_base + a.src_off[i];
+  bool go = parse_item(src, a.src_size[i], fi, &r, start, outBase, a.dict ? a.dict->err : 0, a.dict ? a.dict->dictID : 0);
+  if (go && a.units) {
+    // multi-block frames whose structure is sound become BlockUnits (zb_blocks.cuh): count, reserve, fill
+    const u32 cap = a.dst_cap[i] - fi.out_base, maxU = cap / PAR_UNIT_BYTES + PAR_UNIT_SLACK;
+    const u32 nu = par_walk(src, a.src_size[i], fi.body_off, lit_capacity(cap), seq_capacity(cap), a.dict, maxU, nullptr, i);
+    if (nu) {
+      const u32 base = atomicAdd(a.cnt, nu);
+      par_walk(src, a.src_size[i], fi.body_off, lit_capacity(cap), seq_capacity(cap), a.dict, maxU, a.units + unit_slice_base(a) + base, i);
+      fi.flags |= FI_PAR; fi.unit_base = base; fi.unit_count = nu;
+      a.par_list[a.item_base + atomicAdd(a.cnt + 1, 1u)] = i;
+    }
+  }
   a.info[i] = fi;
   if (!go) a.result[i] = r;
 }
@@ -65,7 +81,7 @@ __global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
   const unsigned gmask = 0xFu << (slot * 4);
   bool active = f < a.n;
   FrameInfo fi;
-  if (active) { fi = a.info[f]; if (fi.flags & FI_DONE) active = false; }
+  if (active) { fi = a.info[f]; if (fi.flags & (FI_DONE | FI_PAR)) active = false; }
   if (!active) return;   // whole 4-lane group leaves together; group syncs below use gmask
   const u8* src = a.src_base + a.src_off[f]; const u32 size = a.src_size[f];
   u8* lit = lit_region(a, f, fi); const u64 litCap = lit_capacity(frame_cap(a, f, fi));
@@ -179,7 +195,7 @@ __global__ void __launch_bounds__(32) k_seq(DecodeArgs a) {
   const u32 f = blockIdx.x * 32 + lane;
   if (f >= a.n) return;
   FrameInfo fi = a.info[f];
-  if (fi.flags & FI_DONE) return;
+  if (fi.flags & (FI_DONE | FI_PAR)) return;
   SeqTableSet T;
   T.space[KIND_LL] = &sm.ll[0][lane]; T.space[KIND_ML] = &sm.ml[0][lane]; T.space[KIND_OF] = &sm.of[0][lane]; T.stride = 32;
   T.defs[KIND_LL] = sm.defLL; T.defs[KIND_OF] = sm.defOF; T.defs[KIND_ML] = sm.defML;
@@ -392,7 +408,7 @@ __global__ void __launch_bounds__(EXEC_THREADS, 16) k_exec(DecodeArgs a) {
   const u32 f = (blockIdx.x * EXEC_THREADS + threadIdx.x) >> 5;
   if (f >= a.n) return;
   FrameInfo fi = a.info[f];
-  if (fi.flags & FI_DONE) return;
+  if (fi.flags & (FI_DONE | FI_PAR)) return;
   const u8* src = a.src_base + a.src_off[f]; const u32 size = a.src_size[f];
   u8* dst = a.dst_base + frame_dst_off(a, f, fi); const u32 cap = frame_cap(a, f, fi);
   const u8* litScratch = lit_region(a, f, fi);
@@ -576,6 +592,380 @@ __global__ void __launch_bounds__(EXEC_THREADS, 16) k_exec(DecodeArgs a) {
 }
 
 // =================================================================================================
+// Block-parallel path for multi-block frames (zb_blocks.cuh): every compressed block of an FI_PAR frame is a unit
+// =================================================================================================
+// k_huf_blk : k_huf's mapping (4 lanes per unit, 8 units per warp), persistent over the launch's units
+__global__ void __launch_bounds__(32) k_huf_blk(DecodeArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  HufSmem& sm = *reinterpret_cast<HufSmem*>(smem_raw);
+  const u32 lane = threadIdx.x, sub = lane & 3, slot = lane >> 2;
+  const unsigned gmask = 0xFu << (slot * 4);
+  const u32 nunits = a.cnt[0];
+  BlockUnit* const sliceUnits = a.units + unit_slice_base(a);
+  u16* dt = sm.table[slot]; HufBuildWk& wk = sm.wk[slot];
+  u8* const sideMem = (u8*)&sm.ring[slot * 4][0];
+  u8* const slotMem = (u8*)&sm.ring[slot * 4 + 1][0];
+  for (u32 w0 = blockIdx.x * 8; w0 < nunits; w0 += gridDim.x * 8) {
+    const u32 w = w0 + slot;
+    if (w >= nunits) continue;                                                     // the whole 4-lane group together
+    const BlockUnit u = sliceUnits[w];
+    const u32 f = u.frame;
+    const FrameInfo fi = a.info[f];
+    const u8* src = a.src_base + a.src_off[f];
+    const u8* bp = src + u.body;
+    LitHdr lh; bool needs;
+    read_lit_hdr(bp, u.csize, lh, &needs);                                         // sound: par_walk has parsed it
+    if (lh.type < 2) continue;
+    u8* lit = lit_region(a, f, fi) + u.lit_off;
+    bool ok = true; u32 tableLog = 0; const u8* side = nullptr;
+    const u8* body = bp + lh.lhSize; u32 bodySize = lh.litCSize;
+    __syncwarp(gmask);                                                             // the group's previous unit is done with dt / rings
+    if (lh.type == 3 && u.huf_def == DEF_DICT) {
+      const uint4* s4 = reinterpret_cast<const uint4*>(a.dict->huf); uint4* d4 = reinterpret_cast<uint4*>(dt);
+      for (u32 i = sub; i < (sizeof(u16) << HUF_TABLE_LOG) / 16; i += 4) d4[i] = s4[i];
+      tableLog = a.dict->hufLog;
+      if (tableLog > HUF_TABLE_LOG) { for (u32 i = sub; i < 256; i += 4) sideMem[i] = a.dict->hufSide[i]; side = sideMem; }
+      __syncwarp(gmask);
+    } else {
+      // the weights: this block's own (type 2) or those of the block that defined the table in force (treeless)
+      const u8* tb = body; u32 tbSize = bodySize;
+      if (lh.type == 3) {
+        const BlockUnit d = sliceUnits[fi.unit_base + u.huf_def];
+        LitHdr lhD; bool n2;
+        read_lit_hdr(src + d.body, d.csize, lhD, &n2);
+        tb = src + d.body + lhD.lhSize; tbSize = lhD.litCSize;
+      } else if (!lh.single && (lh.litSize == 0 || bodySize == 0)) ok = false;     // HufDecompress.cs:1211-1212
+      u32 hdr = 0, nbSym = 0, tl = 0;
+      if (ok) {
+        u32 e = 0;
+        if (sub == 0) {
+          e = huf_read_weights(tb, tbSize, wk, *reinterpret_cast<HufFseScratch*>(dt), slotMem, &hdr, &tl, &nbSym);
+          if (!e && hdr >= tbSize) e = ZE_srcSize_wrong;                           // HufDecompress.cs:1193
+        }
+        __syncwarp(gmask);
+        e = __shfl_sync(gmask, e, slot * 4); hdr = __shfl_sync(gmask, hdr, slot * 4);
+        tl = __shfl_sync(gmask, tl, slot * 4); nbSym = __shfl_sync(gmask, nbSym, slot * 4);
+        if (e) ok = false;
+      }
+      if (ok) {
+        __syncwarp(gmask);
+        huf_fill_table(dt, sideMem, wk, slotMem, tl, nbSym, sub, 4);
+        __syncwarp(gmask);
+        tableLog = tl; side = tl > HUF_TABLE_LOG ? sideMem : nullptr;
+        if (lh.type == 2) { body += hdr; bodySize -= hdr; }
+      }
+    }
+    if (ok) {
+      bool good = true;
+      if (lh.single) {
+        if (sub == 0) good = huf_decode_stream(body, bodySize, lit, lh.litSize, dt, tableLog, &sm.ring[lane][0], side);
+      } else {
+        HufStream st;
+        good = huf_split4(body, bodySize, lh.litSize, sub, st);
+        if (good) good = huf_decode_stream(st.src, st.len, lit + st.outOfs, st.count, dt, tableLog, &sm.ring[lane][0], side);
+      }
+      const unsigned okmask = __ballot_sync(gmask, good);
+      if ((okmask & gmask) != gmask) ok = false;
+    }
+    if (sub == 0 && !ok) sliceUnits[w].huf_err = ZE_corruption_detected;           // :742
+  }
+}
+
+// k_seq_blk : k_seq's mapping (one unit per lane, tables bank-interleaved), persistent over the launch's units
+__global__ void __launch_bounds__(32) k_seq_blk(DecodeArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SeqSmem& sm = *reinterpret_cast<SeqSmem*>(smem_raw);
+  const u32 lane = threadIdx.x;
+  const u32 nunits = a.cnt[0];
+  if (blockIdx.x * 32 >= nunits) return;
+  if (lane < 3) {
+    s16* norm = &sm.norm[0][lane]; u16* next = &sm.next[0][lane];
+    Strided<s16> nv{norm, 32}; Strided<u16> sn{next, 32};
+    if (lane == 0) { for (int i = 0; i < 36; i++) nv[i] = kLLnorm[i]; build_seq_table(sm.defLL, 1, nv, 35, 6, sn); }
+    if (lane == 1) { for (int i = 0; i < 29; i++) nv[i] = kOFnorm[i]; build_seq_table(sm.defOF, 1, nv, 28, 5, sn); }
+    if (lane == 2) { for (int i = 0; i < 53; i++) nv[i] = kMLnorm[i]; build_seq_table(sm.defML, 1, nv, 52, 6, sn); }
+  }
+  for (u32 i = lane; i < 36; i += 32) sm.llInfo[i] = ll_info(i);
+  for (u32 i = lane; i < 53; i += 32) sm.mlInfo[i] = ml_info(i);
+  __syncwarp();
+  BlockUnit* const sliceUnits = a.units + unit_slice_base(a);
+  for (u32 w = blockIdx.x * 32 + lane; w < nunits; w += gridDim.x * 32) {
+    const BlockUnit u = sliceUnits[w];
+    const u32 f = u.frame;
+    const FrameInfo fi = a.info[f];
+    SeqTableSet T;
+    T.space[KIND_LL] = &sm.ll[0][lane]; T.space[KIND_ML] = &sm.ml[0][lane]; T.space[KIND_OF] = &sm.of[0][lane]; T.stride = 32;
+    T.defs[KIND_LL] = sm.defLL; T.defs[KIND_OF] = sm.defOF; T.defs[KIND_ML] = sm.defML;
+    UnitEmitter em;
+    em.init(seq_region(a, f, fi) + u.rec_off, sm.llInfo, sm.mlInfo);
+    seq_decode_unit(a.src_base + a.src_off[f], u, sliceUnits + fi.unit_base, fi.window, T, em, sm.llInfo, sm.mlInfo,
+                    Strided<s16>{&sm.norm[0][lane], 32}, Strided<u16>{&sm.next[0][lane], 32}, &sm.ring[lane][0], a.dict);
+    if (em.dead) { sliceUnits[w].seq_err_code = em.err_code; sliceUnits[w].seq_err_index = em.err_index; }
+    else if (em.n) {
+      sliceUnits[w].rep[0] = em.h.v0; sliceUnits[w].rep[1] = em.h.v1; sliceUnits[w].rep[2] = em.h.v2;
+      sliceUnits[w].rep_sym = em.h.t0 | (em.h.t1 << 3) | (em.h.t2 << 6);
+    }
+  }
+}
+
+// k_exec_big : one CTA of EXECB_WARPS warps per FI_PAR frame.  The frame's work is cut into GROUPS in output order —
+// 32 sequence records, a raw / RLE block, or a block's last literals — and group G belongs to warp G % EXECB_WARPS.
+// Groups complete in order: a warp that has written its group waits until all earlier groups are complete, then moves
+// the frame's watermark (bytes that are final) to its group's end.  Literal runs never wait; matches whose source
+// lies before their group wait for the watermark to pass the source; sources inside the group are resolved in
+// dependency rounds exactly as in k_exec.  So record loads, literal copies and the waits for far memory of up to
+// EXECB_WARPS consecutive groups overlap, which is what a single warp per large frame could not do.
+#define EXECB_WARPS 4
+struct ExecBigShared {
+  volatile u32 wm, done;          // watermark (frame-relative output bytes that are final), groups completed
+  volatile u32 errG;              // lowest group that failed a record check (0xFFFFFFFF = none)
+  u32 errAt[EXECB_WARPS], errCode[EXECB_WARPS];
+};
+// publishes group G (ending at output position endPos) once every earlier group is complete; false = an earlier group failed
+__device__ __forceinline__ bool chain_complete(ExecBigShared& sh, u32 G, u32 endPos, u32 lane) {
+  __threadfence_block();
+  __syncwarp();
+  u32 ok = 1;
+  if (lane == 0) {
+    while (sh.done != G) { if (sh.errG < G) { ok = 0; break; } }
+    if (ok) { sh.wm = endPos; __threadfence_block(); sh.done = G + 1; }
+  }
+  return __shfl_sync(FULLMASK, ok, 0) != 0;
+}
+// waits until the watermark has reached `need`; false = an earlier group failed
+__device__ __forceinline__ bool chain_wait(ExecBigShared& sh, u32 G, u32 need, u32 lane) {
+  u32 ok = 1;
+  if (lane == 0) { while (sh.wm < need) { if (sh.errG < G) { ok = 0; break; } } }
+  ok = __shfl_sync(FULLMASK, ok, 0);
+  __threadfence_block();
+  return ok != 0;
+}
+
+template <bool DICT>
+__global__ void __launch_bounds__(EXECB_WARPS * 32, 8) k_exec_big(DecodeArgs a) {
+  __shared__ ExecBigShared sh;
+  const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const u32 npar = a.cnt[1];
+  const BlockUnit* const sliceUnits = a.units + unit_slice_base(a);
+  for (u32 p = blockIdx.x; p < npar; p += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x == 0) { sh.wm = 0; sh.done = 0; sh.errG = 0xFFFFFFFFu; }
+    if (lane == 0) sh.errAt[warp] = 0xFFFFFFFFu;
+    __syncthreads();
+    const u32 f = a.par_list[a.item_base + p];
+    const FrameInfo fi = a.info[f];
+    const u8* src = a.src_base + a.src_off[f]; const u32 size = a.src_size[f];
+    u8* dst = a.dst_base + frame_dst_off(a, f, fi); const u32 cap = frame_cap(a, f, fi);
+    const u8* litScratch = lit_region(a, f, fi);
+    const SeqRec* recs = seq_region(a, f, fi);
+    const BlockUnit* units = sliceUnits + fi.unit_base;
+    u32 pos = fi.body_off, op = 0, G = 0, cblk = 0;
+    bool litEntropy = false, bail = false; u32 err = 0;
+    u32 R[3] = {1, 4, 8};                                                          // ZStdInternal.cs:111
+    const u32 dictContent = DICT ? a.dict->contentSize : 0;
+    const u8* const dictEnd = DICT ? a.dict_bytes + a.dict->contentOff + dictContent : nullptr;
+    if (DICT && a.dict->hasEntropy) { litEntropy = true; R[0] = a.dict->rep[0]; R[1] = a.dict->rep[1]; R[2] = a.dict->rep[2]; }
+    if (DICT && !a.dict->hasEntropy) { R[0] = a.dict->rep[0]; R[1] = a.dict->rep[1]; R[2] = a.dict->rep[2]; }
+    while (true) {
+      BlockHdr bh;
+      err = read_block_hdr(src + pos, size - pos, bh);
+      if (err) break;
+      pos += 3;
+      if (bh.type == 0) {                                                          // raw, :662-667
+        if (bh.csize > cap - op) { err = ZE_dstSize_tooSmall; break; }
+        if (G % EXECB_WARPS == warp) {
+          warp_copy(dst + op, src + pos, bh.csize, lane);
+          if (!chain_complete(sh, G, op + bh.csize, lane)) { bail = true; break; }
+        }
+        G++; op += bh.csize;
+      } else if (bh.type == 1) {                                                   // RLE, :1945-1950
+        if (bh.orig > cap - op) { err = ZE_dstSize_tooSmall; break; }
+        if (G % EXECB_WARPS == warp) {
+          warp_fill(dst + op, src[pos], bh.orig, lane);
+          if (!chain_complete(sh, G, op + bh.orig, lane)) { bail = true; break; }
+        }
+        G++; op += bh.orig;
+      } else {
+        const BlockUnit bu = units[cblk]; cblk++;
+        const u8* bp = src + pos; const u32 bsz = bh.csize;
+        LitHdr lh; bool needs;
+        read_lit_hdr(bp, bsz, lh, &needs);                                         // sound, and a needed table exists: par_walk
+        const u8* lit; u32 rleByte = 0; bool isRle = false;
+        if (lh.type >= 2) {
+          if (bu.huf_err) { err = bu.huf_err; break; }                             // :742
+          litEntropy = true; lit = litScratch + bu.lit_off;
+        } else if (lh.type == 0) lit = bp + lh.lhSize;
+        else { lit = nullptr; isRle = true; rleByte = bp[lh.lhSize]; }
+        const u32 litSize = lh.litSize;
+        const u8* sp = bp + lh.consumed; const u32 ssz = bsz - lh.consumed;
+        u32 nbSeq, modes, hdr;
+        read_seq_count(sp, ssz, &nbSeq, &modes, &hdr);
+        if (bu.seq_err_code && bu.seq_err_index == 0xFFFFFFFFu) { err = bu.seq_err_code; break; }
+        u32 litPos = 0;
+        if (nbSeq) {
+          const uint4 h = __ldg(reinterpret_cast<const uint4*>(recs + bu.rec_off));
+          const u32 nRecs = h.x, outBytes = h.y, litBytes = h.z;
+          const uint4* rv = reinterpret_cast<const uint4*>(recs + bu.rec_off + 1);
+          const u32 blockBase = op;
+          for (u32 g0 = 0; g0 < nRecs; g0 += 32, G++) {
+            if (G % EXECB_WARPS != warp) continue;
+            const bool valid = g0 + lane < nRecs;
+            const uint4 rec = valid ? __ldg(rv + g0 + lane) : make_uint4(0, 0, 0, 0);
+            if (lane < 2 && g0 + 32 * EXECB_WARPS < nRecs) prefetch_line(rv + g0 + 32 * EXECB_WARPS + 16 * lane);   // this warp's next group
+            const u32 ll = valid ? (rec.w & 0x1FFFF) : 0, ml = valid ? ((rec.w >> 17) | (((rec.y >> 18) & 7) << 15)) : 0, lpos = rec.y & 0x3FFFF;
+            const u32 off = repsym_resolve(rec.z, (rec.y >> 21) & 7, R);
+            const u64 start64 = (u64)blockBase + rec.x;
+            const bool e1 = valid && start64 + ll + ml > cap;
+            const bool e2 = valid && lpos + ll > litSize;
+            const bool e3 = valid && (u64)off > start64 + ll + dictContent;         // :1290-1294
+            const unsigned bad = __ballot_sync(FULLMASK, e1 | e2 | e3);
+            if (bad) {
+              const u32 first = (u32)__ffs(bad) - 1;
+              const u32 code = __shfl_sync(FULLMASK, e1 ? (u32)ZE_dstSize_tooSmall : (u32)ZE_corruption_detected, first);
+              if (lane == 0) { sh.errAt[warp] = G; sh.errCode[warp] = code; atomicMin((u32*)&sh.errG, G); }
+              bail = true; break;
+            }
+            const u32 base = __shfl_sync(FULLMASK, rec.x, 0), lbase = __shfl_sync(FULLMASK, lpos, 0);
+            const u32 gstart = blockBase + base;                                   // frame-relative output position of the group
+            const u32 excl = valid ? rec.x - base : 0, mrel = excl + ll, incl = valid ? mrel + ml : 0xFFFFFFFFu;
+            const u32 lsrc = lpos - lbase;
+            u8* const g = dst + gstart;
+            const u32 gend = gstart + __shfl_sync(FULLMASK, valid ? mrel + ml : 0, min(31u, nRecs - g0 - 1));
+            // ---- literals ----
+            {
+              const bool bigL = ll >= 128;
+              unsigned bigMask = __ballot_sync(FULLMASK, bigL);
+              const u32 ls = bigL ? 0 : ll;
+              const u32 lu = word_units(g + excl, ls);
+              const u32 sincl = warp_incl_scan(lu, lane), sexcl = sincl - lu;
+              const u32 Ls = __shfl_sync(FULLMASK, sincl, 31);
+              if (isRle) { if (Ls) flat_fill_w<1>(g, rleByte * 0x01010101u, Ls, sincl, sexcl, excl, ls, lane); }
+              else if (Ls > 32) flat_copy_w<2>(g, lit + lbase, Ls, sincl, sexcl, excl, lsrc, ls, lane);
+              else if (Ls) flat_copy_w<1>(g, lit + lbase, Ls, sincl, sexcl, excl, lsrc, ls, lane);
+              while (bigMask) {
+                const u32 j = (u32)__ffs(bigMask) - 1; bigMask &= bigMask - 1;
+                const u32 dj = __shfl_sync(FULLMASK, excl, j), nj = __shfl_sync(FULLMASK, ll, j), lj = __shfl_sync(FULLMASK, lsrc, j);
+                if (isRle) warp_fill(g + dj, (u8)rleByte, nj, lane); else warp_copy(g + dj, lit + lbase + lj, nj, lane);
+              }
+            }
+            __syncwarp();
+            // ---- matches ----
+            const bool hasM = ml > 0 && off != 0;
+            const unsigned matchMask = __ballot_sync(FULLMASK, hasM);
+            if (matchMask) {
+              const i64 slo = (i64)mrel - (i64)off;                                // source range, group-relative
+              // sources before the group: the watermark must have passed them
+              {
+                u32 need = 0;
+                if (hasM && slo < 0) {
+                  const i64 endAbs = (i64)gstart + (slo + (i64)ml < 0 ? slo + (i64)ml : 0);
+                  need = endAbs > 0 ? (u32)endAbs : 0;                             // (<= 0: the dictionary, always there)
+                }
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) need = max(need, __shfl_xor_sync(FULLMASK, need, d));
+                if (need && !chain_wait(sh, G, need, lane)) { bail = true; break; }
+              }
+              unsigned depMask = 0;
+              {
+                i64 shi = slo + (i64)ml; if (shi > (i64)mrel) shi = (i64)mrel;
+                const bool dep = hasM && shi > 0;
+                const u32 needLo = slo > 0 ? (u32)slo : 0, needHi = dep ? (u32)shi : 1;
+                const u32 aIdx = warp_upper_bound(incl, dep ? needLo : 0), bIdx = warp_upper_bound(incl, needHi - 1);
+                if (dep) {
+                  const unsigned upTo = bIdx >= 31 ? 0xFFFFFFFFu : ((1u << (bIdx + 1)) - 1);
+                  depMask = upTo & ~((1u << aIdx) - 1) & ((1u << lane) - 1) & matchMask;
+                }
+              }
+              unsigned doneMask = ~matchMask;
+              while (doneMask != 0xFFFFFFFFu) {
+                const bool ready = hasM && !((doneMask >> lane) & 1) && ((depMask & ~doneMask) == 0);
+                const unsigned Rdy = __ballot_sync(FULLMASK, ready);
+                const bool inDict = DICT && off > gstart + mrel;
+                const bool plain = ready && off >= ml && ml < 128 && !inDict;
+                const u32 len = plain ? ml : 0, units4 = (len + 3) >> 2;
+                const u32 pincl = warp_incl_scan(units4, lane), pexcl = pincl - units4;
+                const u32 Tt = __shfl_sync(FULLMASK, pincl, 31);
+                if (Tt > 32) flat_copy_m4<2>(g, Tt, pincl, pexcl, mrel, off, len, lane);
+                else if (Tt) flat_copy_m4<1>(g, Tt, pincl, pexcl, mrel, off, len, lane);
+                unsigned big = __ballot_sync(FULLMASK, ready && !plain);
+                while (big) {
+                  const u32 j = (u32)__ffs(big) - 1; big &= big - 1;
+                  const u32 mj = __shfl_sync(FULLMASK, mrel, j), oj = __shfl_sync(FULLMASK, off, j), nj = __shfl_sync(FULLMASK, ml, j);
+                  const u32 pj = gstart + mj;
+                  if (DICT && oj > pj) {
+                    const u32 back = oj - pj, l1 = back < nj ? back : nj;
+                    warp_copy(g + mj, dictEnd - back, l1, lane);
+                    __syncwarp();
+                    if (nj > l1) warp_match(g + mj + l1, pj + l1, nj - l1, lane);
+                  } else warp_match(g + mj, oj, nj, lane);
+                }
+                __syncwarp();
+                doneMask |= Rdy;
+              }
+            }
+            if (!chain_complete(sh, G, gend, lane)) { bail = true; break; }
+          }
+          if (bail) break;
+          if (bu.seq_err_code) { err = bu.seq_err_code; break; }                   // :1594 after the decodable prefix
+          op = blockBase + outBytes; litPos = litBytes;
+          // the repeat offsets after this block, from its symbolic history (zb_blocks.cuh)
+          const u32 n0 = repsym_resolve(bu.rep[0], bu.rep_sym & 7, R), n1 = repsym_resolve(bu.rep[1], (bu.rep_sym >> 3) & 7, R),
+                    n2 = repsym_resolve(bu.rep[2], (bu.rep_sym >> 6) & 7, R);
+          R[0] = n0; R[1] = n1; R[2] = n2;
+        }
+        // last literals (:1599-1605)
+        const u32 lastLL = litSize - litPos;
+        if (lastLL > cap - op) { err = ZE_dstSize_tooSmall; break; }
+        if (G % EXECB_WARPS == warp) {
+          if (isRle) warp_fill(dst + op, (u8)rleByte, lastLL, lane); else warp_copy(dst + op, lit + litPos, lastLL, lane);
+          if (!chain_complete(sh, G, op + lastLL, lane)) { bail = true; break; }
+        }
+        G++; op += lastLL;
+      }
+      pos += bh.csize;
+      if (bh.last) break;
+    }
+    __syncthreads();
+    if (warp != 0) continue;
+    // a failed record check comes before anything the warps met afterwards; without one, no warp left early and all
+    // of them hold the same err / op / pos
+    if (sh.errG != 0xFFFFFFFFu) {
+      const u32 eg = sh.errG;
+      for (u32 k = 0; k < EXECB_WARPS; k++) if (sh.errAt[k] == eg) err = sh.errCode[k];
+    }
+    // ---- frame epilogue (:2069-2085) and the multi-frame loop tail (:2111-2157), as k_exec ----
+    bool needXxh = false; u32 trailer = 0;
+    if (!err) {
+      if ((fi.flags & FI_FCS_KNOWN) && op != fi.fcs) err = ZE_corruption_detected;
+      else if (fi.flags & FI_CHECKSUM) {
+        if (size - pos < 4) err = ZE_checksum_wrong; else { trailer = pos; pos += 4; needXxh = true; }
+      }
+    }
+    u32 tailErr = 0, nextOff = 0;
+    if (!err) {
+      while (true) {
+        u32 rem = size - pos;
+        if (rem < 5) { if (rem) tailErr = ZE_srcSize_wrong; break; }
+        u32 magic = ld32(src + pos);
+        if (magic == MAGIC) { nextOff = pos; break; }
+        if ((magic & 0xFFFFFFF0u) != MAGIC_SKIP) { tailErr = ZE_prefix_unknown; break; }
+        if (rem < 8) { tailErr = ZE_srcSize_wrong; break; }
+        u32 skip = ld32(src + pos + 4) + 8u;
+        if (rem < skip) { tailErr = ZE_srcSize_wrong; break; }
+        pos += skip;
+      }
+    }
+    if (lane == 0) {
+      u32 res = err ? zerr(err) : (tailErr ? zerr(tailErr) : fi.out_base + (u32)op);
+      a.result[f] = res;
+      a.info[f].trailer_off = trailer; a.info[f].decoded = (u32)op; a.info[f].next_off = nextOff;
+      a.info[f].flags = fi.flags | (needXxh ? FI_NEED_XXH : 0);
+      if (nextOff && a.more) atomicAdd(a.more, 1u);
+    }
+  }
+}
+
+// =================================================================================================
 // k_xxh : XXH64(seed 0) of the decoded bytes, 4 lanes per frame (one accumulator each)
 // =================================================================================================
 __global__ void __launch_bounds__(128) k_xxh(DecodeArgs a) {
@@ -610,9 +1000,24 @@ cudaError_t decode_load_dictionary(const u8* d_dict_bytes, u32 size, DictState* 
   return cudaGetLastError();
 }
 
+// grids of the persistent block-parallel kernels: what one wave of the device holds (set by decode_configure)
+static int g_par_grid_huf = 148 * 5, g_par_grid_seq = 148 * 2, g_par_grid_exec = 148 * 8;
+size_t decode_unit_arena_count(u64 max_dst_bytes, u64 max_items) { return (size_t)(max_dst_bytes / PAR_UNIT_BYTES + PAR_UNIT_SLACK * (max_items + 2) + 64); }
+
 cudaError_t decode_configure() {
   cudaError_t e = cudaFuncSetAttribute(k_huf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HufSmem));
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_huf_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HufSmem));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_seq_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqSmem));
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) {
+    int per = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_huf_blk, 32, sizeof(HufSmem)) == cudaSuccess && per > 0) g_par_grid_huf = sms * per;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_seq_blk, 32, sizeof(SeqSmem)) == cudaSuccess && per > 0) g_par_grid_seq = sms * per;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_exec_big<false>, EXECB_WARPS * 32, 0) == cudaSuccess && per > 0) g_par_grid_exec = sms * per;
+  }
   return cudaFuncSetAttribute(k_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqSmem));
 }
 
@@ -623,24 +1028,31 @@ const char* const kDecodeKernelNames[DECODE_KERNELS] = {"k_parse", "k_huf", "k_s
 // on one stream.
 cudaError_t decode_launch_entropy(const DecodeArgs& a, cudaStream_t st, int* launches, cudaEvent_t* marks) {
   if (a.n == 0) return cudaSuccess;
+  if (a.units) { cudaError_t e = cudaMemsetAsync(a.cnt, 0, 8, st); if (e != cudaSuccess) return e; }
   if (marks) cudaEventRecord(marks[0], st);
   k_parse<<<(a.n + 127) / 128, 128, 0, st>>>(a);
   if (marks) cudaEventRecord(marks[1], st);
   k_huf<<<(a.n + 7) / 8, 32, sizeof(HufSmem), st>>>(a);
+  if (a.units) k_huf_blk<<<g_par_grid_huf, 32, sizeof(HufSmem), st>>>(a);
   if (marks) cudaEventRecord(marks[2], st);
   k_seq<<<(a.n + 31) / 32, 32, sizeof(SeqSmem), st>>>(a);
+  if (a.units) k_seq_blk<<<g_par_grid_seq, 32, sizeof(SeqSmem), st>>>(a);
   if (marks) cudaEventRecord(marks[3], st);
-  if (launches) *launches += 3;
+  if (launches) *launches += a.units ? 5 : 3;
   return cudaGetLastError();
 }
 cudaError_t decode_launch_exec(const DecodeArgs& a, cudaStream_t st, int* launches, cudaEvent_t* marks) {
   if (a.n == 0) return cudaSuccess;
   if (a.dict) k_exec<true><<<(a.n + (EXEC_THREADS / 32) - 1) / (EXEC_THREADS / 32), EXEC_THREADS, 0, st>>>(a);
   else k_exec<false><<<(a.n + (EXEC_THREADS / 32) - 1) / (EXEC_THREADS / 32), EXEC_THREADS, 0, st>>>(a);
+  if (a.units) {
+    if (a.dict) k_exec_big<true><<<g_par_grid_exec, EXECB_WARPS * 32, 0, st>>>(a);
+    else k_exec_big<false><<<g_par_grid_exec, EXECB_WARPS * 32, 0, st>>>(a);
+  }
   if (marks) cudaEventRecord(marks[4], st);
   k_xxh<<<(a.n * 4 + 127) / 128, 128, 0, st>>>(a);
   if (marks) cudaEventRecord(marks[5], st);
-  if (launches) *launches += 2;
+  if (launches) *launches += a.units ? 3 : 2;
   return cudaGetLastError();
 }
 cudaError_t decode_launch(const DecodeArgs& a, cudaStream_t st, int* launches, cudaEvent_t* marks) {

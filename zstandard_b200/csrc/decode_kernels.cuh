@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "zb_decode.cuh"
+#include "zb_blocks.cuh"
 
 namespace zb {
 
@@ -24,10 +25,15 @@ struct DecodeArgs {
   const u8* dict_bytes;
   u32 pass;            // 0 = first data frame of every item
   u32* more;           // device counter, zeroed by the host before each pass (may be null: multi-frame items end after frame 1)
+  // Block-parallel path for multi-block frames (zb_blocks.cuh).  units == nullptr switches it off.
+  BlockUnit* units;    // decode_unit_arena_count() units; a slice uses the range that follows from its first dst_off / item_base
+  u32* par_list;       // one entry per item of the arena numbering: the slice's FI_PAR items, dense from par_list[item_base]
+  u32* cnt;            // device counters zeroed by the host before each pass: [0] units, [1] FI_PAR items of this launch
 };
 
 size_t decode_lit_arena_bytes(u64 max_dst_bytes, u64 max_items);
 size_t decode_seq_arena_bytes(u64 max_dst_bytes, u64 max_items);
+size_t decode_unit_arena_count(u64 max_dst_bytes, u64 max_items);
 cudaError_t decode_configure();
 // parses the dictionary at d_dict_bytes (device memory, size bytes) into *d_state on `st` (one small kernel)
 cudaError_t decode_load_dictionary(const u8* d_dict_bytes, u32 size, DictState* d_state, cudaStream_t st);
@@ -37,6 +43,7 @@ cudaError_t decode_launch(const DecodeArgs& a, cudaStream_t st, int* launches, c
 cudaError_t decode_launch_entropy(const DecodeArgs& a, cudaStream_t st, int* launches, cudaEvent_t* marks = nullptr);
 cudaError_t decode_launch_exec(const DecodeArgs& a, cudaStream_t st, int* launches, cudaEvent_t* marks = nullptr);
 // marks (optional): DECODE_KERNELS + 1 events recorded before the first kernel and after each kernel
+// (the block-parallel kernels k_huf_blk / k_seq_blk / k_exec_big run right after k_huf / k_seq / k_exec and are timed with them)
 #define DECODE_KERNELS 5
 extern const char* const kDecodeKernelNames[DECODE_KERNELS];
 

@@ -47,7 +47,8 @@ static const u32 HUF_TABLE_LOG = 11;      // log of the decode table the kernels
 // scratch (the output cannot fit either): the execute stage replays the block's checks without copying.
 #define HUF_DRY 0xFFFFu
 enum : u32 { FI_CHECKSUM = 1, FI_FCS_KNOWN = 2, FI_DONE = 4 /* result[] already final, later stages skip the item */,
-              FI_NEED_XXH = 8 /* set by the execute stage: verify the content checksum */ };
+              FI_NEED_XXH = 8 /* set by the execute stage: verify the content checksum */,
+              FI_PAR = 16 /* multi-block frame decoded block-parallel: its compressed blocks are BlockUnits (zb_blocks.cuh) */ };
 struct FrameInfo {
   u32 flags;
   u32 body_off;      // offset within the item of the first block header of its data frame
@@ -62,6 +63,8 @@ struct FrameInfo {
   // items holding several data frames (DecompressMultiFrame, ZStdDecompress.cs:2096-2160) take one pass per frame
   u32 out_base;      // bytes produced by the item's earlier data frames: this frame writes at dst + out_base
   u32 next_off;      // offset within the item of the next data frame's magic (0 = none), set by the execute stage
+  // FI_PAR frames: their compressed blocks are units [unit_base, unit_base + unit_count) of the slice's unit list
+  u32 unit_base, unit_count;
 };
 
 // array view with a stride (bank-interleaved per-lane arrays in shared memory)

@@ -187,6 +187,92 @@ struct SeqEmitter {
   ZB_HD void fail(u32 blk, u32 code) { if (dead) return; res.err_block = blk; res.err_code = code; res.err_index = 0xFFFFFFFFu; dead = true; }
 };
 
+// The bitstream of one compressed block: nbSeq sequences out of bits[0..nbytes) with the tables in force (T.cur, T.log)
+// go to `sink` (block_begin ... block_end).  Returns true when the frame cannot go on (the stream failed or the sink has
+// stopped).  blk = the block's index for the sink's error record.
+template <class Sink>
+ZB_HD bool seq_decode_bitstream(const u8* bits, u32 nbytes, u32 nbSeq, u64 window, const SeqTableSet& T, Sink& sink,
+                                const u32* llInfo, const u32* mlInfo, u32* ringMem, u32 blk) {
+  // Windows above 16 MiB whose offset table has >= 20/256 cells of more than 22 extra bits run the sequence loop
+  // that decodes four sequences ahead of their execution (:1898-1905, GetLongOffsetsShare :1845-1865)
+  bool longVariant = false;
+  if (window > (1u << 24)) {
+    const u32 lg = T.log[KIND_OF]; u32 total = 0;
+    for (u32 u = 0; u < (1u << lg); u++) total += (T.cur[KIND_OF][u * T.curStride[KIND_OF]] >> 10) > 22;
+    longVariant = (total << (8 - lg)) >= 20;
+  }
+  // ---- bitstream ----
+  BitCursor c;
+  sink.block_begin();
+  u32 decoded = 0; bool bad = false;
+  if (!bc_init(c, bits, nbytes)) bad = true;                          // :1577 -> corruption_detected
+  if (!bad) {
+    i32 P = c.P;
+    const u16 *tLL = T.cur[KIND_LL], *tOF = T.cur[KIND_OF], *tML = T.cur[KIND_ML];
+    const u32 sLLs = T.curStride[KIND_LL], sOFs = T.curStride[KIND_OF], sMLs = T.curStride[KIND_ML];
+    u32 stLL, stOF, stML;
+    { u64 w = bc_window64(c, P); u32 lg = T.log[KIND_LL]; stLL = top_bits(w, lg); w <<= lg; P -= (i32)lg;
+      lg = T.log[KIND_OF]; stOF = top_bits(w, lg); w <<= lg; P -= (i32)lg;
+      lg = T.log[KIND_ML]; stML = top_bits(w, lg); P -= (i32)lg; }             // :1578-1580 (<= 26 bits)
+    u32 i = 0;
+    // ---- fast loop: >= 128 unread bits, so no over-read is possible (a sequence takes <= 89 bits); leaves to
+    //      the careful loop when a sequence carries >= 32 value bits (rare: very long lengths / offsets) ----
+    BitRing ring;
+    if (nbSeq && P >= 128) ring_init(ring, ringMem, bits, nbytes);
+    while (i < nbSeq && P >= 128) {
+      u32 lo, hi;
+      ring_window(ring, P, lo, hi);                                          // 64-bit window ending at P
+      const u32 yLL = tLL[stLL * sLLs], yOF = tOF[stOF * sOFs], yML = tML[stML * sMLs];
+      const u32 llSym = yLL >> 10, mlSym = yML >> 10, ofBits = yOF >> 10;   // the offset code is its own extra-bit count
+      const u32 iLL = llInfo[llSym], iML = mlInfo[mlSym];
+      const u32 valBits = ofBits + (iML >> 24) + (iLL >> 24);
+      const u32 lLL = yLL & 0x3FF, lOF = yOF & 0x3FF, lML = yML & 0x3FF;
+      const u32 nLL = cell_nb(lLL), nML = cell_nb(lML), nOF = cell_nb(lOF);
+      // the one rare exit of the loop: >= 32 value bits (they do not fit the word handed over) — nothing has been
+      // committed yet, the careful loop redoes this sequence
+      if (valBits >= 32) break;
+      sink.fast(hi, llSym, ofBits, iLL, iML);
+      const u32 h2 = fshl(lo, hi, valBits);                                  // the 32 bits after the value bits
+      stLL = cell_base(lLL) + shr_c(h2, 32 - nLL);                           // state update LL, ML, OF (:1547-1550)
+      stML = cell_base(lML) + shr_c(h2 << nLL, 32 - nML);
+      stOF = cell_base(lOF) + shr_c(h2 << (nLL + nML), 32 - nOF);
+      const i32 Pn = P - (i32)(valBits + nLL + nML + nOF);
+      ring_advance(ring, Pn);
+      P = Pn; i++;
+    }
+    decoded = i;
+    // ---- careful loop: stream tail and oversized sequences ----
+    for (; i < nbSeq; i++) {
+      if (P < 0) { bad = true; break; }                                      // loop test :1582 (overflow)
+      const u64 w0 = bc_window64(c, P);
+      const u32 yLL = tLL[stLL * sLLs], yOF = tOF[stOF * sOFs], yML = tML[stML * sMLs];
+      const u32 llSym = yLL >> 10, mlSym = yML >> 10, ofBits = yOF >> 10;
+      const u32 llBits = llInfo[llSym] >> 24, mlBits = mlInfo[mlSym] >> 24;
+      const u32 lLL = yLL & 0x3FF, lOF = yOF & 0x3FF, lML = yML & 0x3FF;
+      const u32 nLL = cell_nb(lLL), nML = cell_nb(lML), nOF = cell_nb(lOF);
+      const u32 valBits = ofBits + mlBits + llBits, stBits = nLL + nML + nOF;
+      u64 w = w0;
+      u32 ofv = top_bits(w, ofBits); w <<= ofBits;
+      u32 mlv = top_bits(w, mlBits); w <<= mlBits;
+      u32 llv = top_bits(w, llBits); w <<= llBits;
+      const i32 Pv = P - (i32)valBits;
+      if (Pv < 0) seq_values_ref32(bits, nbytes, P, window > (1ull << 25), longVariant, ofBits, mlBits, llBits, ofv, mlv, llv);   // over-read: the reference's container garbage
+      else if (valBits + stBits > 64) w = bc_window64(c, Pv);                // rare: more than 64 bits in one sequence
+      sink.values(ofv, mlv, llv, llSym, mlSym, ofBits);
+      decoded++;
+      // past the last sequence these bits do not exist (the stream ends after its value bits)
+      stLL = cell_base(lLL) + top_bits(w, nLL); w <<= nLL;
+      stML = cell_base(lML) + top_bits(w, nML); w <<= nML;
+      stOF = cell_base(lOF) + top_bits(w, nOF);
+      P = Pv - (i32)stBits;
+    }
+  }
+  // the look-ahead loop has executed all but the last four sequences when the stream runs out (:1748-1764)
+  if (bad && longVariant) decoded = decoded > 4 ? decoded - 4 : 0;
+  sink.block_end(blk, decoded, bad);
+  return bad || sink.stopped();
+}
+
 // Walks the frame at item `src` (size bytes, first block header at body_off) and decodes every compressed
 // block's sequences into `sink` (block_begin / fast / values / block_end / fail / stopped, see SeqEmitter).  Stops silently at
 // structural errors that the execute stage will report itself from the same headers.
@@ -240,84 +326,7 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, S
         }
         if (e) { sink.fail(blk, ZE_corruption_detected); return; }
         haveRepeat = true;                                                         // fseEntropy = 1 (:1575)
-        // Windows above 16 MiB whose offset table has >= 20/256 cells of more than 22 extra bits run the sequence loop
-        // that decodes four sequences ahead of their execution (:1898-1905, GetLongOffsetsShare :1845-1865)
-        bool longVariant = false;
-        if (window > (1u << 24)) {
-          const u32 lg = T.log[KIND_OF]; u32 total = 0;
-          for (u32 u = 0; u < (1u << lg); u++) total += (T.cur[KIND_OF][u * T.curStride[KIND_OF]] >> 10) > 22;
-          longVariant = (total << (8 - lg)) >= 20;
-        }
-        // ---- bitstream ----
-        BitCursor c;
-        sink.block_begin();
-        u32 decoded = 0; bool bad = false;
-        if (!bc_init(c, sp + hdr, ssz - hdr)) bad = true;                          // :1577 -> corruption_detected
-        if (!bad) {
-          i32 P = c.P;
-          const u16 *tLL = T.cur[KIND_LL], *tOF = T.cur[KIND_OF], *tML = T.cur[KIND_ML];
-          const u32 sLLs = T.curStride[KIND_LL], sOFs = T.curStride[KIND_OF], sMLs = T.curStride[KIND_ML];
-          u32 stLL, stOF, stML;
-          { u64 w = bc_window64(c, P); u32 lg = T.log[KIND_LL]; stLL = top_bits(w, lg); w <<= lg; P -= (i32)lg;
-            lg = T.log[KIND_OF]; stOF = top_bits(w, lg); w <<= lg; P -= (i32)lg;
-            lg = T.log[KIND_ML]; stML = top_bits(w, lg); P -= (i32)lg; }             // :1578-1580 (<= 26 bits)
-          u32 i = 0;
-          // ---- fast loop: >= 128 unread bits, so no over-read is possible (a sequence takes <= 89 bits); leaves to
-          //      the careful loop when a sequence carries >= 32 value bits (rare: very long lengths / offsets) ----
-          BitRing ring;
-          if (nbSeq && P >= 128) ring_init(ring, ringMem, sp + hdr, ssz - hdr);
-          while (i < nbSeq && P >= 128) {
-            u32 lo, hi;
-            ring_window(ring, P, lo, hi);                                          // 64-bit window ending at P
-            const u32 yLL = tLL[stLL * sLLs], yOF = tOF[stOF * sOFs], yML = tML[stML * sMLs];
-            const u32 llSym = yLL >> 10, mlSym = yML >> 10, ofBits = yOF >> 10;   // the offset code is its own extra-bit count
-            const u32 iLL = llInfo[llSym], iML = mlInfo[mlSym];
-            const u32 valBits = ofBits + (iML >> 24) + (iLL >> 24);
-            const u32 lLL = yLL & 0x3FF, lOF = yOF & 0x3FF, lML = yML & 0x3FF;
-            const u32 nLL = cell_nb(lLL), nML = cell_nb(lML), nOF = cell_nb(lOF);
-            // the one rare exit of the loop: >= 32 value bits (they do not fit the word handed over) — nothing has been
-            // committed yet, the careful loop redoes this sequence
-            if (valBits >= 32) break;
-            sink.fast(hi, llSym, ofBits, iLL, iML);
-            const u32 h2 = fshl(lo, hi, valBits);                                  // the 32 bits after the value bits
-            stLL = cell_base(lLL) + shr_c(h2, 32 - nLL);                           // state update LL, ML, OF (:1547-1550)
-            stML = cell_base(lML) + shr_c(h2 << nLL, 32 - nML);
-            stOF = cell_base(lOF) + shr_c(h2 << (nLL + nML), 32 - nOF);
-            const i32 Pn = P - (i32)(valBits + nLL + nML + nOF);
-            ring_advance(ring, Pn);
-            P = Pn; i++;
-          }
-          decoded = i;
-          // ---- careful loop: stream tail and oversized sequences ----
-          for (; i < nbSeq; i++) {
-            if (P < 0) { bad = true; break; }                                      // loop test :1582 (overflow)
-            const u64 w0 = bc_window64(c, P);
-            const u32 yLL = tLL[stLL * sLLs], yOF = tOF[stOF * sOFs], yML = tML[stML * sMLs];
-            const u32 llSym = yLL >> 10, mlSym = yML >> 10, ofBits = yOF >> 10;
-            const u32 llBits = llInfo[llSym] >> 24, mlBits = mlInfo[mlSym] >> 24;
-            const u32 lLL = yLL & 0x3FF, lOF = yOF & 0x3FF, lML = yML & 0x3FF;
-            const u32 nLL = cell_nb(lLL), nML = cell_nb(lML), nOF = cell_nb(lOF);
-            const u32 valBits = ofBits + mlBits + llBits, stBits = nLL + nML + nOF;
-            u64 w = w0;
-            u32 ofv = top_bits(w, ofBits); w <<= ofBits;
-            u32 mlv = top_bits(w, mlBits); w <<= mlBits;
-            u32 llv = top_bits(w, llBits); w <<= llBits;
-            const i32 Pv = P - (i32)valBits;
-            if (Pv < 0) seq_values_ref32(sp + hdr, ssz - hdr, P, window > (1ull << 25), longVariant, ofBits, mlBits, llBits, ofv, mlv, llv);   // over-read: the reference's container garbage
-            else if (valBits + stBits > 64) w = bc_window64(c, Pv);                // rare: more than 64 bits in one sequence
-            sink.values(ofv, mlv, llv, llSym, mlSym, ofBits);
-            decoded++;
-            // past the last sequence these bits do not exist (the stream ends after its value bits)
-            stLL = cell_base(lLL) + top_bits(w, nLL); w <<= nLL;
-            stML = cell_base(lML) + top_bits(w, nML); w <<= nML;
-            stOF = cell_base(lOF) + top_bits(w, nOF);
-            P = Pv - (i32)stBits;
-          }
-        }
-        // the look-ahead loop has executed all but the last four sequences when the stream runs out (:1748-1764)
-        if (bad && longVariant) decoded = decoded > 4 ? decoded - 4 : 0;
-        sink.block_end(blk, decoded, bad);
-        if (bad || sink.stopped()) return;
+        if (seq_decode_bitstream(sp + hdr, ssz - hdr, nbSeq, window, T, sink, llInfo, mlInfo, ringMem, blk)) return;
       }
     }
     pos += bh.csize; blk++;

@@ -21,7 +21,7 @@ namespace zb {
 ZB_HD bool parse_item(const u8* src, u32 size, FrameInfo& fi, u32* result, u32 start = 0, u32 out_base = 0, u32 dictErr = 0, u32 ctxDictID = 0) {
   fi.flags = 0; fi.body_off = 0; fi.fcs = 0; fi.window = 0;
   fi.huf_err_block = 0xFFFFFFFFu; fi.huf_err_code = 0; fi.seq_err_block = 0xFFFFFFFFu; fi.seq_err_code = 0; fi.seq_err_index = 0;
-  fi.trailer_off = 0; fi.decoded = 0; fi.out_base = out_base; fi.next_off = 0;
+  fi.trailer_off = 0; fi.decoded = 0; fi.out_base = out_base; fi.next_off = 0; fi.unit_base = 0; fi.unit_count = 0;
   u32 pos = start;
   while (true) {
     u32 rem = size - pos;
