@@ -708,48 +708,76 @@ __global__ void __launch_bounds__(32) k_seq_blk(DecodeArgs a) {
   }
 }
 
-// k_exec_big : one CTA of EXECB_WARPS warps per FI_PAR frame.  The frame's work is cut into GROUPS in output order —
-// 32 sequence records, a raw / RLE block, or a block's last literals — and group G belongs to warp G % EXECB_WARPS.
-// Groups complete in order: a warp that has written its group waits until all earlier groups are complete, then moves
-// the frame's watermark (bytes that are final) to its group's end.  Literal runs never wait; matches whose source
-// lies before their group wait for the watermark to pass the source; sources inside the group are resolved in
-// dependency rounds exactly as in k_exec.  So record loads, literal copies and the waits for far memory of up to
-// EXECB_WARPS consecutive groups overlap, which is what a single warp per large frame could not do.
-#define EXECB_WARPS 4
-struct ExecBigShared {
-  volatile u32 wm, done;          // watermark (frame-relative output bytes that are final), groups completed
+// k_exec_big : one CTA of W warps per FI_PAR frame.  The frame's work is cut into GROUPS in output order — 32 sequence
+// records, a raw / RLE block, or a block's last literals — and group G belongs to warp G % W.  A warp that has written
+// its group marks it in a small ring; whoever gets there moves the in-order chain (groups complete, watermark = output
+// bytes that are final) over every consecutive written group.  Literal runs never wait; a match whose source lies
+// before its group waits until the watermark has passed that source; sources inside the group are resolved in dependency
+// rounds exactly as in k_exec.  So the record loads, the literal copies and the far-memory matches of up to W
+// consecutive groups overlap, which one warp per large frame cannot do; what stays serial is the chain "group G-1
+// complete -> the few matches of G that read its output -> G complete" (one L2 round trip per round: measured
+// 1.8 us per group).  W follows from how many FI_PAR frames the launch holds (execb_warps): few large
+// frames need the parallelism inside a frame, many frames fill the device on their own and a single warp each has no
+// synchronisation cost.  All three instantiations are launched; the two that do not match return at once.
+__host__ __device__ inline u32 execb_warps(u32 npar) { return npar * 4 <= 148 * 32 ? 4 : (npar * 2 <= 148 * 32 ? 2 : 1); }
+template <int W> struct ExecBigShared {
+  volatile u32 wm;                // watermark: frame-relative output bytes that are final (every group before is complete)
+  volatile u32 done;              // groups completed in order
   volatile u32 errG;              // lowest group that failed a record check (0xFFFFFFFF = none)
-  u32 errAt[EXECB_WARPS], errCode[EXECB_WARPS];
+  volatile u32 flag[4 * W];       // flag[G % RING] == G + 1: group G has been written (RING = 4 W groups may be in flight)
+  volatile u32 endPos[4 * W];
+  u32 errAt[W], errCode[W];
 };
-// publishes group G (ending at output position endPos) once every earlier group is complete; false = an earlier group failed
-__device__ __forceinline__ bool chain_complete(ExecBigShared& sh, u32 G, u32 endPos, u32 lane) {
+// Group G (ending at output position endPos) has been written: mark it, then move the chain as far as it goes.
+template <int W>
+__device__ __forceinline__ void chain_publish(ExecBigShared<W>& sh, u32 G, u32 endPos, u32 lane) {
   __threadfence_block();
   __syncwarp();
-  u32 ok = 1;
   if (lane == 0) {
-    while (sh.done != G) { if (sh.errG < G) { ok = 0; break; } }
-    if (ok) { sh.wm = endPos; __threadfence_block(); sh.done = G + 1; }
+    if (W == 1) { sh.wm = endPos; sh.done = G + 1; }
+    else {
+      sh.endPos[G % (4 * W)] = endPos;
+      __threadfence_block();
+      sh.flag[G % (4 * W)] = G + 1;
+      __threadfence_block();                                                       // (store flag, load done) vs (CAS done, load flag)
+      u32 d = sh.done;
+      while (sh.flag[d % (4 * W)] == d + 1) {
+        const u32 e = sh.endPos[d % (4 * W)];
+        if (atomicCAS((u32*)&sh.done, d, d + 1) == d) atomicMax((u32*)&sh.wm, e);
+        __threadfence_block();
+        d = sh.done;
+      }
+    }
   }
+  __syncwarp();
+}
+// before group G starts: its ring slot must be free (group G - RING consumed by the chain); false = an earlier group failed
+template <int W>
+__device__ __forceinline__ bool chain_admit(ExecBigShared<W>& sh, u32 G, u32 lane) {
+  if (W == 1) return true;
+  u32 ok = 1;
+  if (lane == 0) { while (G >= sh.done + 4 * W) { if (sh.errG < G) { ok = 0; break; } __nanosleep(20); } }
   return __shfl_sync(FULLMASK, ok, 0) != 0;
 }
-// waits until the watermark has reached `need`; false = an earlier group failed
-__device__ __forceinline__ bool chain_wait(ExecBigShared& sh, u32 G, u32 need, u32 lane) {
+// waits until the watermark has moved past `seen`; false = an earlier group failed
+template <int W>
+__device__ __forceinline__ bool chain_wait_move(ExecBigShared<W>& sh, u32 G, u32 seen, u32 lane) {
   u32 ok = 1;
-  if (lane == 0) { while (sh.wm < need) { if (sh.errG < G) { ok = 0; break; } } }
-  ok = __shfl_sync(FULLMASK, ok, 0);
-  __threadfence_block();
-  return ok != 0;
+  if (lane == 0) { while (sh.wm == seen) { if (sh.errG < G) { ok = 0; break; } __nanosleep(20); } }
+  return __shfl_sync(FULLMASK, ok, 0) != 0;
 }
 
-template <bool DICT>
-__global__ void __launch_bounds__(EXECB_WARPS * 32, 8) k_exec_big(DecodeArgs a) {
-  __shared__ ExecBigShared sh;
+template <bool DICT, int W>
+__global__ void __launch_bounds__(W * 32, 32 / W) k_exec_big(DecodeArgs a) {
+  __shared__ ExecBigShared<W> sh;
   const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const u32 npar = a.cnt[1];
+  if (execb_warps(npar) != (u32)W) return;
   const BlockUnit* const sliceUnits = a.units + unit_slice_base(a);
   for (u32 p = blockIdx.x; p < npar; p += gridDim.x) {
     __syncthreads();
     if (threadIdx.x == 0) { sh.wm = 0; sh.done = 0; sh.errG = 0xFFFFFFFFu; }
+    if (threadIdx.x < (4 * W)) sh.flag[threadIdx.x] = 0;
     if (lane == 0) sh.errAt[warp] = 0xFFFFFFFFu;
     __syncthreads();
     const u32 f = a.par_list[a.item_base + p];
@@ -773,16 +801,18 @@ __global__ void __launch_bounds__(EXECB_WARPS * 32, 8) k_exec_big(DecodeArgs a) 
       pos += 3;
       if (bh.type == 0) {                                                          // raw, :662-667
         if (bh.csize > cap - op) { err = ZE_dstSize_tooSmall; break; }
-        if (G % EXECB_WARPS == warp) {
+        if (G % W == warp) {
+          if (!chain_admit(sh, G, lane)) { bail = true; break; }
           warp_copy(dst + op, src + pos, bh.csize, lane);
-          if (!chain_complete(sh, G, op + bh.csize, lane)) { bail = true; break; }
+          chain_publish(sh, G, op + bh.csize, lane);
         }
         G++; op += bh.csize;
       } else if (bh.type == 1) {                                                   // RLE, :1945-1950
         if (bh.orig > cap - op) { err = ZE_dstSize_tooSmall; break; }
-        if (G % EXECB_WARPS == warp) {
+        if (G % W == warp) {
+          if (!chain_admit(sh, G, lane)) { bail = true; break; }
           warp_fill(dst + op, src[pos], bh.orig, lane);
-          if (!chain_complete(sh, G, op + bh.orig, lane)) { bail = true; break; }
+          chain_publish(sh, G, op + bh.orig, lane);
         }
         G++; op += bh.orig;
       } else {
@@ -808,10 +838,11 @@ __global__ void __launch_bounds__(EXECB_WARPS * 32, 8) k_exec_big(DecodeArgs a) 
           const uint4* rv = reinterpret_cast<const uint4*>(recs + bu.rec_off + 1);
           const u32 blockBase = op;
           for (u32 g0 = 0; g0 < nRecs; g0 += 32, G++) {
-            if (G % EXECB_WARPS != warp) continue;
+            if (G % W != warp) continue;
+            if (!chain_admit(sh, G, lane)) { bail = true; break; }
             const bool valid = g0 + lane < nRecs;
             const uint4 rec = valid ? __ldg(rv + g0 + lane) : make_uint4(0, 0, 0, 0);
-            if (lane < 2 && g0 + 32 * EXECB_WARPS < nRecs) prefetch_line(rv + g0 + 32 * EXECB_WARPS + 16 * lane);   // this warp's next group
+            if (lane < 2 && g0 + 32 * W < nRecs) prefetch_line(rv + g0 + 32 * W + 16 * lane);   // this warp's next group
             const u32 ll = valid ? (rec.w & 0x1FFFF) : 0, ml = valid ? ((rec.w >> 17) | (((rec.y >> 18) & 7) << 15)) : 0, lpos = rec.y & 0x3FFFF;
             const u32 off = repsym_resolve(rec.z, (rec.y >> 21) & 7, R);
             const u64 start64 = (u64)blockBase + rec.x;
@@ -854,16 +885,11 @@ __global__ void __launch_bounds__(EXECB_WARPS * 32, 8) k_exec_big(DecodeArgs a) 
             const unsigned matchMask = __ballot_sync(FULLMASK, hasM);
             if (matchMask) {
               const i64 slo = (i64)mrel - (i64)off;                                // source range, group-relative
-              // sources before the group: the watermark must have passed them
-              {
-                u32 need = 0;
-                if (hasM && slo < 0) {
-                  const i64 endAbs = (i64)gstart + (slo + (i64)ml < 0 ? slo + (i64)ml : 0);
-                  need = endAbs > 0 ? (u32)endAbs : 0;                             // (<= 0: the dictionary, always there)
-                }
-#pragma unroll
-                for (int d = 16; d >= 1; d >>= 1) need = max(need, __shfl_xor_sync(FULLMASK, need, d));
-                if (need && !chain_wait(sh, G, need, lane)) { bail = true; break; }
+              // a source before the group needs the watermark to have passed it (<= 0: the dictionary, always there)
+              u32 needAbs = 0;
+              if (hasM && slo < 0) {
+                const i64 endAbs = (i64)gstart + (slo + (i64)ml < 0 ? slo + (i64)ml : 0);
+                needAbs = endAbs > 0 ? (u32)endAbs : 0;
               }
               unsigned depMask = 0;
               {
@@ -878,8 +904,14 @@ __global__ void __launch_bounds__(EXECB_WARPS * 32, 8) k_exec_big(DecodeArgs a) 
               }
               unsigned doneMask = ~matchMask;
               while (doneMask != 0xFFFFFFFFu) {
-                const bool ready = hasM && !((doneMask >> lane) & 1) && ((depMask & ~doneMask) == 0);
+                const u32 wmNow = __shfl_sync(FULLMASK, sh.wm, 0);
+                __threadfence_block();
+                const bool ready = hasM && !((doneMask >> lane) & 1) && ((depMask & ~doneMask) == 0) && needAbs <= wmNow;
                 const unsigned Rdy = __ballot_sync(FULLMASK, ready);
+                if (!Rdy) {                                                        // every pending match waits for earlier groups
+                  if (!chain_wait_move(sh, G, wmNow, lane)) { bail = true; break; }
+                  continue;
+                }
                 const bool inDict = DICT && off > gstart + mrel;
                 const bool plain = ready && off >= ml && ml < 128 && !inDict;
                 const u32 len = plain ? ml : 0, units4 = (len + 3) >> 2;
@@ -902,8 +934,9 @@ __global__ void __launch_bounds__(EXECB_WARPS * 32, 8) k_exec_big(DecodeArgs a) 
                 __syncwarp();
                 doneMask |= Rdy;
               }
+              if (bail) break;
             }
-            if (!chain_complete(sh, G, gend, lane)) { bail = true; break; }
+            chain_publish(sh, G, gend, lane);
           }
           if (bail) break;
           if (bu.seq_err_code) { err = bu.seq_err_code; break; }                   // :1594 after the decodable prefix
@@ -916,9 +949,10 @@ __global__ void __launch_bounds__(EXECB_WARPS * 32, 8) k_exec_big(DecodeArgs a) 
         // last literals (:1599-1605)
         const u32 lastLL = litSize - litPos;
         if (lastLL > cap - op) { err = ZE_dstSize_tooSmall; break; }
-        if (G % EXECB_WARPS == warp) {
+        if (G % W == warp) {
+          if (!chain_admit(sh, G, lane)) { bail = true; break; }
           if (isRle) warp_fill(dst + op, (u8)rleByte, lastLL, lane); else warp_copy(dst + op, lit + litPos, lastLL, lane);
-          if (!chain_complete(sh, G, op + lastLL, lane)) { bail = true; break; }
+          chain_publish(sh, G, op + lastLL, lane);
         }
         G++; op += lastLL;
       }
@@ -931,7 +965,7 @@ __global__ void __launch_bounds__(EXECB_WARPS * 32, 8) k_exec_big(DecodeArgs a) 
     // of them hold the same err / op / pos
     if (sh.errG != 0xFFFFFFFFu) {
       const u32 eg = sh.errG;
-      for (u32 k = 0; k < EXECB_WARPS; k++) if (sh.errAt[k] == eg) err = sh.errCode[k];
+      for (u32 k = 0; k < W; k++) if (sh.errAt[k] == eg) err = sh.errCode[k];
     }
     // ---- frame epilogue (:2069-2085) and the multi-frame loop tail (:2111-2157), as k_exec ----
     bool needXxh = false; u32 trailer = 0;
@@ -974,12 +1008,29 @@ __global__ void __launch_bounds__(128) k_xxh(DecodeArgs a) {
   const unsigned gmask = 0xFu << (lane & ~3u);
   if (f >= a.n) return;
   FrameInfo fi = a.info[f];
-  if (!(fi.flags & FI_NEED_XXH)) return;
+  if (!(fi.flags & FI_NEED_XXH) || (fi.flags & FI_PAR)) return;
   const u8* dst = a.dst_base + frame_dst_off(a, f, fi);
-  u64 h = xxh64_group(dst, fi.decoded, sub, gmask, lane & ~3u);
+  u64 h = xxh64_group<false>(dst, fi.decoded, sub, gmask, lane & ~3u);
   if (sub == 0) {
     const u8* src = a.src_base + a.src_off[f];
     if ((u32)h != ld32(src + fi.trailer_off)) a.result[f] = zerr(ZE_checksum_wrong);   // :2078-2082
+  }
+}
+// the FI_PAR frames (few and long): the same 4 lanes per frame with the deeper load pipeline, persistent over the list
+__global__ void __launch_bounds__(32) k_xxh_big(DecodeArgs a) {
+  const u32 lane = threadIdx.x, sub = lane & 3, slot = lane >> 2;
+  const unsigned gmask = 0xFu << (lane & ~3u);
+  const u32 npar = a.cnt[1];
+  for (u32 p = blockIdx.x * 8 + slot; p < npar; p += gridDim.x * 8) {
+    const u32 f = a.par_list[a.item_base + p];
+    const FrameInfo fi = a.info[f];
+    if (!(fi.flags & FI_NEED_XXH)) continue;
+    const u8* dst = a.dst_base + frame_dst_off(a, f, fi);
+    const u64 h = xxh64_group<true>(dst, fi.decoded, sub, gmask, lane & ~3u);
+    if (sub == 0) {
+      const u8* src = a.src_base + a.src_off[f];
+      if ((u32)h != ld32(src + fi.trailer_off)) a.result[f] = zerr(ZE_checksum_wrong);
+    }
   }
 }
 
@@ -1001,7 +1052,7 @@ cudaError_t decode_load_dictionary(const u8* d_dict_bytes, u32 size, DictState* 
 }
 
 // grids of the persistent block-parallel kernels: what one wave of the device holds (set by decode_configure)
-static int g_par_grid_huf = 148 * 5, g_par_grid_seq = 148 * 2, g_par_grid_exec = 148 * 8;
+static int g_par_grid_huf = 148 * 5, g_par_grid_seq = 148 * 2, g_par_grid_exec = 148 * 32;   // (exec: in warps)
 size_t decode_unit_arena_count(u64 max_dst_bytes, u64 max_items) { return (size_t)(max_dst_bytes / PAR_UNIT_BYTES + PAR_UNIT_SLACK * (max_items + 2) + 64); }
 
 cudaError_t decode_configure() {
@@ -1016,7 +1067,7 @@ cudaError_t decode_configure() {
     int per = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_huf_blk, 32, sizeof(HufSmem)) == cudaSuccess && per > 0) g_par_grid_huf = sms * per;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_seq_blk, 32, sizeof(SeqSmem)) == cudaSuccess && per > 0) g_par_grid_seq = sms * per;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_exec_big<false>, EXECB_WARPS * 32, 0) == cudaSuccess && per > 0) g_par_grid_exec = sms * per;
+    g_par_grid_exec = sms * 32;
   }
   return cudaFuncSetAttribute(k_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqSmem));
 }
@@ -1046,13 +1097,17 @@ cudaError_t decode_launch_exec(const DecodeArgs& a, cudaStream_t st, int* launch
   if (a.dict) k_exec<true><<<(a.n + (EXEC_THREADS / 32) - 1) / (EXEC_THREADS / 32), EXEC_THREADS, 0, st>>>(a);
   else k_exec<false><<<(a.n + (EXEC_THREADS / 32) - 1) / (EXEC_THREADS / 32), EXEC_THREADS, 0, st>>>(a);
   if (a.units) {
-    if (a.dict) k_exec_big<true><<<g_par_grid_exec, EXECB_WARPS * 32, 0, st>>>(a);
-    else k_exec_big<false><<<g_par_grid_exec, EXECB_WARPS * 32, 0, st>>>(a);
+    if (a.dict) {
+      k_exec_big<true, 4><<<g_par_grid_exec / 4, 128, 0, st>>>(a); k_exec_big<true, 2><<<g_par_grid_exec / 2, 64, 0, st>>>(a); k_exec_big<true, 1><<<g_par_grid_exec, 32, 0, st>>>(a);
+    } else {
+      k_exec_big<false, 4><<<g_par_grid_exec / 4, 128, 0, st>>>(a); k_exec_big<false, 2><<<g_par_grid_exec / 2, 64, 0, st>>>(a); k_exec_big<false, 1><<<g_par_grid_exec, 32, 0, st>>>(a);
+    }
   }
   if (marks) cudaEventRecord(marks[4], st);
   k_xxh<<<(a.n * 4 + 127) / 128, 128, 0, st>>>(a);
+  if (a.units) k_xxh_big<<<148 * 8, 32, 0, st>>>(a);
   if (marks) cudaEventRecord(marks[5], st);
-  if (launches) *launches += a.units ? 3 : 2;
+  if (launches) *launches += a.units ? 6 : 2;
   return cudaGetLastError();
 }
 cudaError_t decode_launch(const DecodeArgs& a, cudaStream_t st, int* launches, cudaEvent_t* marks) {

@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(128) k_enc_xxh(EncodeArgs a) {
   if (f >= a.n) return;
   const u32 r = a.result[f];
   if (is_err(r)) return;
-  const u64 h = xxh64_group(a.src_base + a.src_off[f], a.src_size[f], sub, gmask, lane & ~3u);
+  const u64 h = xxh64_group<false>(a.src_base + a.src_off[f], a.src_size[f], sub, gmask, lane & ~3u);
   if (sub == 0) {
     u8* p = a.dst_base + a.dst_off[f] + r;   // encode_frame_with reserved these 4 bytes
     p[0] = (u8)h; p[1] = (u8)(h >> 8); p[2] = (u8)(h >> 16); p[3] = (u8)(h >> 24);

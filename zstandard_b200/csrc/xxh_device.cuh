@@ -20,6 +20,9 @@ __device__ __forceinline__ u64 ldg64u(const u8* p) {   // unaligned 8-byte load 
   return ((u64)__funnelshift_r(a1, a2, sh) << 32) | __funnelshift_r(a0, a1, sh);
 }
 
+// DEEP: two batches of 16 loads alternate, so that 16 loads are in flight WHILE the other batch feeds the accumulator
+// (for the few long frames of the block-parallel path, where a lane's chain over 32 768 stripes is the kernel's time)
+template <bool DEEP>
 static __device__ u64 xxh64_group(const u8* p, u64 len, u32 sub, unsigned gmask, u32 lead) {
   u64 h;
   const u8* tail = p;
@@ -28,6 +31,25 @@ static __device__ u64 xxh64_group(const u8* p, u64 len, u32 sub, unsigned gmask,
     const u64 stripes = len / 32;
     const u8* q = p + 8 * sub;
     u64 i = 0;
+    if (DEEP && stripes >= 32) {
+      u64 x[16], y[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) x[k] = ldg64u(q + 32 * k);
+      q += 512; i = 16;
+      for (; i + 32 <= stripes; i += 32) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) y[k] = ldg64u(q + 32 * k);
+#pragma unroll
+        for (int k = 0; k < 16; k++) v = xxh_round(v, x[k]);
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = ldg64u(q + 512 + 32 * k);
+#pragma unroll
+        for (int k = 0; k < 16; k++) v = xxh_round(v, y[k]);
+        q += 1024;
+      }
+#pragma unroll
+      for (int k = 0; k < 16; k++) v = xxh_round(v, x[k]);
+    }
     // the accumulator chain is serial; keep 16 independent loads in flight ahead of it
     for (; i + 16 <= stripes; i += 16) {
       u64 x[16];
