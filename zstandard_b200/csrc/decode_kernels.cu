@@ -719,7 +719,7 @@ __global__ void __launch_bounds__(32) k_seq_blk(DecodeArgs a) {
 // 1.8 us per group).  W follows from how many FI_PAR frames the launch holds (execb_warps): few large
 // frames need the parallelism inside a frame, many frames fill the device on their own and a single warp each has no
 // synchronisation cost.  All three instantiations are launched; the two that do not match return at once.
-__host__ __device__ inline u32 execb_warps(u32 npar) { return npar * 4 <= 148 * 32 ? 4 : (npar * 2 <= 148 * 32 ? 2 : 1); }
+__host__ __device__ inline u32 execb_warps(u32 npar) { return npar <= 148 * 7 ? 4 : (npar <= 148 * 16 ? 2 : 1); }   // (7 CTAs of 4 + 1 warps per SM)
 template <int W> struct ExecBigShared {
   volatile u32 wm;                // watermark: frame-relative output bytes that are final (every group before is complete)
   volatile u32 done;              // groups completed in order
@@ -727,6 +727,10 @@ template <int W> struct ExecBigShared {
   volatile u32 flag[4 * W];       // flag[G % RING] == G + 1: group G has been written (RING = 4 W groups may be in flight)
   volatile u32 endPos[4 * W];
   u32 errAt[W], errCode[W];
+  // W == 4 only: a fifth warp hashes the output behind the watermark (the content checksum of a long frame is a serial
+  // chain of its own: done here it costs no time of its own, in k_xxh_big it did)
+  volatile u32 left;              // worker warps that have finished the frame
+  u32 hashed; u64 hv[4];          // bytes hashed and the four XXH64 accumulators when the hashing warp stops
 };
 // Group G (ending at output position endPos) has been written: mark it, then move the chain as far as it goes.
 template <int W>
@@ -768,22 +772,59 @@ __device__ __forceinline__ bool chain_wait_move(ExecBigShared<W>& sh, u32 G, u32
 }
 
 template <bool DICT, int W>
-__global__ void __launch_bounds__(W * 32, 32 / W) k_exec_big(DecodeArgs a) {
+__global__ void __launch_bounds__((W + (W == 4)) * 32, W == 4 ? 7 : 32 / W) k_exec_big(DecodeArgs a) {
   __shared__ ExecBigShared<W> sh;
+  constexpr bool HASH = W == 4;
   const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const u32 npar = a.cnt[1];
   if (execb_warps(npar) != (u32)W) return;
   const BlockUnit* const sliceUnits = a.units + unit_slice_base(a);
   for (u32 p = blockIdx.x; p < npar; p += gridDim.x) {
     __syncthreads();
-    if (threadIdx.x == 0) { sh.wm = 0; sh.done = 0; sh.errG = 0xFFFFFFFFu; }
+    if (threadIdx.x == 0) { sh.wm = 0; sh.done = 0; sh.errG = 0xFFFFFFFFu; sh.left = 0; sh.hashed = 0; }
     if (threadIdx.x < (4 * W)) sh.flag[threadIdx.x] = 0;
-    if (lane == 0) sh.errAt[warp] = 0xFFFFFFFFu;
+    if (lane == 0 && warp < W) sh.errAt[warp] = 0xFFFFFFFFu;
     __syncthreads();
     const u32 f = a.par_list[a.item_base + p];
     const FrameInfo fi = a.info[f];
     const u8* src = a.src_base + a.src_off[f]; const u32 size = a.src_size[f];
     u8* dst = a.dst_base + frame_dst_off(a, f, fi); const u32 cap = frame_cap(a, f, fi);
+    if (HASH && warp == W) {
+      // ---- the hashing warp: XXH64 stripes of everything below the watermark (all lanes run the chain of accumulator
+      //      lane & 3 on the same addresses; lanes 0-3 deliver) ----
+      if (fi.flags & FI_CHECKSUM) {
+        const u32 sub = lane & 3;
+        u64 v = sub == 0 ? XP1 + XP2 : (sub == 1 ? XP2 : (sub == 2 ? 0 : 0 - XP1));
+        const u8* q = dst + 8 * sub; u32 hashed = 0;
+        while (true) {
+          const u32 left = sh.left;                                                // before the watermark: all gone => it is final
+          __threadfence_block();
+          const u32 wmNow = __shfl_sync(FULLMASK, sh.wm, 0);
+          __threadfence_block();
+          u32 avail = (wmNow - hashed) >> 5;
+          if (avail >= 8) {
+            for (; avail >= 8; avail -= 8) {
+              u64 x[8];
+#pragma unroll
+              for (int k = 0; k < 8; k++) x[k] = ldg64u(q + 32 * k);
+#pragma unroll
+              for (int k = 0; k < 8; k++) v = xxh_round(v, x[k]);
+              q += 256; hashed += 256;
+            }
+            continue;
+          }
+          if (__shfl_sync(FULLMASK, left, 0) == (u32)W) {
+            for (; avail; avail--) { v = xxh_round(v, ldg64u(q)); q += 32; hashed += 32; }
+            break;
+          }
+          __nanosleep(200);
+        }
+        if (lane < 4) sh.hv[lane] = v;
+        if (lane == 0) sh.hashed = hashed;
+      }
+      __syncthreads();
+      continue;
+    }
     const u8* litScratch = lit_region(a, f, fi);
     const SeqRec* recs = seq_region(a, f, fi);
     const BlockUnit* units = sliceUnits + fi.unit_base;
@@ -959,6 +1000,7 @@ __global__ void __launch_bounds__(W * 32, 32 / W) k_exec_big(DecodeArgs a) {
       pos += bh.csize;
       if (bh.last) break;
     }
+    if (HASH) { __threadfence_block(); __syncwarp(); if (lane == 0) atomicAdd((u32*)&sh.left, 1u); }
     __syncthreads();
     if (warp != 0) continue;
     // a failed record check comes before anything the warps met afterwards; without one, no warp left early and all
@@ -991,6 +1033,12 @@ __global__ void __launch_bounds__(W * 32, 32 / W) k_exec_big(DecodeArgs a) {
     }
     if (lane == 0) {
       u32 res = err ? zerr(err) : (tailErr ? zerr(tailErr) : fi.out_base + (u32)op);
+      if (HASH && needXxh && sh.hashed == (op & ~31u)) {
+        // the hashing warp has covered every stripe: finish the digest here (:2078-2082; k_xxh_big then skips the frame)
+        const u64 h = xxh64_finish(sh.hv[0], sh.hv[1], sh.hv[2], sh.hv[3], dst, op);
+        if ((u32)h != ld32(src + trailer)) res = zerr(ZE_checksum_wrong);
+        needXxh = false;
+      }
       a.result[f] = res;
       a.info[f].trailer_off = trailer; a.info[f].decoded = (u32)op; a.info[f].next_off = nextOff;
       a.info[f].flags = fi.flags | (needXxh ? FI_NEED_XXH : 0);
@@ -1098,9 +1146,9 @@ cudaError_t decode_launch_exec(const DecodeArgs& a, cudaStream_t st, int* launch
   else k_exec<false><<<(a.n + (EXEC_THREADS / 32) - 1) / (EXEC_THREADS / 32), EXEC_THREADS, 0, st>>>(a);
   if (a.units) {
     if (a.dict) {
-      k_exec_big<true, 4><<<g_par_grid_exec / 4, 128, 0, st>>>(a); k_exec_big<true, 2><<<g_par_grid_exec / 2, 64, 0, st>>>(a); k_exec_big<true, 1><<<g_par_grid_exec, 32, 0, st>>>(a);
+      k_exec_big<true, 4><<<g_par_grid_exec / 32 * 7, 160, 0, st>>>(a); k_exec_big<true, 2><<<g_par_grid_exec / 2, 64, 0, st>>>(a); k_exec_big<true, 1><<<g_par_grid_exec, 32, 0, st>>>(a);
     } else {
-      k_exec_big<false, 4><<<g_par_grid_exec / 4, 128, 0, st>>>(a); k_exec_big<false, 2><<<g_par_grid_exec / 2, 64, 0, st>>>(a); k_exec_big<false, 1><<<g_par_grid_exec, 32, 0, st>>>(a);
+      k_exec_big<false, 4><<<g_par_grid_exec / 32 * 7, 160, 0, st>>>(a); k_exec_big<false, 2><<<g_par_grid_exec / 2, 64, 0, st>>>(a); k_exec_big<false, 1><<<g_par_grid_exec, 32, 0, st>>>(a);
     }
   }
   if (marks) cudaEventRecord(marks[4], st);

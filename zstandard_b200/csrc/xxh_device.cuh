@@ -74,5 +74,21 @@ static __device__ u64 xxh64_group(const u8* p, u64 len, u32 sub, unsigned gmask,
   return h;
 }
 
+// the digest from the four accumulators after len / 32 stripes of p[0..len) (XxHash.cs:1105-1161)
+static __device__ u64 xxh64_finish(u64 v1, u64 v2, u64 v3, u64 v4, const u8* p, u64 len) {
+  u64 h; const u8* tail = p;
+  if (len >= 32) {
+    h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
+    h = xxh_merge(h, v1); h = xxh_merge(h, v2); h = xxh_merge(h, v3); h = xxh_merge(h, v4);
+    tail = p + (len / 32) * 32;
+  } else h = XP5;
+  h += len;
+  const u8* end = p + len;
+  while (tail + 8 <= end) { h ^= xxh_round(0, ldg64u(tail)); h = rotl64(h, 27) * XP1 + XP4; tail += 8; }
+  if (tail + 4 <= end) { h ^= (u64)ld32(tail) * XP1; h = rotl64(h, 23) * XP2 + XP3; tail += 4; }
+  while (tail < end) { h ^= (*tail) * XP5; h = rotl64(h, 11) * XP1; tail++; }
+  h ^= h >> 33; h *= XP2; h ^= h >> 29; h *= XP3; h ^= h >> 32;
+  return h;
+}
 
 }  // namespace zb
