@@ -719,6 +719,9 @@ __global__ void __launch_bounds__(32) k_seq_blk(DecodeArgs a) {
 // 1.8 us per group).  W follows from how many FI_PAR frames the launch holds (execb_warps): few large
 // frames need the parallelism inside a frame, many frames fill the device on their own and a single warp each has no
 // synchronisation cost.  All three instantiations are launched; the two that do not match return at once.
+#ifndef EXECB_SLEEP
+#define EXECB_SLEEP 100   // ns between two looks at the chain state while waiting (polling warps cost issue slots)
+#endif
 __host__ __device__ inline u32 execb_warps(u32 npar) { return npar <= 148 * 7 ? 4 : (npar <= 148 * 16 ? 2 : 1); }   // (7 CTAs of 4 + 1 warps per SM)
 template <int W> struct ExecBigShared {
   volatile u32 wm;                // watermark: frame-relative output bytes that are final (every group before is complete)
@@ -760,14 +763,14 @@ template <int W>
 __device__ __forceinline__ bool chain_admit(ExecBigShared<W>& sh, u32 G, u32 lane) {
   if (W == 1) return true;
   u32 ok = 1;
-  if (lane == 0) { while (G >= sh.done + 4 * W) { if (sh.errG < G) { ok = 0; break; } __nanosleep(20); } }
+  if (lane == 0) { while (G >= sh.done + 4 * W) { if (sh.errG < G) { ok = 0; break; } __nanosleep(EXECB_SLEEP); } }
   return __shfl_sync(FULLMASK, ok, 0) != 0;
 }
 // waits until the watermark has moved past `seen`; false = an earlier group failed
 template <int W>
 __device__ __forceinline__ bool chain_wait_move(ExecBigShared<W>& sh, u32 G, u32 seen, u32 lane) {
   u32 ok = 1;
-  if (lane == 0) { while (sh.wm == seen) { if (sh.errG < G) { ok = 0; break; } __nanosleep(20); } }
+  if (lane == 0) { while (sh.wm == seen) { if (sh.errG < G) { ok = 0; break; } __nanosleep(EXECB_SLEEP); } }
   return __shfl_sync(FULLMASK, ok, 0) != 0;
 }
 
@@ -817,7 +820,7 @@ __global__ void __launch_bounds__((W + (W == 4)) * 32, W == 4 ? 7 : 32 / W) k_ex
             for (; avail; avail--) { v = xxh_round(v, ldg64u(q)); q += 32; hashed += 32; }
             break;
           }
-          __nanosleep(200);
+          __nanosleep(4 * EXECB_SLEEP);
         }
         if (lane < 4) sh.hv[lane] = v;
         if (lane == 0) sh.hashed = hashed;
