@@ -270,6 +270,52 @@ class ZStdDecompress:
         return (ctx or default_context()).decompress_batch(srcs, dsts)
 
 
+class ZstdDecompressor:
+    """Mirror of the reference's Java class `com.epam.deltix.zstd.ZstdDecompressor`
+    (java/src/main/java/com/epam/deltix/zstd/ZstdDecompressor.java:18-34) over the same C ABI — what the JNI binding in
+    bindings/java/ does on a box with a JDK.  `decompress` returns the bytes written and raises RuntimeError where the
+    reference throws (Util.java:32-40); `maxOutputLength == 0` returns 0 without looking at the input
+    (ZstdFrameDecompressor.java:164-166).  `getDecompressedSize` follows ZstdFrameDecompressor.java:922-940: RuntimeError
+    on a bad magic number, -1 when the header carries no content size.  The decoding itself follows the C# reference
+    (the Java port is a second statement of the same format with a few extra restrictions)."""
+
+    def __init__(self, ctx=None):
+        self._ctx = ctx
+
+    def decompress(self, input, inputOffset, inputLength, output, outputOffset, maxOutputLength):
+        if maxOutputLength == 0:
+            return 0
+        sv, dv = _as_u8(input), _as_u8(output, writable=True)
+        if inputOffset < 0 or inputLength < 0 or inputOffset + inputLength > sv.size or outputOffset < 0 or maxOutputLength < 0 \
+                or outputOffset + maxOutputLength > dv.size:
+            raise IndexError("offset / length outside the array")
+        ctx = self._ctx or default_context()
+        r = int(load_library().zstdb200_decompress(ctx.handle, dv.ctypes.data + outputOffset, int(maxOutputLength),
+                                                   (sv.ctypes.data + inputOffset) if inputLength else None, int(inputLength)))
+        if is_error(r):
+            raise RuntimeError("%s: offset=%d" % (error_name(r), inputOffset))
+        return r
+
+    def decompressBatch(self, inputs, outputs):
+        """[(array, offset, length)] x [(array, offset, maxOutputLength)] -> result codes (one bad frame does not fail the batch)."""
+        srcs = [_as_u8(a)[o:o + n] for a, o, n in inputs]
+        dsts = [_as_u8(a, writable=True)[o:o + n] for a, o, n in outputs]
+        return (self._ctx or default_context()).decompress_batch(srcs, dsts)
+
+    @staticmethod
+    def getDecompressedSize(input, offset, length):
+        v = _as_u8(input)
+        if length < 4 or offset < 0 or offset + length > v.size:
+            raise RuntimeError("Not enough input bytes: offset=%d" % offset)
+        head = v[offset:offset + min(length, 18)]
+        magic = int.from_bytes(head[:4].tobytes(), "little")
+        if magic != 0xFD2FB528:
+            raise RuntimeError("Invalid magic prefix: %x: offset=%d" % (magic, offset))
+        if head.size >= 5 and (int(head[4]) >> 6) == 0 and not (int(head[4]) & 0x20):
+            return -1
+        return int(load_library().zstdb200_get_decompressed_size(head.ctypes.data, head.size))
+
+
 class ZStdCompress:
     """Compressor added by this project (the reference has none); same calling shape."""
 
