@@ -431,6 +431,15 @@ struct WarpMatcher {
     const u32 bpos = (u32)(bstart - src), bend = bpos + bsize;
     if (blk > 0) { rep1 = 0; rep2 = 0; }
     u16* tabL = tab.data(); u16* tabS = tab.data() + (1u << hlogL);
+    {
+      // every block is an independent unit of the match kernel: cleared tables, primed with the 16 KiB before the block
+      std::fill(tab.begin(), tab.end(), (u16)0);
+      const u32 b0 = (u32)(bstart - src);
+      if (blk > 0) for (u32 q = b0 - 16384u; q < b0; q++) {        // ascending: the last position of a hash value is the one kept
+        const u64 v = ld64(src + q);
+        tabL[h64(v, hlogL, dfast ? 8 : mls)] = (u16)q; if (dfast) tabS[h64(v, hlogS, mls)] = (u16)q;
+      }
+    }
     u32 anchor = bpos; const u32 ilimit = bend - 8; u32 p0 = bpos + (bpos == 0 ? 1 : 0);
     while (p0 < ilimit) {
       const u32 step = 1 + ((p0 - anchor) >> 8);

@@ -24,6 +24,7 @@ namespace zb {
 
 #define FULLMASK 0xFFFFFFFFu
 static constexpr u32 kBlockSeqCap = BLOCKSIZE_MAX / 4 + 64;
+#define ENC_PRIME 16384u   // bytes before a block that prime its match tables (multiple of 32, <= BLOCKSIZE_MAX)
 
 struct BlockMeta { u32 nseq, nlits; };
 
@@ -78,14 +79,35 @@ __global__ void __launch_bounds__(32) k_enc_match(EncodeArgs a, EncodeScratch sc
   u16* const tabL = tab; u16* const tabS = tab + (1u << hlogL);
   const u32 lane = threadIdx.x;
   const u32 tw = (1u << hlogL) + (DFAST ? (1u << hlogS) : 0);
-  for (u32 f = blockIdx.x; f < a.n; f += gridDim.x) {
+  // The unit of work is one BLOCK (<= 128 KiB) of one chunk: blocks of a chunk are matched independently, so a batch of
+  // few large chunks spreads over as many warps as a batch of many small ones.  A block that is not the chunk's first
+  // starts from a table primed with the ENC_PRIME bytes before it (the positions a table of this size would still
+  // remember), and — as before — without repeat offsets.
+  const u32 perChunk = a.max_src_size > BLOCKSIZE_MAX ? (a.max_src_size + BLOCKSIZE_MAX - 1) / BLOCKSIZE_MAX : 1;
+  for (u64 unit = blockIdx.x; unit < (u64)a.n * perChunk; unit += gridDim.x) {
+    const u32 f = (u32)(unit / perChunk), blk = (u32)(unit % perChunk), bpos = blk * BLOCKSIZE_MAX;
     const u8* src = a.src_base + a.src_off[f]; const u32 size = a.src_size[f];
+    if (blk > 0 && bpos >= size) continue;
     u8* const lits0 = lit_base(a, sc, f); u32* const seqs0 = seq_base(a, sc, f); BlockMeta* const meta = meta_base(a, sc, f);
     for (u32 i = lane; i < tw / 2; i += 32) ((u32*)tab)[i] = 0;
     __syncwarp();
+    if (blk > 0) {
+      for (u32 q0 = bpos - ENC_PRIME; q0 < bpos; q0 += 32) {
+        const u32 q = q0 + lane;
+        const u64 v = ldu64(src + q);
+        const u32 hL = hash64(v, hlogL, DFAST ? 8 : mls);
+        const unsigned mL = __match_any_sync(FULLMASK, hL);
+        if ((mL >> lane) == 1) tabL[hL] = (u16)q;                   // the last position of each hash group is the one kept
+        if (DFAST) {
+          const u32 hS = hash64(v, hlogS, mls);
+          const unsigned mS = __match_any_sync(FULLMASK, hS);
+          if ((mS >> lane) == 1) tabS[hS] = (u16)q;
+        }
+        __syncwarp();
+      }
+    }
     u32 rep1 = 1, rep2 = 4;
-    u32 blk = 0, bpos = 0;
-    do {
+    {
       const u32 bsize = size - bpos < BLOCKSIZE_MAX ? size - bpos : BLOCKSIZE_MAX;
       const u32 bend = bpos + bsize;
       u8* const lits = lits0 + (size_t)blk * BLOCKSIZE_MAX; u32* const seqs = seqs0 + 2 * (size_t)blk * kBlockSeqCap;
@@ -210,8 +232,7 @@ __global__ void __launch_bounds__(32) k_enc_match(EncodeArgs a, EncodeScratch sc
         nlits += ll;
       }
       if (lane == 0) { meta[blk].nseq = nseq; meta[blk].nlits = nlits; }
-      bpos = bend; blk++;
-    } while (bpos < size);
+    }
   }
 }
 
@@ -648,7 +669,8 @@ cudaError_t encode_launch(const EncodeArgs& a, EncodeScratch& s, cudaStream_t st
   const size_t smem = ((size_t)(1u << hlogL) + (dfast ? (1u << hlogS) : 0)) * 2;
   const u32 capSm = envPerSm ? (u32)envPerSm : 32;
   u32 perSm = (u32)((220 * 1024) / (smem + 1024)); if (perSm > capSm) perSm = capSm;
-  u32 grid = (u32)s.sms * perSm; if (grid > a.n) grid = a.n;
+  const u64 units = (u64)a.n * (a.max_src_size > BLOCKSIZE_MAX ? (a.max_src_size + BLOCKSIZE_MAX - 1) / BLOCKSIZE_MAX : 1);
+  u32 grid = (u32)s.sms * perSm; if (grid > units) grid = (u32)units;
   if (marks) cudaEventRecord(marks[0], st);
   if (dfast) k_enc_match<true><<<grid, 32, smem, st>>>(a, s, hlogL, hlogS, mls);
   else k_enc_match<false><<<grid, 32, smem, st>>>(a, s, hlogL, hlogS, mls);
