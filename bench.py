@@ -23,6 +23,7 @@ The default line (decode64k, log text, no --chunk) also carries
                   per-kernel ms, roofline fractions (the reference has no compressor: the ratio band is unpinned by it)
   e2e_pageable    the same C-ABI call on pageable caller memory (what a managed byte[] is): one array pair / one array per frame
   single_call_us  median latency of zstdb200_decompress on one 64 KiB frame
+  multi_block     (N = 1) tick records as 256 KiB / 1 MiB frames (2 / 8 blocks each, configs[4]'s large end): value, e2e, per-kernel ms
   e2e_single_ctx  (N > 1, under torchrun) rank 0 alone driving ONE context over all N devices on N x the workload
 The other BASELINE.json configs are the same two workloads with other shapes: --corpus mixed (configs[3]), --corpus tick
 --chunk 4096..1048576 (configs[4]); profiles/ holds the lines measured for them.
@@ -510,6 +511,24 @@ def main():
         compress["workload"] = (f"compress128k: {total} B/GPU of log text in 128 KiB chunks, one frame each with XXH64; ratio comparator = libzstd 1.5.5 at the "
                                 "same level (the reference has no compressor: ratio parity is unpinned by the reference)")
 
+    # ---------------- multi-block frames (BASELINE.json configs[4], large end): tick records as 256 KiB and 1 MiB frames ----------------
+    multi = None
+    if decode and args.corpus == "log" and not args.chunk and not args.no_extras and not args.dictionary and world == 1:
+        multi = {}
+        for chunk in (262144, 1048576):
+            a2 = argparse.Namespace(**vars(args)); a2.corpus = "tick"; a2.chunk = chunk
+            wm = prepare(a2, g.rank)
+            k_steps = max(2, min(args.steps, 3))
+            mm = measure(g, a2, wm, k_steps, 3)
+            multi[f"tick_{chunk // 1024}k"] = {
+                "value": round(wm["total"] * k_steps / (mm["ms"] * 1e-3) / 1e9, 3), "unit": "GB/s",
+                "e2e": round(wm["total"] * k_steps / mm["e2e_s"] / 1e9, 3), "frames": wm["n"], "blocks_per_frame": chunk // 131072,
+                "libzstd_ratio": round(wm["total"] / wm["ref_compressed_bytes"], 4),
+                "kernel_ms": {k: round(v, 3) for k, v in mm["kernel_ms"].items()}, "gpu_launches": mm["launches"]}
+            del wm, mm
+        multi["workload"] = (f"decode of {total} B/GPU of libzstd-1.5.5 level-3 tick records held as 256 KiB / 1 MiB frames (2 / 8 blocks each): the "
+                             "block-parallel path (DESIGN.md 3b); kernel_ms includes the _blk / _big kernels under their stage's name")
+
     single = None
     if world > 1 and decode and not args.no_extras:
         g.barrier()
@@ -564,6 +583,8 @@ def main():
             line["single_call_us"] = round(m["single_call_us"], 1)
         if compress:
             line["compress"] = compress
+        if multi:
+            line["multi_block"] = multi
         if single:
             line["e2e_single_ctx"] = single
         print(json.dumps(line), flush=True)
