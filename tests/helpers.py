@@ -80,6 +80,7 @@ class HostSim:
                                           ctypes.POINTER(ctypes.c_uint32), ctypes.c_void_p]
         h.hostsim_set_par.argtypes = [ctypes.c_int]
         h.hostsim_par_frames.restype = ctypes.c_int
+        h.hostsim_set_huf_root.argtypes = [ctypes.c_int]
         self.lib = h
 
     def set_par(self, on):
@@ -88,6 +89,11 @@ class HostSim:
 
     def par_frames(self):
         return self.lib.hostsim_par_frames()
+
+    def set_huf_root(self, root_log):
+        """Root-table log of the replayed Huffman stage: 9 (k_huf<9>, frames of few literals; the default here because it
+        exercises the long-code path on every larger table) or 11 (k_huf<11> / k_huf_blk)."""
+        self.lib.hostsim_set_huf_root(int(root_log))
 
     def decompress(self, frame, cap, oracle):
         """One item through the replayed stages, one pass per data frame; the oracle's XXH64 stands in for k_xxh."""

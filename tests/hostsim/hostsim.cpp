@@ -39,15 +39,18 @@ struct Sim {
 // mirrors k_huf for one frame; returns first failing block / code through fi
 // the replay's dictionary (hostsim_set_dict): what zstdb200_load_dictionary prepares on the device
 static DictState g_dict; static std::vector<u8> g_dictBytes; static bool g_haveDict = false;
+static u32 g_rootLog = HUF_ROOT_SMALL;   // hostsim_set_huf_root: the Huffman kernels run with root tables of 2^9 (small frames) or 2^11 cells
 static const DictState* cur_dict() { return g_haveDict ? &g_dict : nullptr; }
 
 void sim_huf(const u8* src, u32 size, FrameInfo& fi, u8* lit, u64 litCap) {
-  alignas(16) static thread_local u16 dt[1 << HUF_TABLE_LOG]; static thread_local HufBuildWk wk; alignas(16) u32 ringBuf[ZB_RING_WORDS];
-  static thread_local u8 sideMem[256], slotMem[256]; const u8* side = nullptr;
-  u32 pos = fi.body_off, blk = 0; u64 litRun = 0; u32 tableLog = 0; bool haveTable = false;
+  // as the kernels: a root table (shared memory there) plus the full table for the codes longer than the root log
+  alignas(16) static thread_local u16 root[1 << HUF_TABLE_LOG], fullMem[1 << HUF_TABLE_LOG]; static thread_local HufBuildWk wk; alignas(16) u32 ringBuf[ZB_RING_WORDS];
+  static thread_local u8 sideMem[256], slotMem[256]; static thread_local HufFseScratch fs;
+  HufTabs T{root, g_rootLog, fullMem, sideMem, 0};
+  u32 pos = fi.body_off, blk = 0; u64 litRun = 0; bool haveTable = false;
   if (const DictState* ds = cur_dict()) if (ds->hasEntropy) {
-    memcpy(dt, ds->huf, sizeof(ds->huf)); tableLog = ds->hufLog; haveTable = true;
-    if (tableLog > HUF_TABLE_LOG) { memcpy(sideMem, ds->hufSide, 256); side = sideMem; }
+    for (u32 sub = 0; sub < 4; sub++) huf_root_from_full(root, g_rootLog, ds->huf, ds->hufLog, sub, 4);
+    T.full = ds->huf; T.side = ds->hufSide; T.log = ds->hufLog; haveTable = true;
   }
   while (true) {
     BlockHdr bh;
@@ -67,20 +70,22 @@ void sim_huf(const u8* src, u32 size, FrameInfo& fi, u8* lit, u64 litCap) {
           if (!lh.single && (lh.litSize == 0 || bodySize == 0)) ok = false;
           u32 hdr = 0, nbSym = 0, tl = 0;
           if (ok) {
-            u32 e = huf_read_weights(body, bodySize, wk, *reinterpret_cast<HufFseScratch*>(dt), slotMem, &hdr, &tl, &nbSym);
+            u32 e = huf_read_weights(body, bodySize, wk, fs, slotMem, &hdr, &tl, &nbSym);
             if (!e && hdr >= bodySize) e = ZE_srcSize_wrong;
             if (e) ok = false;
           }
           if (ok) {
-            for (u32 sub = 0; sub < 4; sub++) huf_fill_table(dt, sideMem, wk, slotMem, tl, nbSym, sub, 4);
-            tableLog = tl; haveTable = true; body += hdr; bodySize -= hdr; side = tl > HUF_TABLE_LOG ? sideMem : nullptr;
+            for (u32 sub = 0; sub < 4; sub++) huf_fill_root(root, g_rootLog, wk, slotMem, tl, nbSym, sub, 4);
+            if (tl > g_rootLog) for (u32 sub = 0; sub < 4; sub++) huf_fill_table(fullMem, sideMem, wk, slotMem, tl, nbSym, sub, 4, g_rootLog);
+            T.full = fullMem; T.side = sideMem; T.log = tl;
+            haveTable = true; body += hdr; bodySize -= hdr;
           }
         }
         if (ok) {
-          if (lh.single) ok = dry ? huf_check_stream(body, bodySize, lh.litSize, dt, tableLog, side) : huf_decode_stream(body, bodySize, lit + litRun, lh.litSize, dt, tableLog, ringBuf, side);
+          if (lh.single) ok = dry ? huf_check_stream(body, bodySize, lh.litSize, T) : huf_decode_stream(body, bodySize, lit + litRun, lh.litSize, T, ringBuf);
           else for (u32 sub = 0; sub < 4; sub++) {
             HufStream st; bool good = huf_split4(body, bodySize, lh.litSize, sub, st);
-            if (good) good = dry ? huf_check_stream(st.src, st.len, st.count, dt, tableLog, side) : huf_decode_stream(st.src, st.len, lit + litRun + st.outOfs, st.count, dt, tableLog, ringBuf, side);
+            if (good) good = dry ? huf_check_stream(st.src, st.len, st.count, T) : huf_decode_stream(st.src, st.len, lit + litRun + st.outOfs, st.count, T, ringBuf);
             if (!good) ok = false;
           }
         }
@@ -182,19 +187,20 @@ static int g_parFrames = 0;      // data frames that took the block-parallel rep
 
 // mirrors k_huf_blk for one unit
 void sim_huf_unit(const u8* src, BlockUnit& u, const BlockUnit* frameUnits, u8* litRegion) {
-  alignas(16) static thread_local u16 dt[1 << HUF_TABLE_LOG]; static thread_local HufBuildWk wk; alignas(16) u32 ringBuf[ZB_RING_WORDS];
-  static thread_local u8 sideMem[256], slotMem[256]; const u8* side = nullptr;
+  alignas(16) static thread_local u16 root[1 << HUF_TABLE_LOG], fullMem[1 << HUF_TABLE_LOG]; static thread_local HufBuildWk wk; alignas(16) u32 ringBuf[ZB_RING_WORDS];
+  static thread_local u8 sideMem[256], slotMem[256]; static thread_local HufFseScratch fs;
+  HufTabs T{root, g_rootLog, fullMem, sideMem, 0};
   const u8* bp = src + u.body;
   LitHdr lh; bool needs;
   read_lit_hdr(bp, u.csize, lh, &needs);
   if (lh.type < 2) return;
   u8* lit = litRegion + u.lit_off;
-  bool ok = true; u32 tableLog = 0;
+  bool ok = true;
   const u8* body = bp + lh.lhSize; u32 bodySize = lh.litCSize;
   if (lh.type == 3 && u.huf_def == DEF_DICT) {
     const DictState* ds = cur_dict();
-    memcpy(dt, ds->huf, sizeof(ds->huf)); tableLog = ds->hufLog;
-    if (tableLog > HUF_TABLE_LOG) { memcpy(sideMem, ds->hufSide, 256); side = sideMem; }
+    for (u32 sub = 0; sub < 4; sub++) huf_root_from_full(root, g_rootLog, ds->huf, ds->hufLog, sub, 4);
+    T.full = ds->huf; T.side = ds->hufSide; T.log = ds->hufLog;
   } else {
     const u8* tb = body; u32 tbSize = bodySize;
     if (lh.type == 3) {
@@ -205,21 +211,22 @@ void sim_huf_unit(const u8* src, BlockUnit& u, const BlockUnit* frameUnits, u8* 
     } else if (!lh.single && (lh.litSize == 0 || bodySize == 0)) ok = false;
     u32 hdr = 0, nbSym = 0, tl = 0;
     if (ok) {
-      u32 e = huf_read_weights(tb, tbSize, wk, *reinterpret_cast<HufFseScratch*>(dt), slotMem, &hdr, &tl, &nbSym);
+      u32 e = huf_read_weights(tb, tbSize, wk, fs, slotMem, &hdr, &tl, &nbSym);
       if (!e && hdr >= tbSize) e = ZE_srcSize_wrong;
       if (e) ok = false;
     }
     if (ok) {
-      for (u32 sub = 0; sub < 4; sub++) huf_fill_table(dt, sideMem, wk, slotMem, tl, nbSym, sub, 4);
-      tableLog = tl; side = tl > HUF_TABLE_LOG ? sideMem : nullptr;
+      for (u32 sub = 0; sub < 4; sub++) huf_fill_root(root, g_rootLog, wk, slotMem, tl, nbSym, sub, 4);
+      if (tl > g_rootLog) for (u32 sub = 0; sub < 4; sub++) huf_fill_table(fullMem, sideMem, wk, slotMem, tl, nbSym, sub, 4, g_rootLog);
+      T.log = tl;
       if (lh.type == 2) { body += hdr; bodySize -= hdr; }
     }
   }
   if (ok) {
-    if (lh.single) ok = huf_decode_stream(body, bodySize, lit, lh.litSize, dt, tableLog, ringBuf, side);
+    if (lh.single) ok = huf_decode_stream(body, bodySize, lit, lh.litSize, T, ringBuf);
     else for (u32 sub = 0; sub < 4; sub++) {
       HufStream st; bool good = huf_split4(body, bodySize, lh.litSize, sub, st);
-      if (good) good = huf_decode_stream(st.src, st.len, lit + st.outOfs, st.count, dt, tableLog, ringBuf, side);
+      if (good) good = huf_decode_stream(st.src, st.len, lit + st.outOfs, st.count, T, ringBuf);
       if (!good) ok = false;
     }
   }
@@ -365,6 +372,7 @@ extern "C" uint32_t hostsim_decompress2(uint8_t* dst_in, uint32_t capAll, const 
   }
 }
 extern "C" void hostsim_set_par(int on) { g_par = on; }
+extern "C" void hostsim_set_huf_root(int rootLog) { g_rootLog = (u32)rootLog; }
 extern "C" int hostsim_par_frames() { return g_parFrames; }
 extern "C" uint32_t hostsim_decompress(uint8_t* dst, uint32_t cap, const uint8_t* src_in, uint32_t size, uint32_t* trailer_off, int* need_xxh) {
   uint32_t lastBase;

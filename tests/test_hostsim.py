@@ -148,3 +148,28 @@ def test_large_window_frames_use_the_look_ahead_sequence_loop(hostsim, oracle):
             assert ro == rh and oo == oh, (bytes(b).hex()[:80], cap, hex(ro), hex(rh))
             n_long_fail += helpers.is_err(ro)
     assert n_long_fail > 300
+
+
+def test_both_root_table_sizes_of_the_huffman_stage(hostsim, oracle):
+    """The Huffman kernels keep a root table of 2^9 (frames of few literals) or 2^11 cells in shared memory and look longer
+    codes up in the full table (zb_format.cuh huf_fill_root, zb_decode.cuh huf_cell).  The replay defaults to 2^9, which sends
+    every code of 10+ bits through the long path; this runs valid, damaged and log-12 frames with 2^11 as well."""
+    rng = random.Random(5)
+    frames = helpers.make_frames(203, 80)
+    try:
+        for root_log in (11, 9):
+            hostsim.set_huf_root(root_log)
+            for frame, data in frames:
+                ro, oo, _ = oracle.decompress(frame, len(data))
+                rh, oh = hostsim.decompress(frame, len(data), oracle)
+                assert ro == rh and oo == oh, (root_log, len(data))
+                if len(frame) > 12:
+                    b = helpers.mutate(rng, frame)
+                    ro, oo, _ = oracle.decompress(b, len(data))
+                    rh, oh = hostsim.decompress(b, len(data), oracle)
+                    assert ro == rh and oo == oh, (root_log, "mutated", len(data))
+            for four in (True, False):
+                frame, plain = helpers.huf12_frame(700, four, seed=9, raw_prefix=0)
+                assert hostsim.decompress(frame, len(plain), oracle) == (len(plain), plain)
+    finally:
+        hostsim.set_huf_root(9)

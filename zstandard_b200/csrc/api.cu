@@ -55,6 +55,7 @@ struct Device {
   FrameInfo* d_info = nullptr; u8* d_lit = nullptr; SeqRec* d_seq = nullptr;
   u32* d_more = nullptr;                        // per-stream counters of items with another data frame to decode (DecodeArgs::more)
   BlockUnit* d_units = nullptr; u32* d_parList = nullptr; u32* d_cnt = nullptr;   // block-parallel path of multi-block frames (DecodeArgs::units / par_list / cnt, 2 counters per stream)
+  u8* d_hufFull = nullptr; size_t hufFullBytes = 0;   // full Huffman tables of the resident frames (DecodeArgs::huf_full), one region per stream
   u8* d_dict = nullptr; size_t dictCap = 0; DictState* d_dictState = nullptr; bool dictOn = false;   // zstdb200_load_dictionary
   EncodeScratch enc;                            // encoder arenas (encode_kernels.cuh)
   // pinned host memory
@@ -110,7 +111,10 @@ int alloc_device(zstdb200_ctx* ctx, Device& d) {
   CK(cudaMalloc(&d.d_seq, decode_seq_arena_bytes(ctx->dstSpan, items)));
   CK(cudaMalloc(&d.d_units, decode_unit_arena_count(ctx->dstSpan, items) * sizeof(BlockUnit)));
   CK(cudaMalloc(&d.d_parList, (items + 1) * 4));
-  CK(cudaMalloc(&d.d_cnt, NSTREAMS * 2 * 4));
+  CK(cudaMalloc(&d.d_cnt, NSTREAMS * 4 * 4));
+  CK(decode_configure());
+  d.hufFullBytes = align_up(decode_huf_full_bytes(decode_huf_ctas()), 256);
+  CK(cudaMalloc(&d.d_hufFull, d.hufFullBytes * NSTREAMS));
   CK(cudaMallocHost(&d.h_src, ctx->srcCap + 256)); CK(cudaMallocHost(&d.h_dst, ctx->srcCap + 256));
   CK(cudaMallocHost(&d.h_desc, items * 24 + 64));
   CK(decode_configure());
@@ -124,7 +128,7 @@ void free_device(Device& d) {
   for (auto& s : d.stream) if (s) cudaStreamSynchronize(s);
   cudaFree(d.d_src); cudaFree(d.d_dst); cudaFree(d.d_desc);
   cudaFree(d.d_info); cudaFree(d.d_lit); cudaFree(d.d_seq); cudaFree(d.d_more); cudaFreeHost(d.h_more);
-  cudaFree(d.d_units); cudaFree(d.d_parList); cudaFree(d.d_cnt);
+  cudaFree(d.d_units); cudaFree(d.d_parList); cudaFree(d.d_cnt); cudaFree(d.d_hufFull);
   cudaFree(d.d_dict); cudaFree(d.d_dictState);
   encode_free(d.enc);
   cudaFreeHost(d.h_src); cudaFreeHost(d.h_dst); cudaFreeHost(d.h_desc);
@@ -202,8 +206,10 @@ enum class Op { Decompress, Compress };
 // on the frame-serial kernels (A/B measurements).  slot: the stream slot the launch runs on (its pair of counters).
 void with_units(Device& d, DecodeArgs& a, u32 slot) {
   static const bool on = env_int("ZSTDB200_PAR", 1, 0, 1) != 0;
+  a.huf_full = (u16*)(d.d_hufFull + d.hufFullBytes * slot);       // (every launch: the Huffman kernels' full-table scratch and the counters of this stream)
+  a.cnt = d.d_cnt + 4 * slot;
   if (!on) return;
-  a.units = d.d_units; a.par_list = d.d_parList; a.cnt = d.d_cnt + 2 * slot;
+  a.units = d.d_units; a.par_list = d.d_parList;
 }
 
 // Items that hold more than one data frame (DecompressMultiFrame, ZStdDecompress.cs:2096-2160): after the first pass

@@ -46,6 +46,12 @@ __global__ void __launch_bounds__(128) k_parse(DecodeArgs a) {
   }
   const u8* src = a.src_base + a.src_off[i];
   bool go = parse_item(src, a.src_size[i], fi, &r, start, outBase, a.dict ? a.dict->err : 0, a.dict ? a.dict->dictID : 0);
+  if (go) {
+    // frames of few literals go to the Huffman kernel with the small root table (k_huf<HUF_ROOT_SMALL>)
+    BlockHdr bh; LitHdr lh; bool needs;
+    if (!read_block_hdr(src + fi.body_off, a.src_size[i] - fi.body_off, bh) && bh.type == 2 && bh.csize < BLOCKSIZE_MAX &&
+        !read_lit_hdr(src + fi.body_off + 3, bh.csize, lh, &needs) && lh.type >= 2 && lh.litSize <= 2048) { fi.flags |= FI_SMALLHUF; atomicAdd(a.cnt + 2, 1u); }
+  }
   if (go && a.units) {
     // multi-block frames whose structure is sound become BlockUnits (zb_blocks.cuh): count, reserve, fill
     const u32 cap = a.dst_cap[i] - fi.out_base, maxU = cap / PAR_UNIT_BYTES + PAR_UNIT_SLACK;
@@ -64,39 +70,73 @@ __global__ void __launch_bounds__(128) k_parse(DecodeArgs a) {
 // =================================================================================================
 // k_huf : one warp per CTA, 8 frames per warp, lanes 4f..4f+3 own the 4 streams of frame f
 // =================================================================================================
-struct HufSmem {
-  __align__(16) u16 table[8][1 << HUF_TABLE_LOG];   // also lent as HufFseScratch while a frame's weights are decoded
+// The kernel is bound by how many frames an SM holds (one warp decodes eight frames' streams as eight dependent lookup
+// chains).  What it keeps in shared memory is a ROOT table of 2^R cells (zb_format.cuh huf_fill_root); codes longer than R
+// bits are looked up in the full table, which lives in a per-CTA-slot region of global memory (DecodeArgs::huf_full; only
+// the long codes' cells are ever written or read there).  Two instantiations share the frames: R = 9 (1 KB per frame,
+// 11 CTAs per SM) takes the frames k_parse marked FI_SMALLHUF — at most 2 048 literals in their first block, for which every
+// known encoder chooses a table log <= 9, so nothing is ever "long" (a crafted frame that is takes the long path and is
+// still decoded correctly) — and R = 11 (4 KB per frame, 5 CTAs per SM) the others, where only the 12-bit codes of a log-12
+// table are long.  (Measured: R = 9 for every frame costs 2.7 ms instead of 1.2 ms on 64 KiB tick frames, whose 256-symbol
+// alphabets put a quarter of the symbols on 10- and 11-bit codes; on 4 KiB frames it is 2.8 ms against 4.7 ms.)
+template <int R> struct HufSmem {
+  __align__(16) u16 root[8][1 << R];               // while a frame's weights are read, its cells hold the weights' FSE cells
   HufBuildWk wk[8];
-  __align__(16) u32 ring[32][ZB_RING_WORDS + 4];   // per-lane (= per-stream) bitstream read-ahead (BitRing); a folded
-                                                   // log-12 table keeps its 256-byte side table in the group's first ring
+  __align__(16) u32 ring[32][ZB_RING_WORDS + 4];   // per-lane (= per-stream) bitstream read-ahead (BitRing).  While a frame's
+                                                   // weights are read, the group's four rings hold norm / symbolNext of the
+                                                   // weights' FSE table, then the second ring the per-symbol slots
 };
-static_assert(sizeof(HufFseScratch) <= sizeof(u16) << HUF_TABLE_LOG, "FSE scratch must fit the decode table it borrows");
-static_assert((ZB_RING_WORDS + 4) * 4 >= 256, "side table must fit one lane's ring");
+static_assert(4 * (ZB_RING_WORDS + 4) * 4 >= 1024 && (sizeof(u16) << HUF_ROOT_SMALL) >= 256, "FSE scratch of the weights must fit");
+// full table of one resident frame: 2^11 cells + the 256-byte side table of a folded log-12 table
+#define HUF_FULL_STRIDE ((1u << HUF_TABLE_LOG) + 128u)   // in u16
+size_t decode_huf_full_bytes(int ctas) { return (size_t)ctas * 8 * HUF_FULL_STRIDE * sizeof(u16); }
 
-__global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  HufSmem& sm = *reinterpret_cast<HufSmem*>(smem_raw);
-  const u32 lane = threadIdx.x, sub = lane & 3, slot = lane >> 2;
-  const u32 f = blockIdx.x * 8 + slot;
+
+// weights at (tb, tbSize) -> root table in shared memory (+ the long codes in the slot's full table); group-uniform result
+template <int R>
+__device__ __forceinline__ bool huf_build_tables(HufSmem<R>& sm, u32 slot, u32 sub, unsigned gmask, const u8* tb, u32 tbSize, u16* fullMem,
+                                                 HufTabs& T, u32* hdrOut) {
+  HufBuildWk& wk = sm.wk[slot];
+  u8* const slotMem = (u8*)&sm.ring[slot * 4 + 1][0];
+  u32 hdr = 0, nbSym = 0, tl = 0, e = 0;
+  if (sub == 0) {
+    HufFseScratchRef fs{(s16*)&sm.ring[slot * 4][0], (u16*)((u8*)&sm.ring[slot * 4][0] + 512), (u32*)sm.root[slot]};
+    e = huf_read_weights(tb, tbSize, wk, fs, slotMem, &hdr, &tl, &nbSym);
+    if (!e && hdr >= tbSize) e = ZE_srcSize_wrong;                                 // HufDecompress.cs:1193
+  }
+  __syncwarp(gmask);
+  e = __shfl_sync(gmask, e, slot * 4); hdr = __shfl_sync(gmask, hdr, slot * 4);
+  tl = __shfl_sync(gmask, tl, slot * 4); nbSym = __shfl_sync(gmask, nbSym, slot * 4);
+  if (e) return false;
+  huf_fill_root(sm.root[slot], R, wk, slotMem, tl, nbSym, sub, 4);
+  if (tl > R) huf_fill_table(fullMem, (u8*)(fullMem + (1u << HUF_TABLE_LOG)), wk, slotMem, tl, nbSym, sub, 4, R);
+  __syncwarp(gmask);
+  T.full = fullMem; T.side = (const u8*)(fullMem + (1u << HUF_TABLE_LOG)); T.log = tl;
+  *hdrOut = hdr;
+  return true;
+}
+// the dictionary's table (litEntropy = 1 after ZSTD_decompress_insertDictionary, :2468)
+template <int R>
+__device__ __forceinline__ void huf_dict_tables(HufSmem<R>& sm, u32 slot, u32 sub, unsigned gmask, const DictState* ds, HufTabs& T) {
+  huf_root_from_full(sm.root[slot], R, ds->huf, ds->hufLog, sub, 4);
+  __syncwarp(gmask);
+  T.full = ds->huf; T.side = ds->hufSide; T.log = ds->hufLog;
+}
+
+// one frame by its 4-lane group
+template <int R>
+__device__ __forceinline__ void huf_frame(const DecodeArgs& a, HufSmem<R>& sm, u32 f, u32 lane, u16* fullMem) {
+  const u32 sub = lane & 3, slot = lane >> 2;
   const unsigned gmask = 0xFu << (slot * 4);
-  bool active = f < a.n;
-  FrameInfo fi;
-  if (active) { fi = a.info[f]; if (fi.flags & (FI_DONE | FI_PAR)) active = false; }
-  if (!active) return;   // whole 4-lane group leaves together; group syncs below use gmask
+  const FrameInfo fi = a.info[f];
+  if (fi.flags & (FI_DONE | FI_PAR)) return;   // whole 4-lane group leaves together; group syncs below use gmask
+  if (((fi.flags & FI_SMALLHUF) != 0) != (R == (int)HUF_ROOT_SMALL)) return;       // the other instantiation's frame
   const u8* src = a.src_base + a.src_off[f]; const u32 size = a.src_size[f];
   u8* lit = lit_region(a, f, fi); const u64 litCap = lit_capacity(frame_cap(a, f, fi));
-  u16* dt = sm.table[slot]; HufBuildWk& wk = sm.wk[slot];
-  u8* const sideMem = (u8*)&sm.ring[slot * 4][0]; const u8* side = nullptr;
-  u8* const slotMem = (u8*)&sm.ring[slot * 4 + 1][0];   // per-symbol rank within its weight: dead once the table is filled
   u32 pos = fi.body_off, blk = 0; u64 litRun = 0;
-  u32 tableLog = 0; bool haveTable = false;
-  if (a.dict && a.dict->hasEntropy) {                                              // litEntropy = 1 after ZSTD_decompress_insertDictionary (:2468)
-    const uint4* s4 = reinterpret_cast<const uint4*>(a.dict->huf); uint4* d4 = reinterpret_cast<uint4*>(dt);
-    for (u32 i = sub; i < (sizeof(u16) << HUF_TABLE_LOG) / 16; i += 4) d4[i] = s4[i];
-    tableLog = a.dict->hufLog; haveTable = true;
-    if (tableLog > HUF_TABLE_LOG) { for (u32 i = sub; i < 256; i += 4) sideMem[i] = a.dict->hufSide[i]; side = sideMem; }
-    __syncwarp(gmask);
-  }
+  HufTabs T{sm.root[slot], R, nullptr, nullptr, 0}; bool haveTable = false;
+  __syncwarp(gmask);                                                               // the group's previous frame is done with root / rings
+  if (a.dict && a.dict->hasEntropy) { huf_dict_tables(sm, slot, sub, gmask, a.dict, T); haveTable = true; }
   u32 errBlock = 0xFFFFFFFFu, errCode = 0;
   while (true) {
     BlockHdr bh;
@@ -114,39 +154,24 @@ __global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
         const bool dry = litRun + lh.litSize + 3 > litCap;                         // cannot be stored: validate only (HUF_DRY)
         if (lh.type == 2) {
           if (!lh.single && (lh.litSize == 0 || bodySize == 0)) ok = false;       // HufDecompress.cs:1211-1212
-          u32 hdr = 0, nbSym = 0, tl = 0;
-          if (ok) {
-            u32 e = 0;
-            if (sub == 0) {
-              e = huf_read_weights(body, bodySize, wk, *reinterpret_cast<HufFseScratch*>(dt), slotMem, &hdr, &tl, &nbSym);
-              if (!e && hdr >= bodySize) e = ZE_srcSize_wrong;                     // HufDecompress.cs:1193
-            }
-            __syncwarp(gmask);
-            e = __shfl_sync(gmask, e, slot * 4); hdr = __shfl_sync(gmask, hdr, slot * 4);
-            tl = __shfl_sync(gmask, tl, slot * 4); nbSym = __shfl_sync(gmask, nbSym, slot * 4);
-            if (e) ok = false;
-          }
-          if (ok) {
-            __syncwarp(gmask);                                                     // lane 0's scratch use of dt is over
-            huf_fill_table(dt, sideMem, wk, slotMem, tl, nbSym, sub, 4);
-            __syncwarp(gmask);
-            tableLog = tl; haveTable = true; side = tl > HUF_TABLE_LOG ? sideMem : nullptr;
-            body += hdr; bodySize -= hdr;
-          }
+          u32 hdr = 0;
+          if (ok) ok = huf_build_tables(sm, slot, sub, gmask, body, bodySize, fullMem, T, &hdr);
+          if (ok) { body += hdr; bodySize -= hdr; haveTable = true; }
         }
         if (ok) {
           bool good = true;
           if (lh.single) {
-            if (sub == 0) good = dry ? huf_check_stream(body, bodySize, lh.litSize, dt, tableLog, side)
-                                     : huf_decode_stream(body, bodySize, lit + litRun, lh.litSize, dt, tableLog, &sm.ring[lane][0], side);   // HufDecompress.cs:247-264
+            if (sub == 0) good = dry ? huf_check_stream(body, bodySize, lh.litSize, T)
+                                     : huf_decode_stream(body, bodySize, lit + litRun, lh.litSize, T, &sm.ring[lane][0]);   // HufDecompress.cs:247-264
           } else {
             HufStream st;
             good = huf_split4(body, bodySize, lh.litSize, sub, st);
-            if (good) good = dry ? huf_check_stream(st.src, st.len, st.count, dt, tableLog, side)
-                                 : huf_decode_stream(st.src, st.len, lit + litRun + st.outOfs, st.count, dt, tableLog, &sm.ring[lane][0], side);
+            if (good) good = dry ? huf_check_stream(st.src, st.len, st.count, T)
+                                 : huf_decode_stream(st.src, st.len, lit + litRun + st.outOfs, st.count, T, &sm.ring[lane][0]);
           }
           unsigned okmask = __ballot_sync(gmask, good);
           if ((okmask & gmask) != gmask) ok = false;
+          __syncwarp(gmask);                                                       // the rings are free again (a later block's weights use them)
         }
         if (!ok || dry) { errBlock = blk; errCode = ok ? HUF_DRY : ZE_corruption_detected; break; }
         litRun += lh.litSize;
@@ -156,6 +181,21 @@ __global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
     if (bh.last) break;
   }
   if (sub == 0 && errBlock != 0xFFFFFFFFu) { a.info[f].huf_err_block = errBlock; a.info[f].huf_err_code = errCode; }
+}
+
+// persistent: grid = the CTAs one wave of the device holds (or fewer for small batches)
+template <int R>
+__global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  HufSmem<R>& sm = *reinterpret_cast<HufSmem<R>*>(smem_raw);
+  const u32 lane = threadIdx.x, slot = lane >> 2;
+  const u32 nSmall = a.cnt[2];                                                     // frames k_parse marked FI_SMALLHUF
+  if (R == (int)HUF_ROOT_SMALL ? nSmall == 0 : nSmall == a.n) return;              // nothing for this instantiation in the launch
+  u16* const fullMem = a.huf_full + (size_t)(blockIdx.x * 8 + slot) * HUF_FULL_STRIDE;
+  for (u32 g = blockIdx.x; g * 8 < a.n; g += gridDim.x) {
+    const u32 f = g * 8 + slot;
+    if (f < a.n) huf_frame(a, sm, f, lane, fullMem);
+  }
 }
 
 // =================================================================================================
@@ -597,14 +637,12 @@ __global__ void __launch_bounds__(EXEC_THREADS, 16) k_exec(DecodeArgs a) {
 // k_huf_blk : k_huf's mapping (4 lanes per unit, 8 units per warp), persistent over the launch's units
 __global__ void __launch_bounds__(32) k_huf_blk(DecodeArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  HufSmem& sm = *reinterpret_cast<HufSmem*>(smem_raw);
+  HufSmem<HUF_TABLE_LOG>& sm = *reinterpret_cast<HufSmem<HUF_TABLE_LOG>*>(smem_raw);
   const u32 lane = threadIdx.x, sub = lane & 3, slot = lane >> 2;
   const unsigned gmask = 0xFu << (slot * 4);
   const u32 nunits = a.cnt[0];
   BlockUnit* const sliceUnits = a.units + unit_slice_base(a);
-  u16* dt = sm.table[slot]; HufBuildWk& wk = sm.wk[slot];
-  u8* const sideMem = (u8*)&sm.ring[slot * 4][0];
-  u8* const slotMem = (u8*)&sm.ring[slot * 4 + 1][0];
+  u16* const fullMem = a.huf_full + (size_t)(blockIdx.x * 8 + slot) * HUF_FULL_STRIDE;
   for (u32 w0 = blockIdx.x * 8; w0 < nunits; w0 += gridDim.x * 8) {
     const u32 w = w0 + slot;
     if (w >= nunits) continue;                                                     // the whole 4-lane group together
@@ -617,16 +655,12 @@ __global__ void __launch_bounds__(32) k_huf_blk(DecodeArgs a) {
     read_lit_hdr(bp, u.csize, lh, &needs);                                         // sound: par_walk has parsed it
     if (lh.type < 2) continue;
     u8* lit = lit_region(a, f, fi) + u.lit_off;
-    bool ok = true; u32 tableLog = 0; const u8* side = nullptr;
+    bool ok = true;
+    HufTabs T{sm.root[slot], HUF_TABLE_LOG, nullptr, nullptr, 0};
     const u8* body = bp + lh.lhSize; u32 bodySize = lh.litCSize;
-    __syncwarp(gmask);                                                             // the group's previous unit is done with dt / rings
-    if (lh.type == 3 && u.huf_def == DEF_DICT) {
-      const uint4* s4 = reinterpret_cast<const uint4*>(a.dict->huf); uint4* d4 = reinterpret_cast<uint4*>(dt);
-      for (u32 i = sub; i < (sizeof(u16) << HUF_TABLE_LOG) / 16; i += 4) d4[i] = s4[i];
-      tableLog = a.dict->hufLog;
-      if (tableLog > HUF_TABLE_LOG) { for (u32 i = sub; i < 256; i += 4) sideMem[i] = a.dict->hufSide[i]; side = sideMem; }
-      __syncwarp(gmask);
-    } else {
+    __syncwarp(gmask);                                                             // the group's previous unit is done with root / rings
+    if (lh.type == 3 && u.huf_def == DEF_DICT) huf_dict_tables(sm, slot, sub, gmask, a.dict, T);
+    else {
       // the weights: this block's own (type 2) or those of the block that defined the table in force (treeless)
       const u8* tb = body; u32 tbSize = bodySize;
       if (lh.type == 3) {
@@ -635,34 +669,18 @@ __global__ void __launch_bounds__(32) k_huf_blk(DecodeArgs a) {
         read_lit_hdr(src + d.body, d.csize, lhD, &n2);
         tb = src + d.body + lhD.lhSize; tbSize = lhD.litCSize;
       } else if (!lh.single && (lh.litSize == 0 || bodySize == 0)) ok = false;     // HufDecompress.cs:1211-1212
-      u32 hdr = 0, nbSym = 0, tl = 0;
-      if (ok) {
-        u32 e = 0;
-        if (sub == 0) {
-          e = huf_read_weights(tb, tbSize, wk, *reinterpret_cast<HufFseScratch*>(dt), slotMem, &hdr, &tl, &nbSym);
-          if (!e && hdr >= tbSize) e = ZE_srcSize_wrong;                           // HufDecompress.cs:1193
-        }
-        __syncwarp(gmask);
-        e = __shfl_sync(gmask, e, slot * 4); hdr = __shfl_sync(gmask, hdr, slot * 4);
-        tl = __shfl_sync(gmask, tl, slot * 4); nbSym = __shfl_sync(gmask, nbSym, slot * 4);
-        if (e) ok = false;
-      }
-      if (ok) {
-        __syncwarp(gmask);
-        huf_fill_table(dt, sideMem, wk, slotMem, tl, nbSym, sub, 4);
-        __syncwarp(gmask);
-        tableLog = tl; side = tl > HUF_TABLE_LOG ? sideMem : nullptr;
-        if (lh.type == 2) { body += hdr; bodySize -= hdr; }
-      }
+      u32 hdr = 0;
+      if (ok) ok = huf_build_tables(sm, slot, sub, gmask, tb, tbSize, fullMem, T, &hdr);
+      if (ok && lh.type == 2) { body += hdr; bodySize -= hdr; }
     }
     if (ok) {
       bool good = true;
       if (lh.single) {
-        if (sub == 0) good = huf_decode_stream(body, bodySize, lit, lh.litSize, dt, tableLog, &sm.ring[lane][0], side);
+        if (sub == 0) good = huf_decode_stream(body, bodySize, lit, lh.litSize, T, &sm.ring[lane][0]);
       } else {
         HufStream st;
         good = huf_split4(body, bodySize, lh.litSize, sub, st);
-        if (good) good = huf_decode_stream(st.src, st.len, lit + st.outOfs, st.count, dt, tableLog, &sm.ring[lane][0], side);
+        if (good) good = huf_decode_stream(st.src, st.len, lit + st.outOfs, st.count, T, &sm.ring[lane][0]);
       }
       const unsigned okmask = __ballot_sync(gmask, good);
       if ((okmask & gmask) != gmask) ok = false;
@@ -1103,20 +1121,24 @@ cudaError_t decode_load_dictionary(const u8* d_dict_bytes, u32 size, DictState* 
 }
 
 // grids of the persistent block-parallel kernels: what one wave of the device holds (set by decode_configure)
-static int g_par_grid_huf = 148 * 5, g_par_grid_seq = 148 * 2, g_par_grid_exec = 148 * 32;   // (exec: in warps)
+static int g_par_grid_huf = 148 * 5, g_grid_huf_small = 148 * 11, g_par_grid_seq = 148 * 2, g_par_grid_exec = 148 * 32;   // (exec: in warps)
+int decode_huf_ctas() { return g_grid_huf_small > g_par_grid_huf ? g_grid_huf_small : g_par_grid_huf; }
 size_t decode_unit_arena_count(u64 max_dst_bytes, u64 max_items) { return (size_t)(max_dst_bytes / PAR_UNIT_BYTES + PAR_UNIT_SLACK * (max_items + 2) + 64); }
 
 cudaError_t decode_configure() {
-  cudaError_t e = cudaFuncSetAttribute(k_huf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HufSmem));
+  cudaError_t e = cudaFuncSetAttribute(k_huf<HUF_TABLE_LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HufSmem<HUF_TABLE_LOG>));
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_huf_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HufSmem));
+  e = cudaFuncSetAttribute(k_huf<HUF_ROOT_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HufSmem<HUF_ROOT_SMALL>));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_huf_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HufSmem<HUF_TABLE_LOG>));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_seq_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqSmem));
   if (e != cudaSuccess) return e;
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) {
     int per = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_huf_blk, 32, sizeof(HufSmem)) == cudaSuccess && per > 0) g_par_grid_huf = sms * per;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_huf_blk, 32, sizeof(HufSmem<HUF_TABLE_LOG>)) == cudaSuccess && per > 0) g_par_grid_huf = sms * per;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_huf<HUF_ROOT_SMALL>, 32, sizeof(HufSmem<HUF_ROOT_SMALL>)) == cudaSuccess && per > 0) g_grid_huf_small = sms * per;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_seq_blk, 32, sizeof(SeqSmem)) == cudaSuccess && per > 0) g_par_grid_seq = sms * per;
     g_par_grid_exec = sms * 32;
   }
@@ -1130,17 +1152,19 @@ const char* const kDecodeKernelNames[DECODE_KERNELS] = {"k_parse", "k_huf", "k_s
 // on one stream.
 cudaError_t decode_launch_entropy(const DecodeArgs& a, cudaStream_t st, int* launches, cudaEvent_t* marks) {
   if (a.n == 0) return cudaSuccess;
-  if (a.units) { cudaError_t e = cudaMemsetAsync(a.cnt, 0, 8, st); if (e != cudaSuccess) return e; }
+  { cudaError_t e = cudaMemsetAsync(a.cnt, 0, 16, st); if (e != cudaSuccess) return e; }
   if (marks) cudaEventRecord(marks[0], st);
   k_parse<<<(a.n + 127) / 128, 128, 0, st>>>(a);
   if (marks) cudaEventRecord(marks[1], st);
-  k_huf<<<(a.n + 7) / 8, 32, sizeof(HufSmem), st>>>(a);
-  if (a.units) k_huf_blk<<<g_par_grid_huf, 32, sizeof(HufSmem), st>>>(a);
+  { const u32 need = (a.n + 7) / 8;
+    k_huf<HUF_ROOT_SMALL><<<need < (u32)g_grid_huf_small ? need : (u32)g_grid_huf_small, 32, sizeof(HufSmem<HUF_ROOT_SMALL>), st>>>(a);
+    k_huf<HUF_TABLE_LOG><<<need < (u32)g_par_grid_huf ? need : (u32)g_par_grid_huf, 32, sizeof(HufSmem<HUF_TABLE_LOG>), st>>>(a); }
+  if (a.units) k_huf_blk<<<g_par_grid_huf, 32, sizeof(HufSmem<HUF_TABLE_LOG>), st>>>(a);
   if (marks) cudaEventRecord(marks[2], st);
   k_seq<<<(a.n + 31) / 32, 32, sizeof(SeqSmem), st>>>(a);
   if (a.units) k_seq_blk<<<g_par_grid_seq, 32, sizeof(SeqSmem), st>>>(a);
   if (marks) cudaEventRecord(marks[3], st);
-  if (launches) *launches += a.units ? 5 : 3;
+  if (launches) *launches += a.units ? 6 : 4;
   return cudaGetLastError();
 }
 cudaError_t decode_launch_exec(const DecodeArgs& a, cudaStream_t st, int* launches, cudaEvent_t* marks) {

@@ -28,12 +28,16 @@ struct DecodeArgs {
   // Block-parallel path for multi-block frames (zb_blocks.cuh).  units == nullptr switches it off.
   BlockUnit* units;    // decode_unit_arena_count() units; a slice uses the range that follows from its first dst_off / item_base
   u32* par_list;       // one entry per item of the arena numbering: the slice's FI_PAR items, dense from par_list[item_base]
-  u32* cnt;            // device counters zeroed by the host before each pass: [0] units, [1] FI_PAR items of this launch
+  u32* cnt;            // four device counters of this launch (zeroed by decode_launch): [0] units, [1] FI_PAR items, [2] FI_SMALLHUF items
+  u16* huf_full;       // decode_huf_full_bytes(decode_huf_ctas()) of scratch for the Huffman kernels of THIS launch (launches
+                       // that run concurrently on different streams need regions of their own)
 };
 
 size_t decode_lit_arena_bytes(u64 max_dst_bytes, u64 max_items);
 size_t decode_seq_arena_bytes(u64 max_dst_bytes, u64 max_items);
 size_t decode_unit_arena_count(u64 max_dst_bytes, u64 max_items);
+int decode_huf_ctas();                      // CTAs of one wave of k_huf / k_huf_blk (valid after decode_configure)
+size_t decode_huf_full_bytes(int ctas);
 cudaError_t decode_configure();
 // parses the dictionary at d_dict_bytes (device memory, size bytes) into *d_state on `st` (one small kernel)
 cudaError_t decode_load_dictionary(const u8* d_dict_bytes, u32 size, DictState* d_state, cudaStream_t st);

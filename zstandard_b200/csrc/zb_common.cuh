@@ -40,7 +40,9 @@ static const u32 BLOCKSIZE_MAX = 1u << 17;
 static const u32 LONGNBSEQ = 0x7F00;
 static const u32 MaxLL = 35, MaxML = 52, MaxOff = 31, LLFSELog = 9, MLFSELog = 9, OffFSELog = 8;
 static const u32 HUF_LOG_MAX = 12;        // largest table log the reference accepts (HufDecompress.cs:128)
-static const u32 HUF_TABLE_LOG = 11;      // log of the decode table the kernels keep (log-12 tables are folded, zb_format.cuh)
+static const u32 HUF_TABLE_LOG = 11;      // log of the full decode table (log-12 tables are folded, zb_format.cuh)
+static const u32 HUF_ROOT_SMALL = 9;      // log of the root table the Huffman kernel for small frames keeps in shared memory (zb_format.cuh huf_fill_root)
+static const u32 HUF_LONG = 0xFF00u;      // root cell: the codes under this prefix are longer than the root log, look in the full table
 
 // ---- per-item record produced by the parse kernel and refined by later stages ----
 // huf_err_code value: the block's Huffman streams are well formed but its literals do not fit the frame's literal
@@ -48,6 +50,7 @@ static const u32 HUF_TABLE_LOG = 11;      // log of the decode table the kernels
 #define HUF_DRY 0xFFFFu
 enum : u32 { FI_CHECKSUM = 1, FI_FCS_KNOWN = 2, FI_DONE = 4 /* result[] already final, later stages skip the item */,
               FI_NEED_XXH = 8 /* set by the execute stage: verify the content checksum */,
+              FI_SMALLHUF = 32 /* few literals: its Huffman table log is at most HUF_ROOT_SMALL with any known encoder: decoded by k_huf<HUF_ROOT_SMALL> */,
               FI_PAR = 16 /* multi-block frame decoded block-parallel: its compressed blocks are BlockUnits (zb_blocks.cuh) */ };
 struct FrameInfo {
   u32 flags;

@@ -356,46 +356,52 @@ ZB_HD bool huf_split4(const u8* body, u32 bodySize, u32 n, u32 lane, HufStream& 
   return true;
 }
 
+// One symbol: the cell for the stream bits at the top of the left-aligned window w.  T.root = 2^T.rootLog cells
+// (huf_fill_root), T.full / T.side = the full table for the codes the root does not hold (huf_fill_table: 2^T.log cells,
+// log 12 folded with its side table).
+struct HufTabs { const u16* root; u32 rootLog; const u16* full; const u8* side; u32 log; };
+// LONGS = false: the table log does not exceed the root log, no root cell is HUF_LONG — the test stays out of the chain
+// of dependent lookups that bounds the decoder
+template <bool LONGS>
+ZB_HD u32 huf_cell(const HufTabs& T, u64 w) {
+  u32 c = T.root[(u32)(w >> (64 - T.rootLog))];
+  if (LONGS && c >= HUF_LONG) {
+    if (T.log > HUF_TABLE_LOG) { const u32 i12 = (u32)(w >> 52), cell = T.full[i12 >> 1]; c = (cell >> 8) == 12 ? (12u << 8) | T.side[i12] : cell; }
+    else c = T.full[(u32)(w >> (64 - T.log))];
+  }
+  return c;
+}
+template <bool LONGS>
+ZB_HD u32 huf_cell32(const HufTabs& T, u32 w32) {
+  u32 c = T.root[w32 >> (32 - T.rootLog)];
+  if (LONGS && c >= HUF_LONG) c = huf_cell<true>(T, (u64)w32 << 32);
+  return c;
+}
+
 // Decodes `count` symbols of one backward stream into out[0..count).  true iff the stream was consumed
 // exactly (EndOfDStream, HufDecompress.cs:350-353 / :261) — which also implies it was never over-read.
-// One symbol of a folded log-12 table (huf_fill_table): window w is left aligned
-ZB_HD u32 huf_cell12(const u16* dt, const u8* side, u64 w) {
-  const u32 i12 = (u32)(w >> 52), cell = dt[i12 >> 1];
-  return (cell >> 8) == 12 ? (12u << 8) | side[i12] : cell;
-}
-// side != nullptr <=> the table is a folded log-12 table: plain per-symbol loop (no encoder emits such tables)
-ZB_HD bool huf_decode_stream(const u8* src, u32 len, u8* out, u32 count, const u16* dt, u32 tableLog, u32* ringMem, const u8* side = nullptr) {
+template <bool LONGS>
+ZB_HD bool huf_decode_stream_t(const u8* src, u32 len, u8* out, u32 count, const HufTabs& T, u32* ringMem) {
   BitCursor c;
   if (!bc_init(c, src, len)) return false;                                         // InitDStream errors :304-307
   i32 P = c.P;
-  if (side) {
-    for (u32 left = count; left; left--) {
-      if (P < 0) return false;
-      const u32 cell = huf_cell12(dt, side, bc_window64(c, P));
-      *out++ = (u8)cell; P -= (i32)(cell >> 8);
-    }
-    return P == 0;
-  }
   u32 left = count;
-  const u32 sh = 64 - tableLog;
   // head: reach 4-byte alignment of the output
   while (left && ((uintptr_t)out & 3)) {
-    u64 w = bc_window64(c, P);
-    u32 cell = dt[(u32)(w >> sh)];
+    const u32 cell = huf_cell<LONGS>(T, bc_window64(c, P));
     *out++ = (u8)cell; P -= (i32)(cell >> 8); left--;
   }
   // fast loop: 4 symbols (<= 48 bits) per iteration out of the shared-memory ring
   if (left >= 4 && P >= 128) {
     BitRing ring;
     ring_init(ring, ringMem, src, len);
-    const u32 sh32 = 32 - tableLog;
     while (left >= 4 && P >= 128) {
       u32 lo, hi;
       ring_window(ring, P, lo, hi);
-      const u32 c0 = dt[hi >> sh32]; u32 used = c0 >> 8;
-      const u32 c1 = dt[fshl(lo, hi, used) >> sh32]; used += c1 >> 8;
-      const u32 c2 = dt[fshl(lo, hi, used) >> sh32]; used += c2 >> 8;
-      const u32 c3 = dt[(used < 32 ? fshl(lo, hi, used) : (lo << (used - 32))) >> sh32]; used += c3 >> 8;
+      const u32 c0 = huf_cell32<LONGS>(T, hi); u32 used = c0 >> 8;
+      const u32 c1 = huf_cell32<LONGS>(T, fshl(lo, hi, used)); used += c1 >> 8;
+      const u32 c2 = huf_cell32<LONGS>(T, fshl(lo, hi, used)); used += c2 >> 8;
+      const u32 c3 = huf_cell32<LONGS>(T, used < 32 ? fshl(lo, hi, used) : (lo << (used - 32))); used += c3 >> 8;
       *(u32*)out = (c0 & 0xFF) | ((c1 & 0xFF) << 8) | ((c2 & 0xFF) << 16) | ((c3 & 0xFF) << 24);
       out += 4; left -= 4;
       P -= (i32)used;
@@ -404,34 +410,34 @@ ZB_HD bool huf_decode_stream(const u8* src, u32 len, u8* out, u32 count, const u
   }
   while (left >= 4) {
     u64 w = bc_window64(c, P);
-    u32 c0 = dt[(u32)(w >> sh)]; w <<= (c0 >> 8);
-    u32 c1 = dt[(u32)(w >> sh)]; w <<= (c1 >> 8);
-    u32 c2 = dt[(u32)(w >> sh)]; w <<= (c2 >> 8);
-    u32 c3 = dt[(u32)(w >> sh)];
+    const u32 c0 = huf_cell<LONGS>(T, w); w <<= (c0 >> 8);
+    const u32 c1 = huf_cell<LONGS>(T, w); w <<= (c1 >> 8);
+    const u32 c2 = huf_cell<LONGS>(T, w); w <<= (c2 >> 8);
+    const u32 c3 = huf_cell<LONGS>(T, w);
     P -= (i32)((c0 >> 8) + (c1 >> 8) + (c2 >> 8) + (c3 >> 8));
     *(u32*)out = (c0 & 0xFF) | ((c1 & 0xFF) << 8) | ((c2 & 0xFF) << 16) | ((c3 & 0xFF) << 24);
     out += 4; left -= 4;
   }
   while (left) {
-    u64 w = bc_window64(c, P);
-    u32 cell = dt[(u32)(w >> sh)];
+    const u32 cell = huf_cell<LONGS>(T, bc_window64(c, P));
     *out++ = (u8)cell; P -= (i32)(cell >> 8); left--;
   }
   return P == 0;
+}
+ZB_HD bool huf_decode_stream(const u8* src, u32 len, u8* out, u32 count, const HufTabs& T, u32* ringMem) {
+  return T.log > T.rootLog ? huf_decode_stream_t<true>(src, len, out, count, T, ringMem) : huf_decode_stream_t<false>(src, len, out, count, T, ringMem);
 }
 
 // Validation without output: same verdict as huf_decode_stream.  Used when a block's literals cannot fit the
 // frame's literal scratch — the frame is then certain to fail, but whether with corruption_detected (here) or with
 // the execute stage's dstSize_tooSmall depends on whether the streams are well formed (HufDecompress.cs:350-353).
-ZB_HD bool huf_check_stream(const u8* src, u32 len, u32 count, const u16* dt, u32 tableLog, const u8* side = nullptr) {
+ZB_HD bool huf_check_stream(const u8* src, u32 len, u32 count, const HufTabs& T) {
   BitCursor c;
   if (!bc_init(c, src, len)) return false;
   i32 P = c.P;
-  const u32 sh = 64 - tableLog;
   for (u32 left = count; left; left--) {
     if (P < 0) return false;
-    const u64 w = bc_window64(c, P);
-    P -= (i32)((side ? huf_cell12(dt, side, w) : dt[(u32)(w >> sh)]) >> 8);
+    P -= (i32)(huf_cell<true>(T, bc_window64(c, P)) >> 8);
   }
   return P == 0;
 }

@@ -319,7 +319,10 @@ struct HufFseScratch {          // 1280 bytes
 // FSE-compressed weights -> w[0..n).  Returns count, or 0xFFFFFFFF on error.  Mirrors the reference's
 // two-state loop: symbols alternate between the states; once a read has crossed the stream start the other
 // state's pending symbol is emitted and decoding stops (FseDecompress.cs:275-292).
-ZB_HD u32 fse_decode_weights(u8* w, u32 maxOut, const u8* src, u32 srcSize, HufFseScratch& wk) {
+// the same three arrays anywhere (the kernels lay them over memory that is idle while weights are read)
+struct HufFseScratchRef { s16* norm; u16* symbolNext; u32* fse; };
+template <class Scratch>
+ZB_HD u32 fse_decode_weights(u8* w, u32 maxOut, const u8* src, u32 srcSize, Scratch& wk) {
   u32 maxSV = 255, tl, h;
   if (read_ncount(wk.norm, &maxSV, &tl, src, srcSize, &h)) return 0xFFFFFFFFu;
   if (tl > 6) return 0xFFFFFFFFu;                                                  // FseDecompress.cs:322 (maxLog 6)
@@ -367,7 +370,8 @@ ZB_HD u32 fse_decode_weights(u8* w, u32 maxOut, const u8* src, u32 srcSize, HufF
 // Parses the weight header at src and validates it.  On success returns 0 and sets *hdrBytes, *tableLog,
 // *nbSym with wk.weight[0..nbSym), wk.rank[] = first cell index of each weight and slot[n] = how many earlier
 // symbols share symbol n's weight — so that any lane can place any symbol's cells without a running count.
-ZB_HD u32 huf_read_weights(const u8* src, u32 srcSize, HufBuildWk& wk, HufFseScratch& fs, u8* slot, u32* hdrBytes, u32* tableLog, u32* nbSym) {
+template <class Scratch>
+ZB_HD u32 huf_read_weights(const u8* src, u32 srcSize, HufBuildWk& wk, Scratch& fs, u8* slot, u32* hdrBytes, u32* tableLog, u32* nbSym) {
   if (srcSize == 0) return ZE_srcSize_wrong;
   u32 iSize = src[0], oSize;
   if (iSize >= 128) {
@@ -419,16 +423,50 @@ ZB_HD void huf_fill_cells(u16* dt, u32 start, u32 len, u16 cell) {
     for (u32 u = 0; u < len / 2; u += 4) { p[u] = c2; p[u + 1] = c2; p[u + 2] = c2; p[u + 3] = c2; }
   } else for (u32 u = 0; u < len; u++) dt[start + u] = cell;
 }
-ZB_HD void huf_fill_table(u16* dt, u8* side, const HufBuildWk& wk, const u8* slot, u32 tableLog, u32 nbSym, u32 first, u32 step) {
+// longerThan: only the symbols whose code is longer than that many bits are entered (0 = all) — the kernels' full table
+// in global memory only ever answers for codes the root table does not hold.
+ZB_HD void huf_fill_table(u16* dt, u8* side, const HufBuildWk& wk, const u8* slot, u32 tableLog, u32 nbSym, u32 first, u32 step, u32 longerThan = 0) {
   const bool folded = tableLog > HUF_TABLE_LOG;
   for (u32 n = first; n < nbSym; n += step) {
     const u32 wv = wk.weight[n];
     if (!wv) continue;
+    if (tableLog + 1 - wv <= longerThan) continue;
     const u32 len = 1u << (wv - 1), start = wk.rank[wv] + slot[n] * len;
     const u16 cell = (u16)(n | ((tableLog + 1 - wv) << 8));
     if (!folded) huf_fill_cells(dt, start, len, cell);
     else if (wv == 1) { side[start] = (u8)n; dt[start >> 1] = (u16)(12u << 8); }
     else huf_fill_cells(dt, start / 2, len / 2, cell);
+  }
+}
+
+// Root table: 2^rootLog cells indexed by the next rootLog stream bits.  A code of at most that many bits owns whole
+// root cells (its cell, as in the full table); the root cells under which only longer codes live hold HUF_LONG and the
+// decoder looks those up in the full table (huf_fill_table with longerThan = rootLog).  The Huffman kernels live on how
+// many frames an SM holds: rootLog 9 (1 KB per frame) for frames of few literals, whose table log is at most 9 with any
+// known encoder; rootLog 11 otherwise (only the 12-bit codes of a log-12 table are then "long").
+ZB_HD void huf_fill_root(u16* root, u32 rootLog, const HufBuildWk& wk, const u8* slot, u32 tableLog, u32 nbSym, u32 first, u32 step) {
+  const u32 HUF_ROOT_LOG = rootLog;
+  for (u32 n = first; n < nbSym; n += step) {
+    const u32 wv = wk.weight[n];
+    if (!wv) continue;
+    const u32 cnt = 1u << (wv - 1), start = wk.rank[wv] + slot[n] * cnt, len = tableLog + 1 - wv;
+    const u16 cell = (u16)(n | (len << 8));
+    if (tableLog <= HUF_ROOT_LOG) huf_fill_cells(root, start << (HUF_ROOT_LOG - tableLog), cnt << (HUF_ROOT_LOG - tableLog), cell);
+    else {
+      const u32 sh = tableLog - HUF_ROOT_LOG;
+      if (cnt >> sh) huf_fill_cells(root, start >> sh, cnt >> sh, cell);
+      else root[start >> sh] = (u16)HUF_LONG;
+    }
+  }
+}
+
+// The root table of an existing full table (a dictionary's): cells first, first + step, ...
+ZB_HD void huf_root_from_full(u16* root, u32 rootLog, const u16* full, u32 tableLog, u32 first, u32 step) {
+  for (u32 i = first; i < (1u << rootLog); i += step) {
+    if (tableLog <= rootLog) { root[i] = full[i >> (rootLog - tableLog)]; continue; }
+    const u32 at = i << (tableLog - rootLog);                                      // first full-table index under this prefix
+    const u32 c = full[tableLog > HUF_TABLE_LOG ? at >> 1 : at];                   // (a log-12 table is folded: cell j stands for 2j, 2j + 1)
+    root[i] = (u16)((c >> 8) <= rootLog ? c : HUF_LONG);
   }
 }
 
