@@ -173,3 +173,27 @@ def test_both_root_table_sizes_of_the_huffman_stage(hostsim, oracle):
                 assert hostsim.decompress(frame, len(plain), oracle) == (len(plain), plain)
     finally:
         hostsim.set_huf_root(9)
+
+
+def test_small_sequence_tables_hand_larger_frames_over(hostsim, oracle):
+    """k_seq runs as three instantiations with room for table logs 6 / 8 / the format's maximum; a frame whose tables do not
+    fit the one k_parse chose is handed to the full-size one (zb_format.cuh read_seq_table capLog, SeqEmitter::defer).  The
+    replay makes every frame start in the small instantiation: same results, and the hand-over did happen."""
+    rng = random.Random(6)
+    frames = helpers.make_frames(204, 90)
+    before = hostsim.lib.hostsim_deferred()
+    try:
+        for cap_log in (6, 8):
+            hostsim.lib.hostsim_set_seq_cap(cap_log)
+            for frame, data in frames:
+                ro, oo, _ = oracle.decompress(frame, len(data))
+                rh, oh = hostsim.decompress(frame, len(data), oracle)
+                assert ro == rh and oo == oh, (cap_log, len(data))
+                if len(frame) > 12:
+                    b = helpers.mutate(rng, frame)
+                    ro, oo, _ = oracle.decompress(b, len(data))
+                    rh, oh = hostsim.decompress(b, len(data), oracle)
+                    assert ro == rh and oo == oh, (cap_log, "mutated", len(data))
+    finally:
+        hostsim.lib.hostsim_set_seq_cap(9)
+    assert hostsim.lib.hostsim_deferred() - before > 20

@@ -110,8 +110,8 @@ int alloc_device(zstdb200_ctx* ctx, Device& d) {
   CK(cudaMalloc(&d.d_lit, decode_lit_arena_bytes(ctx->dstSpan, items)));
   CK(cudaMalloc(&d.d_seq, decode_seq_arena_bytes(ctx->dstSpan, items)));
   CK(cudaMalloc(&d.d_units, decode_unit_arena_count(ctx->dstSpan, items) * sizeof(BlockUnit)));
-  CK(cudaMalloc(&d.d_parList, (items + 1) * 4));
-  CK(cudaMalloc(&d.d_cnt, NSTREAMS * 4 * 4));
+  CK(cudaMalloc(&d.d_parList, 4 * (items + 1) * 4));
+  CK(cudaMalloc(&d.d_cnt, NSTREAMS * 8 * 4));
   CK(decode_configure());
   d.hufFullBytes = align_up(decode_huf_full_bytes(decode_huf_ctas()), 256);
   CK(cudaMalloc(&d.d_hufFull, d.hufFullBytes * NSTREAMS));
@@ -204,12 +204,12 @@ enum class Op { Decompress, Compress };
 
 // Switches a launch to the block-parallel path for multi-block frames (zb_blocks.cuh); ZSTDB200_PAR=0 keeps every frame
 // on the frame-serial kernels (A/B measurements).  slot: the stream slot the launch runs on (its pair of counters).
-void with_units(Device& d, DecodeArgs& a, u32 slot) {
+void with_units(Device& d, DecodeArgs& a, u32 slot, size_t ctx_items) {
   static const bool on = env_int("ZSTDB200_PAR", 1, 0, 1) != 0;
   a.huf_full = (u16*)(d.d_hufFull + d.hufFullBytes * slot);       // (every launch: the Huffman kernels' full-table scratch and the counters of this stream)
-  a.cnt = d.d_cnt + 4 * slot;
+  a.cnt = d.d_cnt + 8 * slot; a.par_list = d.d_parList; a.list_stride = (u32)(ctx_items + 1);
   if (!on) return;
-  a.units = d.d_units; a.par_list = d.d_parList;
+  a.units = d.d_units;
 }
 
 // Items that hold more than one data frame (DecompressMultiFrame, ZStdDecompress.cs:2096-2160): after the first pass
@@ -332,7 +332,7 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     if (j.op == Op::Decompress) {
       DecodeArgs ar{d.d_src, d_srcOff + a, d_srcSize + a, d.d_dst, d_dstOff + a, d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
                     d.d_info + a, d.d_lit, d.d_seq, d.dictOn ? d.d_dictState : nullptr, d.d_dict, 0, d.d_more + (s % nStreams)};
-      with_units(d, ar, (u32)(s % nStreams));
+      with_units(d, ar, (u32)(s % nStreams), ctx->maxItems);
       e = decode_launch(ar, st, &nl);
     } else {
       EncodeArgs ar{d.d_src, d_srcOff + a, d_srcSize + a, d.d_dst, d_dstOff + a, d_dstCap + a, d.d_result + a, (u32)cnt, (u32)a,
@@ -381,7 +381,7 @@ std::string run_subbatch(zstdb200_ctx* ctx, Device& d, const Job& j, size_t lo, 
     // pass by pass over the whole sub-batch, then fetch results and output again.
     cudaStream_t st = d.stream[0]; int nl = 0;
     DecodeArgs ar{d.d_src, d_srcOff, d_srcSize, d.d_dst, d_dstOff, d_dstCap, d.d_result, (u32)m, 0, d.d_info, d.d_lit, d.d_seq, d.dictOn ? d.d_dictState : nullptr, d.d_dict, 0, nullptr};
-    with_units(d, ar, 0);
+    with_units(d, ar, 0, ctx->maxItems);
     e = decode_more_passes(d, ar, 0, st, &nl); *launches += nl;
     if (e) return fail("multi-frame passes", e);
     e = cudaMemcpyAsync(d.h_result, d.d_result, m * 4, cudaMemcpyDeviceToHost, st); if (e) return fail("D2H result", e);
@@ -594,7 +594,7 @@ uint32_t zstdb200_decompress(zstdb200_ctx* ctx, void* dst, uint32_t dstCapacity,
 static int decode_device(zstdb200_ctx* ctx, Device& d, const DecodeArgs& a, cudaStream_t user, cudaEvent_t* marks) {
   int nl = 0;
   DecodeArgs b = a; b.pass = 0; b.more = d.d_more;
-  with_units(d, b, 0);
+  with_units(d, b, 0, ctx->maxItems);
   CK(cudaMemsetAsync(b.more, 0, 4, user));
   CK(decode_launch(b, user, &nl, marks));
   CK(cudaMemcpyAsync(d.h_more, b.more, 4, cudaMemcpyDeviceToHost, user));

@@ -34,24 +34,18 @@ __device__ __forceinline__ u64 unit_slice_base(const DecodeArgs& a) { return a.d
 // =================================================================================================
 // k_parse
 // =================================================================================================
-__global__ void __launch_bounds__(128) k_parse(DecodeArgs a) {
-  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
+// one item: parse, early verdicts, BlockUnits of multi-block frames.  Returns the sequence-kernel list the item's frame is
+// entered in (0 = FI_SEQ_A, 1 = FI_SEQ_B, 2 = full-size tables), -1 = none (finished here, or block-parallel)
+__device__ __forceinline__ int parse_one(const DecodeArgs& a, u32 i) {
   FrameInfo fi; u32 r = 0; u32 start = 0, outBase = 0;
   if (a.pass) {
     // later passes only touch items whose previous data frame decoded cleanly and is followed by another one
     const FrameInfo prev = a.info[i];
-    if ((prev.flags & FI_DONE) || prev.next_off == 0 || is_err(a.result[i])) { a.info[i].flags = FI_DONE; return; }
+    if ((prev.flags & FI_DONE) || prev.next_off == 0 || is_err(a.result[i])) { a.info[i].flags = FI_DONE; return -1; }
     start = prev.next_off; outBase = prev.out_base + prev.decoded;
   }
   const u8* src = a.src_base + a.src_off[i];
   bool go = parse_item(src, a.src_size[i], fi, &r, start, outBase, a.dict ? a.dict->err : 0, a.dict ? a.dict->dictID : 0);
-  if (go) {
-    // frames of few literals go to the Huffman kernel with the small root table (k_huf<HUF_ROOT_SMALL>)
-    BlockHdr bh; LitHdr lh; bool needs;
-    if (!read_block_hdr(src + fi.body_off, a.src_size[i] - fi.body_off, bh) && bh.type == 2 && bh.csize < BLOCKSIZE_MAX &&
-        !read_lit_hdr(src + fi.body_off + 3, bh.csize, lh, &needs) && lh.type >= 2 && lh.litSize <= 2048) { fi.flags |= FI_SMALLHUF; atomicAdd(a.cnt + 2, 1u); }
-  }
   if (go && a.units) {
     // multi-block frames whose structure is sound become BlockUnits (zb_blocks.cuh): count, reserve, fill
     const u32 cap = a.dst_cap[i] - fi.out_base, maxU = cap / PAR_UNIT_BYTES + PAR_UNIT_SLACK;
@@ -63,8 +57,56 @@ __global__ void __launch_bounds__(128) k_parse(DecodeArgs a) {
       a.par_list[a.item_base + atomicAdd(a.cnt + 1, 1u)] = i;
     }
   }
+  int list = -1;
+  if (go) {
+    // frames of few literals go to the Huffman kernel with the small root table (k_huf<HUF_ROOT_SMALL>) ...
+    BlockHdr bh; LitHdr lh; bool needs; u32 cls = 0;
+    if (!read_block_hdr(src + fi.body_off, a.src_size[i] - fi.body_off, bh) && bh.type == 2 && bh.csize < BLOCKSIZE_MAX &&
+        !read_lit_hdr(src + fi.body_off + 3, bh.csize, lh, &needs)) {
+      if (lh.type >= 2 && lh.litSize <= 2048) { fi.flags |= FI_SMALLHUF; atomicAdd(a.cnt + 2, 1u); }
+      // ... and frames of few sequences to a sequence kernel with small tables: an encoder picks table logs of at most
+      // max(highbit(nbSeq - 1) - 2, highbit(largest code) + 2), i.e. <= 6 / 6 / 7 (LL / OF / ML) up to 512 sequences and
+      // <= 8 up to 2 048; a dictionary's tables are full size.  Wrong guesses are handed over (SeqEmitter::defer).
+      u32 nbSeq, modes, hdr;
+      if (!(a.dict && a.dict->hasEntropy) && !read_seq_count(src + fi.body_off + 3 + lh.consumed, bh.csize - lh.consumed, &nbSeq, &modes, &hdr))
+        cls = nbSeq <= 512 ? 1 : (nbSeq <= 2048 ? 2 : 0);
+    }
+    if (!(fi.flags & FI_PAR)) {
+      if (cls == 1) fi.flags |= FI_SEQ_A; else if (cls == 2) fi.flags |= FI_SEQ_B;
+      list = cls == 0 ? 2 : (int)cls - 1;                                           // lists / counters in the order A, B, full size
+    }
+  }
   a.info[i] = fi;
   if (!go) a.result[i] = r;
+  return list;
+}
+
+__global__ void __launch_bounds__(128) k_parse(DecodeArgs a) {
+  __shared__ u32 warpCount[3][4], ctaBase[3];
+  const u32 i = blockIdx.x * 128 + threadIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int list = i < a.n ? parse_one(a, i) : -1;
+  // Every frame of the frame-serial path is entered in its class's dense list (the sequence kernels take 32 consecutive
+  // entries per warp, so a launch of mixed classes wastes no lanes).  The lists keep the items' order inside a CTA's 128
+  // items (ranks from ballots, one reservation per CTA and list): the 32 frames of a sequence-kernel warp stay neighbours
+  // in the source / record arenas.  (Appending item by item scrambles the lists over the whole batch, which cost the
+  // sequence kernel 22-29 % on every shape measured: 1.69 -> 2.06 ms on the 64 KiB log frames.)
+  u32 rank = 0;
+  for (int k = 0; k < 3; k++) {
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, list == k);
+    if (list == k) rank = __popc(m & ((1u << lane) - 1));
+    if (lane == 0) warpCount[k][w] = __popc(m);
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const u32 t = warpCount[threadIdx.x][0] + warpCount[threadIdx.x][1] + warpCount[threadIdx.x][2] + warpCount[threadIdx.x][3];
+    ctaBase[threadIdx.x] = t ? atomicAdd(a.cnt + 3 + threadIdx.x, t) : 0;
+  }
+  __syncthreads();
+  if (list >= 0) {
+    u32 before = 0;
+    for (u32 j = 0; j < w; j++) before += warpCount[list][j];
+    a.par_list[(size_t)(1 + list) * a.list_stride + a.item_base + ctaBase[list] + before + rank] = i;
+  }
 }
 
 // =================================================================================================
@@ -206,21 +248,25 @@ __global__ void __launch_bounds__(32) k_huf(DecodeArgs a) {
 // shared-memory queue.  The chain warp's loop went from 136 to 103 instructions but only from ~400 to ~373 cycles per
 // sequence: it is bound by the dependent chain state -> cell -> extra-bit count -> shift -> state plus the one-warp ALU
 // issue rate, and the queue's back-pressure test adds a divergent branch; 2.06 ms against 1.72 ms for this kernel.)
-struct SeqSmem {
-  u16 ll[512][32];       // lane-interleaved: cell[state][lane]
-  u16 ml[512][32];
-  u16 of[256][32];
+// CL / CO / CM: the largest table logs the instantiation has room for.  Three instantiations share the frames (k_parse
+// classifies them by the first block's sequence count, which bounds the table logs every known encoder chooses):
+// 6 / 6 / 7 (32 KB, 6 CTAs per SM), 8 / 8 / 8 (64 KB, 3 CTAs per SM) and the format's maximum 9 / 8 / 9 (98 KB, 2 CTAs per SM).
+// A frame that turns out to need a larger table than its class provides is handed to the full-size instantiation, which
+// runs last (SeqEmitter::defer).
+template <int CL, int CO, int CM> struct SeqSmemT {
+  u16 ll[1 << CL][32];   // lane-interleaved: cell[state][lane]
+  u16 ml[1 << CM][32];
+  u16 of[1 << CO][32];
   u16 defLL[64], defOF[32], defML[64];
   u32 llInfo[36], mlInfo[53];
   s16 norm[53][32];      // per-lane scratch of the table builder, lane-interleaved like the tables
   u16 next[53][32];
   __align__(16) u32 ring[32][ZB_RING_WORDS + 4];   // per-lane bitstream read-ahead (BitRing), skewed by 4 banks per lane
 };
+typedef SeqSmemT<9, 8, 9> SeqSmem;
 
-__global__ void __launch_bounds__(32) k_seq(DecodeArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  SeqSmem& sm = *reinterpret_cast<SeqSmem*>(smem_raw);
-  const u32 lane = threadIdx.x;
+template <class SM>
+__device__ __forceinline__ void seq_smem_init(SM& sm, u32 lane) {
   // predefined tables + info LUTs, built once per CTA
   if (lane < 3) {
     s16* norm = &sm.norm[0][lane]; u16* next = &sm.next[0][lane];
@@ -232,11 +278,26 @@ __global__ void __launch_bounds__(32) k_seq(DecodeArgs a) {
   for (u32 i = lane; i < 36; i += 32) sm.llInfo[i] = ll_info(i);
   for (u32 i = lane; i < 53; i += 32) sm.mlInfo[i] = ml_info(i);
   __syncwarp();
-  const u32 f = blockIdx.x * 32 + lane;
-  if (f >= a.n) return;
-  FrameInfo fi = a.info[f];
-  if (fi.flags & (FI_DONE | FI_PAR)) return;
+}
+
+// CLS: 0 = full-size tables (also every frame the smaller instantiations handed over), 1 = FI_SEQ_A, 2 = FI_SEQ_B
+template <int CLS, int CL, int CO, int CM>
+__global__ void __launch_bounds__(32) k_seq_t(DecodeArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  typedef SeqSmemT<CL, CO, CM> SM;
+  SM& sm = *reinterpret_cast<SM*>(smem_raw);
+  const u32 lane = threadIdx.x;
+  // this class's frames: a dense list written by k_parse; the full-size class also gets what the smaller ones handed over
+  const u32 k = CLS == 0 ? 2 : CLS - 1;
+  const u32 count = a.cnt[3 + k];
+  if (blockIdx.x * 32 >= count) return;
+  seq_smem_init(sm, lane);
+  const u32 e = blockIdx.x * 32 + lane;
+  if (e >= count) return;
+  const u32 f = a.par_list[(size_t)(1 + k) * a.list_stride + a.item_base + e];
+  const FrameInfo fi = a.info[f];
   SeqTableSet T;
+  T.cap[KIND_LL] = CL; T.cap[KIND_OF] = CO; T.cap[KIND_ML] = CM;
   T.space[KIND_LL] = &sm.ll[0][lane]; T.space[KIND_ML] = &sm.ml[0][lane]; T.space[KIND_OF] = &sm.of[0][lane]; T.stride = 32;
   T.defs[KIND_LL] = sm.defLL; T.defs[KIND_OF] = sm.defOF; T.defs[KIND_ML] = sm.defML;
   SeqEmitter em;
@@ -244,6 +305,11 @@ __global__ void __launch_bounds__(32) k_seq(DecodeArgs a) {
   if (a.dict) em.set_reps(a.dict->rep);
   seq_decode_frame(a.src_base + a.src_off[f], a.src_size[f], fi.body_off, fi.window, T, em, sm.llInfo, sm.mlInfo,
                    Strided<s16>{&sm.norm[0][lane], 32}, Strided<u16>{&sm.next[0][lane], 32}, &sm.ring[lane][0], a.dict);
+  if (CLS != 0 && em.deferred) {                                                   // the full-size instantiation (launched after this one) redoes the frame
+    a.info[f].flags = fi.flags & ~(u32)(FI_SEQ_A | FI_SEQ_B);
+    a.par_list[(size_t)3 * a.list_stride + a.item_base + atomicAdd(a.cnt + 5, 1u)] = f;
+    return;
+  }
   if (em.res.err_block != 0xFFFFFFFFu) {
     a.info[f].seq_err_block = em.res.err_block; a.info[f].seq_err_code = em.res.err_code; a.info[f].seq_err_index = em.res.err_index;
   }
@@ -1142,7 +1208,9 @@ cudaError_t decode_configure() {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_seq_blk, 32, sizeof(SeqSmem)) == cudaSuccess && per > 0) g_par_grid_seq = sms * per;
     g_par_grid_exec = sms * 32;
   }
-  return cudaFuncSetAttribute(k_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqSmem));
+  e = cudaFuncSetAttribute(k_seq_t<2, 8, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqSmemT<8, 8, 8>));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_seq_t<0, 9, 8, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SeqSmem));
 }
 
 const char* const kDecodeKernelNames[DECODE_KERNELS] = {"k_parse", "k_huf", "k_seq", "k_exec", "k_xxh"};
@@ -1152,7 +1220,7 @@ const char* const kDecodeKernelNames[DECODE_KERNELS] = {"k_parse", "k_huf", "k_s
 // on one stream.
 cudaError_t decode_launch_entropy(const DecodeArgs& a, cudaStream_t st, int* launches, cudaEvent_t* marks) {
   if (a.n == 0) return cudaSuccess;
-  { cudaError_t e = cudaMemsetAsync(a.cnt, 0, 16, st); if (e != cudaSuccess) return e; }
+  { cudaError_t e = cudaMemsetAsync(a.cnt, 0, 32, st); if (e != cudaSuccess) return e; }
   if (marks) cudaEventRecord(marks[0], st);
   k_parse<<<(a.n + 127) / 128, 128, 0, st>>>(a);
   if (marks) cudaEventRecord(marks[1], st);
@@ -1161,10 +1229,12 @@ cudaError_t decode_launch_entropy(const DecodeArgs& a, cudaStream_t st, int* lau
     k_huf<HUF_TABLE_LOG><<<need < (u32)g_par_grid_huf ? need : (u32)g_par_grid_huf, 32, sizeof(HufSmem<HUF_TABLE_LOG>), st>>>(a); }
   if (a.units) k_huf_blk<<<g_par_grid_huf, 32, sizeof(HufSmem<HUF_TABLE_LOG>), st>>>(a);
   if (marks) cudaEventRecord(marks[2], st);
-  k_seq<<<(a.n + 31) / 32, 32, sizeof(SeqSmem), st>>>(a);
+  k_seq_t<1, 6, 6, 7><<<(a.n + 31) / 32, 32, sizeof(SeqSmemT<6, 6, 7>), st>>>(a);
+  k_seq_t<2, 8, 8, 8><<<(a.n + 31) / 32, 32, sizeof(SeqSmemT<8, 8, 8>), st>>>(a);
+  k_seq_t<0, 9, 8, 9><<<(a.n + 31) / 32, 32, sizeof(SeqSmem), st>>>(a);
   if (a.units) k_seq_blk<<<g_par_grid_seq, 32, sizeof(SeqSmem), st>>>(a);
   if (marks) cudaEventRecord(marks[3], st);
-  if (launches) *launches += a.units ? 6 : 4;
+  if (launches) *launches += a.units ? 8 : 6;
   return cudaGetLastError();
 }
 cudaError_t decode_launch_exec(const DecodeArgs& a, cudaStream_t st, int* launches, cudaEvent_t* marks) {

@@ -27,8 +27,11 @@ struct DecodeArgs {
   u32* more;           // device counter, zeroed by the host before each pass (may be null: multi-frame items end after frame 1)
   // Block-parallel path for multi-block frames (zb_blocks.cuh).  units == nullptr switches it off.
   BlockUnit* units;    // decode_unit_arena_count() units; a slice uses the range that follows from its first dst_off / item_base
-  u32* par_list;       // one entry per item of the arena numbering: the slice's FI_PAR items, dense from par_list[item_base]
-  u32* cnt;            // four device counters of this launch (zeroed by decode_launch): [0] units, [1] FI_PAR items, [2] FI_SMALLHUF items
+  u32* par_list;       // four lists of list_stride entries each (arena numbering, dense from [item_base]): the launch's FI_PAR items,
+                       // then the items of the three sequence-kernel classes (FI_SEQ_A, FI_SEQ_B, full size)
+  u32 list_stride;
+  u32* cnt;            // eight device counters of this launch (zeroed by decode_launch): [0] units, [1] FI_PAR items, [2] FI_SMALLHUF,
+                       // [3] FI_SEQ_A, [4] FI_SEQ_B, [5] full-size items of the frame-serial path (each the length of its list)
   u16* huf_full;       // decode_huf_full_bytes(decode_huf_ctas()) of scratch for the Huffman kernels of THIS launch (launches
                        // that run concurrently on different streams need regions of their own)
 };

@@ -110,6 +110,7 @@ struct UnitEmitter {
     emit(ofBits, ofv, llSym, (llInfo[llSym] & 0xFFFFFF) + llv, (mlInfo[mlSym] & 0xFFFFFF) + mlv);
   }
   ZB_HD bool stopped() const { return dead; }
+  ZB_HD void defer() {}                      // (units always run with full-size tables)
   ZB_HD void block_end(u32, u32 runnable, bool bad) {
     u32 count = n - 1;
     if (bad && runnable < count) count = runnable;

@@ -29,7 +29,8 @@ enum : u32 {
   ZE_GENERIC = 1, ZE_prefix_unknown = 10, ZE_frameParameter_unsupported = 14, ZE_frameParameter_windowTooLarge = 16,
   ZE_corruption_detected = 20, ZE_checksum_wrong = 22, ZE_dictionary_corrupted = 30, ZE_dictionary_wrong = 32,
   ZE_tableLog_tooLarge = 44, ZE_maxSymbolValue_tooLarge = 46, ZE_maxSymbolValue_tooSmall = 48,
-  ZE_workSpace_tooSmall = 66, ZE_dstSize_tooSmall = 70, ZE_srcSize_wrong = 72, ZE_maxCode = 120
+  ZE_workSpace_tooSmall = 66, ZE_dstSize_tooSmall = 70, ZE_srcSize_wrong = 72, ZE_maxCode = 120,
+  ZB_TABLE_TOO_LARGE = 0xFFF0   // internal, never a result: a sequence table does not fit the space of this kernel instantiation
 };
 ZB_HD u32 zerr(u32 code) { return 0u - code; }
 ZB_HD bool is_err(u32 r) { return r > zerr(ZE_maxCode); }
@@ -51,6 +52,8 @@ static const u32 HUF_LONG = 0xFF00u;      // root cell: the codes under this pre
 enum : u32 { FI_CHECKSUM = 1, FI_FCS_KNOWN = 2, FI_DONE = 4 /* result[] already final, later stages skip the item */,
               FI_NEED_XXH = 8 /* set by the execute stage: verify the content checksum */,
               FI_SMALLHUF = 32 /* few literals: its Huffman table log is at most HUF_ROOT_SMALL with any known encoder: decoded by k_huf<HUF_ROOT_SMALL> */,
+              FI_SEQ_A = 64, FI_SEQ_B = 128 /* few sequences in the first block: sequence tables of at most 2^6 / 2^8 cells with any known
+                                               encoder: decoded by the k_seq instantiation with tables of that size (more frames per SM) */,
               FI_PAR = 16 /* multi-block frame decoded block-parallel: its compressed blocks are BlockUnits (zb_blocks.cuh) */ };
 struct FrameInfo {
   u32 flags;

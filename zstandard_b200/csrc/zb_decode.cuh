@@ -44,6 +44,7 @@ ZB_HD u32 sat_lpos(u32 lpos, u32 ll) { const u32 s = lpos + ll; return s > 0x3FF
 ZB_HD u64 seq_capacity(u64 cap) { return 2 * (cap / 3) + 24; }
 
 struct SeqTableSet {
+  u32 cap[3] = {9, 9, 9};   // table log each space can hold (KIND_LL, KIND_OF, KIND_ML); smaller in the kernels for frames of few sequences
   u16* space[3];            // lane-private cells for LL, OF, ML (index with *stride)
   u32 stride;
   const u16* defs[3];       // predefined tables, stride 1
@@ -143,10 +144,11 @@ struct SeqEmitter {
   u32 hdrSlot, dpos, lpos;        // the current block: its header slot, running output / literal positions
   u32 rep0, rep1, rep2;           // ZStdInternal.cs:111, ZStdDecompress.cs:2492
   bool dead;                      // the frame's first entropy-level error has been recorded: later blocks are ignored
+  bool deferred;                  // a table did not fit this instantiation's space: nothing of this attempt counts
   SeqFrameOut res;
   ZB_HD void init(SeqRec* o, u64 cap64, const u32* lli, const u32* mli) {
     out = o; cap = (u32)cap64; llInfo = lli; mlInfo = mli;        // seq_capacity of a u32 capacity fits 32 bits
-    n = 0; hdrSlot = 0; dpos = 0; lpos = 0; rep0 = 1; rep1 = 4; rep2 = 8; dead = false;
+    n = 0; hdrSlot = 0; dpos = 0; lpos = 0; rep0 = 1; rep1 = 4; rep2 = 8; dead = false; deferred = false;
     res.err_block = 0xFFFFFFFFu; res.err_code = 0; res.err_index = 0;
   }
   ZB_HD void set_reps(const u32* r) { rep0 = r[0]; rep1 = r[1]; rep2 = r[2]; }          // a dictionary's repeat offsets (:2436-2442)
@@ -171,6 +173,7 @@ struct SeqEmitter {
   }
   // true once the frame's first entropy-level error is recorded: the chain half stops (nothing it decodes is used)
   ZB_HD bool stopped() const { return dead; }
+  ZB_HD void defer() { deferred = true; }
   // bad = the bitstream failed (:1577, :1582 -> corruption_detected); runnable = how many of the block's sequences the
   // reference has executed by then (all that were decoded in the regular loop, four fewer in the look-ahead loop)
   ZB_HD void block_end(u32 blk, u32 runnable, bool bad) {
@@ -314,7 +317,8 @@ ZB_HD void seq_decode_frame(const u8* src, u32 size, u32 body_off, u64 window, S
         for (int k = 0; k < 3 && !e; k++) {
           int kind = kinds[k]; u32 used, lg = T.log[kind]; bool isDef = false;
           u32 m = modeOf[k];
-          e = read_seq_table(m, kind, sp + hdr, ssz - hdr, T.space[kind], T.stride, &lg, &isDef, haveRepeat, &used, norm, symbolNext);
+          e = read_seq_table(m, kind, sp + hdr, ssz - hdr, T.space[kind], T.stride, &lg, &isDef, haveRepeat, &used, norm, symbolNext, T.cap[kind]);
+          if (e == ZB_TABLE_TOO_LARGE) { sink.defer(); return; }                   // this frame belongs to the instantiation with full-size tables
           if (!e) {
             hdr += used;
             if (m != 3) {

@@ -274,8 +274,10 @@ ZB_HD void build_seq_table(u16* cells, u32 stride, NormT norm, u32 maxSV, u32 ta
 // On success *log = table log now in force for this kind, *used = header bytes.  `cells/stride` is the
 // lane-private table space; predefined tables live elsewhere (the caller switches pointers when *isDefault).
 template <class NormT, class NextT>
+// capLog: table log the space at `cells` can hold (the format's maximum unless a kernel instantiation keeps smaller tables):
+// a larger, otherwise valid table is reported as ZB_TABLE_TOO_LARGE before anything is written.
 ZB_HD u32 read_seq_table(u32 mode, int kind, const u8* p, u32 srcSize, u16* cells, u32 stride, u32* log, bool* isDefault,
-                         bool haveRepeat, u32* used, NormT norm, NextT symbolNext) {
+                         bool haveRepeat, u32* used, NormT norm, NextT symbolNext, u32 capLog = 9) {
   const u32 maxSym = kind == KIND_LL ? MaxLL : (kind == KIND_ML ? MaxML : MaxOff);
   const u32 maxLog = kind == KIND_LL ? LLFSELog : (kind == KIND_ML ? MLFSELog : OffFSELog);
   *used = 0;
@@ -294,6 +296,7 @@ ZB_HD u32 read_seq_table(u32 mode, int kind, const u8* p, u32 srcSize, u16* cell
       u32 e = read_ncount(norm, &max, &tl, p, srcSize, &h);
       if (e) return ZE_corruption_detected;                                        // :1070
       if (tl > maxLog) return ZE_corruption_detected;                              // :1071
+      if (tl > capLog) return ZB_TABLE_TOO_LARGE;
       build_seq_table(cells, stride, norm, max, tl, symbolNext);
       *log = tl; *isDefault = false; *used = h; return 0;
     }
