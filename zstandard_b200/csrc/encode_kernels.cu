@@ -1,7 +1,8 @@
 // encode_kernels.cu — sm_100a kernels of the batched zstd frame encoder.
 //
-//   k_enc_match<DFAST> : warp / frame    match finder: 32 consecutive (or strided) positions per step, one per lane;
-//                                        position hash table(s) in shared memory (u16 entries), in-window duplicate
+//   k_enc_match<DFAST> : warp / block    match finder: 32 consecutive (or strided) positions per step, one per lane;
+//                                        position hash table(s) of u16 entries in per-warp global scratch (L1 / L2
+//                                        resident; 32 one-warp CTAs per SM), in-window duplicate
 //                                        hashes resolved with __match_any_sync, candidates verified in parallel, the
 //                                        first hit wins (greedy parse), match length by warp ballot; sequence store
 //                                        and literals go to HBM scratch
@@ -27,6 +28,8 @@ static constexpr u32 kBlockSeqCap = BLOCKSIZE_MAX / 4 + 64;
 #define ENC_PRIME 16384u   // bytes before a block that prime its match tables (multiple of 32, <= BLOCKSIZE_MAX)
 
 struct BlockMeta { u32 nseq, nlits; };
+static constexpr u32 kGtabStride = 24 * 1024;   // bytes of global table space per match-stage warp: the largest tables of enc_hlog_*
+static constexpr u32 kGtabWarpsPerSm = 32;      // one-warp CTAs resident per SM (the hardware's CTA limit)
 
 __device__ __forceinline__ u8* lit_base(const EncodeArgs& a, const EncodeScratch& s, u32 f) { return s.lit + a.src_off[f] + 64ull * (a.item_base + f); }
 __device__ __forceinline__ u32* seq_base(const EncodeArgs& a, const EncodeScratch& s, u32 f) {
@@ -74,17 +77,26 @@ __device__ __forceinline__ u32 warp_extend(const u8* src, u32 a, u32 off, u32 en
 }
 
 template <bool DFAST>
-__global__ void __launch_bounds__(32) k_enc_match(EncodeArgs a, EncodeScratch sc, u32 hlogL, u32 hlogS, u32 mls) {
-  extern __shared__ __align__(16) u16 tab[];
-  u16* const tabL = tab; u16* const tabS = tab + (1u << hlogL);
-  const u32 lane = threadIdx.x;
+__global__ void __launch_bounds__(32) k_enc_match(EncodeArgs a, EncodeScratch sc, u32 hlogL, u32 hlogS, u32 mls, u16* gtab) {
+  extern __shared__ __align__(16) u16 tabShared[];
+  const u32 lane = threadIdx.x, warp = blockIdx.x, nWarps = gridDim.x;
   const u32 tw = (1u << hlogL) + (DFAST ? (1u << hlogS) : 0);
+  // gtab != nullptr (the default): the tables of this warp live in global scratch, kGtabStride bytes per warp, and the launch
+  // asks for no shared memory.  This kernel's throughput is its resident warp count (a serial chain per warp with a far
+  // memory round trip per sequence), and shared-memory tables bound that at 24 / 12 / 16 warps per SM (levels 1 / 2 / 3) and
+  // 9 for chunks above 128 KiB; 32 one-warp CTAs per SM keep 256-384 KB of tables in L1 / L2 instead.  Measured on 1 GiB of
+  // log text in 128 KiB chunks: 37.9 -> 28.8 ms (level 1), 60.1 -> 35.4 (level 2), 69.2 -> 50.5 (level 3); tick 1 MiB chunks
+  // 198 -> 111 ms.  At equal warp counts the two placements are within 6 % of each other; 40 / 48 / 64 warps per SM
+  // (two-warp CTAs, registers capped at 48 / 40 / 32) are slower than 32 on every shape but level-1 log text: the tables no
+  // longer stay in L1 (profiles/r2c_enc_match_tables.jsonl).
+  u16* const tab = gtab ? gtab + (size_t)warp * (kGtabStride / 2) : tabShared;
+  u16* const tabL = tab; u16* const tabS = tab + (1u << hlogL);
   // The unit of work is one BLOCK (<= 128 KiB) of one chunk: blocks of a chunk are matched independently, so a batch of
   // few large chunks spreads over as many warps as a batch of many small ones.  A block that is not the chunk's first
   // starts from a table primed with the ENC_PRIME bytes before it (the positions a table of this size would still
   // remember), and — as before — without repeat offsets.
   const u32 perChunk = a.max_src_size > BLOCKSIZE_MAX ? (a.max_src_size + BLOCKSIZE_MAX - 1) / BLOCKSIZE_MAX : 1;
-  for (u64 unit = blockIdx.x; unit < (u64)a.n * perChunk; unit += gridDim.x) {
+  for (u64 unit = warp; unit < (u64)a.n * perChunk; unit += nWarps) {
     const u32 f = (u32)(unit / perChunk), blk = (u32)(unit % perChunk), bpos = blk * BLOCKSIZE_MAX;
     const u8* src = a.src_base + a.src_off[f]; const u32 size = a.src_size[f];
     if (blk > 0 && bpos >= size) continue;
@@ -624,6 +636,7 @@ cudaError_t encode_alloc(EncodeScratch& s, size_t maxBatchBytes, size_t maxItems
 }
 void encode_free(EncodeScratch& s) {
   if (s.lit) cudaFree(s.lit); if (s.seq) cudaFree(s.seq); if (s.meta) cudaFree(s.meta); if (s.slots) cudaFree(s.slots);
+  for (auto& g : s.gtab) { if (g) cudaFree(g); g = nullptr; }
   s.lit = nullptr; s.seq = nullptr; s.meta = nullptr; s.slots = nullptr;
 }
 
@@ -656,14 +669,14 @@ cudaError_t encode_launch(const EncodeArgs& a, EncodeScratch& s, cudaStream_t st
   if (a.n == 0) return cudaSuccess;
   cudaError_t e = encode_lazy_alloc(s);
   if (e != cudaSuccess) return e;
-  // match stage: table sizes per level (u16 entries); as many resident warps as shared memory allows
+  // match stage: table sizes per level (u16 entries)
   const bool dfast = a.level >= 3;
   static const int envLog = getenv("ZSTDB200_ENC_HLOG") ? atoi(getenv("ZSTDB200_ENC_HLOG")) : 0;       // tuning aids
   static const int envPerSm = getenv("ZSTDB200_ENC_PERSM") ? atoi(getenv("ZSTDB200_ENC_PERSM")) : 0;
-  // Table sizes (u16 entries) trade ratio against resident warps, and this kernel's throughput is its warp count:
-  // level 1: 2^12 (8 KB, 24 warps/SM), level 2: 2^13 (16 KB, 12 warps/SM), level 3: 2^11 long + 2^12 short (12 KB, 16 warps/SM).
-  // Measured with the lock-step emulation (tests/hostsim): tick records stay within -2.4 % of libzstd at 128 KiB
-  // chunks, log text gains ratio with the smaller tables.
+  // level 1: 2^12 (8 KB), level 2: 2^13 (16 KB), level 3: 2^11 long + 2^12 short (12 KB); chunks above 128 KiB: enc_hlog_*.
+  // The sizes date from the shared-memory placement (24 / 12 / 16 warps per SM) and are kept: the ratio band is tested
+  // with them (lock-step emulation in tests/hostsim: tick records within -2.4 % of libzstd at 128 KiB chunks, log text
+  // gains ratio with the smaller tables) and 32 warps' tables still mostly fit L1.
   const bool big = a.max_src_size > BLOCKSIZE_MAX;
   const u32 hlogL = envLog ? (u32)envLog : enc_hlog_long(a.level, big), hlogS = envLog ? (u32)envLog - 1 : enc_hlog_short(a.level, big), mls = a.level <= 1 ? 6 : 5;
   const size_t smem = ((size_t)(1u << hlogL) + (dfast ? (1u << hlogS) : 0)) * 2;
@@ -671,10 +684,20 @@ cudaError_t encode_launch(const EncodeArgs& a, EncodeScratch& s, cudaStream_t st
   u32 perSm = (u32)((220 * 1024) / (smem + 1024)); if (perSm > capSm) perSm = capSm;
   const u64 units = (u64)a.n * (a.max_src_size > BLOCKSIZE_MAX ? (a.max_src_size + BLOCKSIZE_MAX - 1) / BLOCKSIZE_MAX : 1);
   u32 grid = (u32)s.sms * perSm; if (grid > units) grid = (u32)units;
-  if (marks) cudaEventRecord(marks[0], st);
-  if (dfast) k_enc_match<true><<<grid, 32, smem, st>>>(a, s, hlogL, hlogS, mls);
-  else k_enc_match<false><<<grid, 32, smem, st>>>(a, s, hlogL, hlogS, mls);
   const bool exclusive = a.stream_slot == ENC_EXCLUSIVE;
+  // Match tables in global scratch, one region per stream partition (ZSTDB200_ENC_GTAB=0: in shared memory, for A/B runs)
+  static const bool envGtab = !getenv("ZSTDB200_ENC_GTAB") || atoi(getenv("ZSTDB200_ENC_GTAB")) != 0;
+  u16* gtab = nullptr;
+  if (envGtab && smem <= kGtabStride) {
+    const u32 wps = envPerSm ? (envPerSm < (int)kGtabWarpsPerSm ? (u32)envPerSm : kGtabWarpsPerSm) : kGtabWarpsPerSm;
+    u8*& region = s.gtab[exclusive ? 0 : a.stream_slot % ENC_STREAM_PARTS];
+    if (!region && (e = cudaMalloc(&region, (size_t)s.sms * kGtabWarpsPerSm * kGtabStride)) != cudaSuccess) return e;
+    gtab = (u16*)region;
+    grid = (u32)s.sms * wps; if (grid > units) grid = (u32)units;
+  }
+  if (marks) cudaEventRecord(marks[0], st);
+  if (dfast) k_enc_match<true><<<grid, 32, gtab ? 0 : smem, st>>>(a, s, hlogL, hlogS, mls, gtab);
+  else k_enc_match<false><<<grid, 32, gtab ? 0 : smem, st>>>(a, s, hlogL, hlogS, mls, gtab);
   const u32 slot0 = exclusive ? 0 : (a.stream_slot % ENC_STREAM_PARTS) * kSlotsPerPart;
   const u32 maxSlots = exclusive ? s.entWarps : kSlotsPerPart;
   const u32 slots = a.n < maxSlots ? a.n : maxSlots;
