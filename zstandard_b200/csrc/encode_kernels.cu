@@ -2,7 +2,8 @@
 //
 //   k_enc_match<DFAST> : warp / block    match finder: 32 consecutive (or strided) positions per step, one per lane;
 //                                        position hash table(s) of u16 entries in per-warp global scratch (L1 / L2
-//                                        resident; 32 one-warp CTAs per SM), in-window duplicate
+//                                        resident; 32 one-warp CTAs per SM) or, for the concurrent slices of a host
+//                                        batch, in shared memory; in-window duplicate
 //                                        hashes resolved with __match_any_sync, candidates verified in parallel, the
 //                                        first hit wins (greedy parse), match length by warp ballot; sequence store
 //                                        and literals go to HBM scratch
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(32) k_enc_match(EncodeArgs a, EncodeScratch sc
   extern __shared__ __align__(16) u16 tabShared[];
   const u32 lane = threadIdx.x, warp = blockIdx.x, nWarps = gridDim.x;
   const u32 tw = (1u << hlogL) + (DFAST ? (1u << hlogS) : 0);
-  // gtab != nullptr (the default): the tables of this warp live in global scratch, kGtabStride bytes per warp, and the launch
+  // gtab != nullptr (launches that have the device to themselves): the tables of this warp live in global scratch, kGtabStride bytes per warp, and the launch
   // asks for no shared memory.  This kernel's throughput is its resident warp count (a serial chain per warp with a far
   // memory round trip per sequence), and shared-memory tables bound that at 24 / 12 / 16 warps per SM (levels 1 / 2 / 3) and
   // 9 for chunks above 128 KiB; 32 one-warp CTAs per SM keep 256-384 KB of tables in L1 / L2 instead.  Measured on 1 GiB of
@@ -636,8 +637,8 @@ cudaError_t encode_alloc(EncodeScratch& s, size_t maxBatchBytes, size_t maxItems
 }
 void encode_free(EncodeScratch& s) {
   if (s.lit) cudaFree(s.lit); if (s.seq) cudaFree(s.seq); if (s.meta) cudaFree(s.meta); if (s.slots) cudaFree(s.slots);
-  for (auto& g : s.gtab) { if (g) cudaFree(g); g = nullptr; }
-  s.lit = nullptr; s.seq = nullptr; s.meta = nullptr; s.slots = nullptr;
+  if (s.gtab) cudaFree(s.gtab);
+  s.lit = nullptr; s.seq = nullptr; s.meta = nullptr; s.slots = nullptr; s.gtab = nullptr;
 }
 
 static cudaError_t encode_lazy_alloc(EncodeScratch& s) {
@@ -685,14 +686,16 @@ cudaError_t encode_launch(const EncodeArgs& a, EncodeScratch& s, cudaStream_t st
   const u64 units = (u64)a.n * (a.max_src_size > BLOCKSIZE_MAX ? (a.max_src_size + BLOCKSIZE_MAX - 1) / BLOCKSIZE_MAX : 1);
   u32 grid = (u32)s.sms * perSm; if (grid > units) grid = (u32)units;
   const bool exclusive = a.stream_slot == ENC_EXCLUSIVE;
-  // Match tables in global scratch, one region per stream partition (ZSTDB200_ENC_GTAB=0: in shared memory, for A/B runs)
+  // Match tables in global scratch when the launch has the device to itself (ZSTDB200_ENC_GTAB=0: always in shared memory,
+  // for A/B runs).  Slices of a host batch run concurrently on several streams, and the entropy stage of one slice then
+  // shares SMs with the match stage of another: its 34 KB of shared memory per CTA shrink the L1 the tables would live in
+  // (measured: host-path level 1 19.1 -> 16.4 GB/s with global tables), so those launches keep their tables in shared memory.
   static const bool envGtab = !getenv("ZSTDB200_ENC_GTAB") || atoi(getenv("ZSTDB200_ENC_GTAB")) != 0;
   u16* gtab = nullptr;
-  if (envGtab && smem <= kGtabStride) {
+  if (envGtab && exclusive && smem <= kGtabStride) {
     const u32 wps = envPerSm ? (envPerSm < (int)kGtabWarpsPerSm ? (u32)envPerSm : kGtabWarpsPerSm) : kGtabWarpsPerSm;
-    u8*& region = s.gtab[exclusive ? 0 : a.stream_slot % ENC_STREAM_PARTS];
-    if (!region && (e = cudaMalloc(&region, (size_t)s.sms * kGtabWarpsPerSm * kGtabStride)) != cudaSuccess) return e;
-    gtab = (u16*)region;
+    if (!s.gtab && (e = cudaMalloc(&s.gtab, (size_t)s.sms * kGtabWarpsPerSm * kGtabStride)) != cudaSuccess) return e;
+    gtab = (u16*)s.gtab;
     grid = (u32)s.sms * wps; if (grid > units) grid = (u32)units;
   }
   if (marks) cudaEventRecord(marks[0], st);

@@ -29,7 +29,7 @@ struct EncodeScratch {
   u32* seq = nullptr;      // sequence stores (2 words per sequence)
   void* meta = nullptr;    // per block: sequence and literal counts
   u8* slots = nullptr;     // entropy-stage work areas (code arrays, FSE state tables), one per resident thread
-  u8* gtab[ENC_STREAM_PARTS] = {};   // match-stage hash tables, one region per stream partition (allocated when first used)
+  u8* gtab = nullptr;      // match-stage hash tables of launches that have the device to themselves (allocated when first used)
   size_t maxBytes = 0, maxItems = 0;
   int sms = 148;
   u32 entWarps = 0;       // entropy-stage warps resident on the device at once (set with the arenas)
