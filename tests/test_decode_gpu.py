@@ -3,7 +3,9 @@
 Bit-exact bar: decoded bytes and result codes (error codes included) equal the oracle's on the same inputs
 (integer/byte work, no tolerance) — also for corrupted frames, where the reference's 4-byte bit container reads
 garbage below the stream start before it notices (zb_decode.cuh "over-read emulation")."""
+import os
 import random
+import sys
 
 import numpy as np
 import pytest
@@ -491,3 +493,20 @@ def test_pinned_contiguous_buffers_take_the_direct_path_and_pageable_ones_the_st
     strided = np.zeros(2 * len(frames[0][1]), dtype=np.uint8)[::2]
     with pytest.raises(ValueError):
         gpu_ctx.decompress_batch([frames[0][0]], [strided])
+
+
+@pytest.mark.skipif(os.environ.get("ZSTDB200_TEST_INNER") == "1", reason="already inside the re-run")
+@pytest.mark.parametrize("a_max,b_max", [("1000000", "1000000"), ("0", "1000000")])
+def test_parity_suite_with_wrong_sequence_class_guesses(a_max, b_max):
+    """k_parse sends frames of few sequences to sequence-kernel instantiations with small tables; a frame whose tables do
+    not fit is handed to the full-size instantiation (k_seq_t, SeqEmitter::defer).  With real encoders that almost never
+    happens, so the oracle-parity tests of this file and of the dictionary suite run again with every frame starting in
+    the smallest (then in the middle) class: most 64 KiB frames are handed over, results must not change."""
+    import subprocess
+    env = dict(os.environ, ZSTDB200_SEQ_A_MAX=a_max, ZSTDB200_SEQ_B_MAX=b_max, ZSTDB200_TEST_INNER="1")
+    keep = ("valid_frames or edge_cases or fuzzed or several_data_frames or bad_item or golden or sequence_count or rle_literals "
+            "or repeat_mode or look_ahead or round_trip_properties or dictionary")
+    p = subprocess.run([sys.executable, "-m", "pytest", "tests/test_decode_gpu.py", "tests/test_dictionary.py", "-m", "gpu", "-x", "-q", "-k", keep],
+                       capture_output=True, text=True, env=env, cwd=helpers.ROOT, timeout=1500)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    assert " passed" in p.stdout and "no tests ran" not in p.stdout

@@ -206,6 +206,8 @@ enum class Op { Decompress, Compress };
 // on the frame-serial kernels (A/B measurements).  slot: the stream slot the launch runs on (its pair of counters).
 void with_units(Device& d, DecodeArgs& a, u32 slot, size_t ctx_items) {
   static const bool on = env_int("ZSTDB200_PAR", 1, 0, 1) != 0;
+  static const u32 seqAMax = (u32)env_int("ZSTDB200_SEQ_A_MAX", 512, 0, 0x7FFFFFFF), seqBMax = (u32)env_int("ZSTDB200_SEQ_B_MAX", 2048, 0, 0x7FFFFFFF);
+  a.seq_a_max = seqAMax; a.seq_b_max = seqBMax;
   a.huf_full = (u16*)(d.d_hufFull + d.hufFullBytes * slot);       // (every launch: the Huffman kernels' full-table scratch and the counters of this stream)
   a.cnt = d.d_cnt + 8 * slot; a.par_list = d.d_parList; a.list_stride = (u32)(ctx_items + 1);
   if (!on) return;

@@ -69,7 +69,7 @@ __device__ __forceinline__ int parse_one(const DecodeArgs& a, u32 i) {
       // <= 8 up to 2 048; a dictionary's tables are full size.  Wrong guesses are handed over (SeqEmitter::defer).
       u32 nbSeq, modes, hdr;
       if (!(a.dict && a.dict->hasEntropy) && !read_seq_count(src + fi.body_off + 3 + lh.consumed, bh.csize - lh.consumed, &nbSeq, &modes, &hdr))
-        cls = nbSeq <= 512 ? 1 : (nbSeq <= 2048 ? 2 : 0);
+        cls = nbSeq <= a.seq_a_max ? 1 : (nbSeq <= a.seq_b_max ? 2 : 0);
     }
     if (!(fi.flags & FI_PAR)) {
       if (cls == 1) fi.flags |= FI_SEQ_A; else if (cls == 2) fi.flags |= FI_SEQ_B;

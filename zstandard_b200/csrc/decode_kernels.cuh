@@ -32,6 +32,8 @@ struct DecodeArgs {
   u32 list_stride;
   u32* cnt;            // eight device counters of this launch (zeroed by decode_launch): [0] units, [1] FI_PAR items, [2] FI_SMALLHUF,
                        // [3] FI_SEQ_A, [4] FI_SEQ_B, [5] full-size items of the frame-serial path (each the length of its list)
+  u32 seq_a_max, seq_b_max;   // most sequences in a frame's first block for the sequence-kernel classes FI_SEQ_A / FI_SEQ_B (512 / 2 048;
+                       // ZSTDB200_SEQ_A_MAX / _B_MAX let tests force wrong guesses and so the hand-over to the full-size kernel)
   u16* huf_full;       // decode_huf_full_bytes(decode_huf_ctas()) of scratch for the Huffman kernels of THIS launch (launches
                        // that run concurrently on different streams need regions of their own)
 };
