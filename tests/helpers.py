@@ -83,6 +83,8 @@ class HostSim:
         h.hostsim_set_huf_root.argtypes = [ctypes.c_int]
         h.hostsim_set_seq_cap.argtypes = [ctypes.c_int]
         h.hostsim_deferred.restype = ctypes.c_int
+        h.hostsim_class_frames.argtypes = [ctypes.c_int]
+        h.hostsim_class_frames.restype = ctypes.c_int
         self.lib = h
 
     def set_par(self, on):

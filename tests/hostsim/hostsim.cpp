@@ -39,7 +39,8 @@ struct Sim {
 // mirrors k_huf for one frame; returns first failing block / code through fi
 // the replay's dictionary (hostsim_set_dict): what zstdb200_load_dictionary prepares on the device
 static DictState g_dict; static std::vector<u8> g_dictBytes; static bool g_haveDict = false;
-static u32 g_seqCap = 9; static int g_deferred = 0;   // hostsim_set_seq_cap: table log the sequence stage's first attempt has room for
+static u32 g_seqCap = 9; static int g_deferred = 0;   // hostsim_set_seq_cap: table log the sequence stage's first attempt has room for;
+static int g_classFrames[3] = {0, 0, 0};              // 0 = k_parse's own choice (first_block_classes): frames per class (full size, A, B)
 static u32 g_rootLog = HUF_ROOT_SMALL;   // hostsim_set_huf_root: the Huffman kernels run with root tables of 2^9 (small frames) or 2^11 cells
 static const DictState* cur_dict() { return g_haveDict ? &g_dict : nullptr; }
 
@@ -362,7 +363,13 @@ extern "C" uint32_t hostsim_decompress2(uint8_t* dst_in, uint32_t capAll, const 
     if (cur_dict()) em.set_reps(cur_dict()->rep);
     // the kernel instantiation with small tables first (k_seq_t<1 / 2>), the full-size one if it hands the frame over
     const bool dictTables = cur_dict() && cur_dict()->hasEntropy;
-    if (g_seqCap < 9 && !dictTables) { T.cap[0] = T.cap[1] = T.cap[2] = g_seqCap; }
+    if (g_seqCap == 0) {                                                           // as k_parse + the three k_seq_t instantiations do
+      bool few; u32 cls = first_block_classes(src + fi.body_off, size - fi.body_off, 512, 2048, &few);
+      if (dictTables) cls = 0;
+      g_classFrames[cls]++;
+      if (cls == 1) { T.cap[KIND_LL] = 6; T.cap[KIND_OF] = 6; T.cap[KIND_ML] = 7; }
+      else if (cls == 2) { T.cap[KIND_LL] = T.cap[KIND_OF] = T.cap[KIND_ML] = 8; }
+    } else if (g_seqCap < 9 && !dictTables) { T.cap[0] = T.cap[1] = T.cap[2] = g_seqCap; }
     seq_decode_frame(src, size, fi.body_off, fi.window, T, em, sim->llInfo, sim->mlInfo, normBuf, nextBuf, ringBuf, cur_dict());
     if (em.deferred) {
       g_deferred++;
@@ -386,6 +393,7 @@ extern "C" void hostsim_set_par(int on) { g_par = on; }
 extern "C" void hostsim_set_huf_root(int rootLog) { g_rootLog = (u32)rootLog; }
 extern "C" void hostsim_set_seq_cap(int capLog) { g_seqCap = (u32)capLog; }
 extern "C" int hostsim_deferred() { return g_deferred; }
+extern "C" int hostsim_class_frames(int cls) { return g_classFrames[cls]; }
 extern "C" int hostsim_par_frames() { return g_parFrames; }
 extern "C" uint32_t hostsim_decompress(uint8_t* dst, uint32_t cap, const uint8_t* src_in, uint32_t size, uint32_t* trailer_off, int* need_xxh) {
   uint32_t lastBase;

@@ -197,3 +197,30 @@ def test_small_sequence_tables_hand_larger_frames_over(hostsim, oracle):
     finally:
         hostsim.lib.hostsim_set_seq_cap(9)
     assert hostsim.lib.hostsim_deferred() - before > 20
+
+
+def test_sequence_class_guesses_hold_for_libzstd_frames(hostsim, oracle):
+    """k_parse's rule (zb_format.cuh first_block_classes): at most 512 sequences in the first block -> tables of at most
+    2^6 / 2^6 / 2^7 cells, at most 2 048 -> 2^8.  The rule is a performance guess, not a correctness condition; this test pins
+    that it IS right for libzstd frames of the benchmark's shapes (log text, tick records, mixed; 1-64 KiB; levels 1-19) -
+    no frame is handed over - that the small classes really get used, and that results equal the oracle's either way."""
+    from tools import corpus, zstd_ref
+    lib = hostsim.lib
+    base = [lib.hostsim_class_frames(c) for c in range(3)]
+    deferred = lib.hostsim_deferred()
+    lib.hostsim_set_seq_cap(0)
+    try:
+        for kind, total in (("log", 1 << 20), ("tick", 1 << 20), ("mixed", 1 << 19)):
+            raw = corpus.make(kind, total).tobytes()
+            for chunk, level in ((1024, 3), (4096, 1), (4096, 3), (4096, 19), (16384, 3), (16384, 9), (65536, 3), (65536, 19)):
+                for pos in range(0, min(total, 6 * chunk), chunk):
+                    data = raw[pos:pos + chunk]
+                    frame = zstd_ref.compress(data, level, checksum=True)
+                    ro, oo, _ = oracle.decompress(frame, len(data))
+                    assert (ro, oo) == (len(data), data)
+                    assert hostsim.decompress(frame, len(data), oracle) == (len(data), data), (kind, chunk, level, pos)
+    finally:
+        lib.hostsim_set_seq_cap(9)
+    used = [lib.hostsim_class_frames(c) - base[c] for c in range(3)]
+    assert used[1] > 20 and used[2] > 20 and used[0] > 20, used       # A, B and the full-size class all occur
+    assert lib.hostsim_deferred() == deferred, "a libzstd frame needed larger tables than its class provides"

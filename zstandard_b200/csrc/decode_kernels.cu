@@ -59,18 +59,12 @@ __device__ __forceinline__ int parse_one(const DecodeArgs& a, u32 i) {
   }
   int list = -1;
   if (go) {
-    // frames of few literals go to the Huffman kernel with the small root table (k_huf<HUF_ROOT_SMALL>) ...
-    BlockHdr bh; LitHdr lh; bool needs; u32 cls = 0;
-    if (!read_block_hdr(src + fi.body_off, a.src_size[i] - fi.body_off, bh) && bh.type == 2 && bh.csize < BLOCKSIZE_MAX &&
-        !read_lit_hdr(src + fi.body_off + 3, bh.csize, lh, &needs)) {
-      if (lh.type >= 2 && lh.litSize <= 2048) { fi.flags |= FI_SMALLHUF; atomicAdd(a.cnt + 2, 1u); }
-      // ... and frames of few sequences to a sequence kernel with small tables: an encoder picks table logs of at most
-      // max(highbit(nbSeq - 1) - 2, highbit(largest code) + 2), i.e. <= 6 / 6 / 7 (LL / OF / ML) up to 512 sequences and
-      // <= 8 up to 2 048; a dictionary's tables are full size.  Wrong guesses are handed over (SeqEmitter::defer).
-      u32 nbSeq, modes, hdr;
-      if (!(a.dict && a.dict->hasEntropy) && !read_seq_count(src + fi.body_off + 3 + lh.consumed, bh.csize - lh.consumed, &nbSeq, &modes, &hdr))
-        cls = nbSeq <= a.seq_a_max ? 1 : (nbSeq <= a.seq_b_max ? 2 : 0);
-    }
+    // frames of few literals go to the Huffman kernel with the small root table (k_huf<HUF_ROOT_SMALL>), frames of few
+    // sequences to a sequence kernel with small tables (a dictionary's tables are full size): zb_format.cuh
+    bool fewLiterals;
+    u32 cls = first_block_classes(src + fi.body_off, a.src_size[i] - fi.body_off, a.seq_a_max, a.seq_b_max, &fewLiterals);
+    if (fewLiterals) { fi.flags |= FI_SMALLHUF; atomicAdd(a.cnt + 2, 1u); }
+    if (a.dict && a.dict->hasEntropy) cls = 0;
     if (!(fi.flags & FI_PAR)) {
       if (cls == 1) fi.flags |= FI_SEQ_A; else if (cls == 2) fi.flags |= FI_SEQ_B;
       list = cls == 0 ? 2 : (int)cls - 1;                                           // lists / counters in the order A, B, full size

@@ -150,6 +150,22 @@ ZB_HD u32 read_seq_count(const u8* p, u32 srcSize, u32* nbSeq, u32* modes, u32* 
   return 0;
 }
 
+// What k_parse learns from a frame's FIRST block for the kernels' per-class launches (p = the block header, rem = bytes
+// left in the item).  *fewLiterals: compressed / treeless literals of at most 2 048 bytes (FI_SMALLHUF).  Returns the
+// sequence-kernel class: 1 (FI_SEQ_A) when the block has at most aMax sequences, 2 (FI_SEQ_B) at most bMax, 0 = full-size
+// tables (also when the block is raw / RLE or does not parse).  An encoder picks table logs of at most
+// max(highbit(nbSeq - 1) - 2, highbit(largest code) + 2), i.e. <= 6 / 6 / 7 (LL / OF / ML) up to 512 sequences and <= 8 up
+// to 2 048; a wrong guess is handed to the full-size kernel (SeqEmitter::defer).
+ZB_HD u32 first_block_classes(const u8* p, u32 rem, u32 aMax, u32 bMax, bool* fewLiterals) {
+  *fewLiterals = false;
+  BlockHdr bh; LitHdr lh; bool needs;
+  if (read_block_hdr(p, rem, bh) || bh.type != 2 || bh.csize >= BLOCKSIZE_MAX || read_lit_hdr(p + 3, bh.csize, lh, &needs)) return 0;
+  *fewLiterals = lh.type >= 2 && lh.litSize <= 2048;
+  u32 nbSeq, modes, hdr;
+  if (read_seq_count(p + 3 + lh.consumed, bh.csize - lh.consumed, &nbSeq, &modes, &hdr)) return 0;
+  return nbSeq <= aMax ? 1 : (nbSeq <= bMax ? 2 : 0);
+}
+
 // =====================================================================================================
 // FSE normalized counts (ReadNCount, EntropyCommon.cs:79-188).  Index arithmetic in i32 relative to hb.
 // =====================================================================================================
