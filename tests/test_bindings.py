@@ -130,3 +130,72 @@ def test_java_golden_vector_through_the_jni_glue_and_the_mirror(glue, oracle):
         assert dec.decompress(b"zz" + frame, 2, len(frame), out, 4, len(raw)) == len(raw) and bytes(out[4:]) == raw
     with pytest.raises(RuntimeError, match="corruption_detected|checksum_wrong|srcSize_wrong|dstSize_tooSmall"):
         dec.decompress(bytes(frames[3]), 0, len(frames[3]), bytearray(len(items[3][1])), 0, len(items[3][1]))
+
+
+# ---- C# (P/Invoke) surface: bindings/csharp/ZStdB200.cs -------------------------------------------------
+# No .NET SDK exists in this image either.  The shim is thin (pin, call, return the code), so what can go wrong without a
+# compiler is the marshalling: a wrong entry-point name, argument count, or argument width.  This checks every
+# [DllImport] declaration against the prototype in include/zstdb200.h.
+_C_WIDTH = {"int": "i32", "uint32_t": "u32", "uint64_t": "u64", "size_t": "ptr", "void": "void"}
+_CS_WIDTH = {"int": "i32", "uint": "u32", "ulong": "u64", "UIntPtr": "ptr", "IntPtr": "ptr", "void": "void"}
+
+
+def _c_kind(t):
+    t = t.replace("const", " ").strip()
+    if "*" in t:
+        return "ptr"
+    return _C_WIDTH[t.split()[0]]
+
+
+def _cs_kind(t):
+    t = t.replace("out ", " ").strip() if not t.startswith("out ") else "IntPtr*"
+    if "*" in t:
+        return "ptr"
+    return _CS_WIDTH[t.split()[0]]
+
+
+def _header_prototypes():
+    import re
+    text = open(os.path.join(ROOT, "include", "zstdb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    protos = {}
+    for m in re.finditer(r"([A-Za-z_][A-Za-z_0-9 \*]*?)\b(zstdb200_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        ret, name, args = m.group(1).strip(), m.group(2), " ".join(m.group(3).split())
+        params = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+        kinds = []
+        for prm in params:
+            ty = prm.rsplit(" ", 1)[0] if not prm.endswith("*") else prm        # drop the parameter name
+            if "*" in prm:
+                ty = prm
+            kinds.append(_c_kind(ty))
+        protos[name] = (_c_kind(ret), kinds)
+    return protos
+
+
+def test_csharp_pinvoke_declarations_match_the_header():
+    import re
+    src = open(os.path.join(ROOT, "bindings", "csharp", "ZStdB200.cs")).read()
+    decls = re.findall(r"\[DllImport\(Lib\)\]\s*internal static extern\s+([A-Za-z\*]+)\s+(zstdb200_[a-z_0-9]+)\(([^)]*)\);", src)
+    assert len(decls) >= 14
+    protos = _header_prototypes()
+    import zstandard_b200 as zb
+    lib = zb.load_library()
+    for ret, name, args in decls:
+        assert name in protos and hasattr(lib, name), name
+        params = [a.strip() for a in args.split(",")] if args.strip() else []
+        kinds = []
+        for prm in params:
+            ty = prm.rsplit(" ", 1)[0]
+            kinds.append("ptr" if (ty.startswith("out ") or "*" in ty) else _CS_WIDTH[ty])
+        c_ret, c_kinds = protos[name]
+        assert _cs_kind(ret) == c_ret, (name, ret, c_ret)
+        assert kinds == c_kinds, (name, kinds, c_kinds)
+    # the public surface keeps the reference's method names and adds the batched overloads (ZStdDecompress.cs:590-607, 2182-2191)
+    for sig in ("public static ulong GetDecompressedSize(byte[] src)", "public static ulong GetDecompressedSize(byte[] src, uint srcSize)",
+                "public static uint Decompress(byte[] dst, uint dstCapacity, byte[] src, uint srcSize)", "public static uint Decompress(byte[] dst, byte[] src)",
+                "public static void Decompress(IReadOnlyList<ArraySegment<byte>> srcs, IReadOnlyList<ArraySegment<byte>> dsts, uint[] results)",
+                "public static void Compress(IReadOnlyList<ArraySegment<byte>> srcs, IReadOnlyList<ArraySegment<byte>> dsts, uint[] results, int level = 3, bool checksum = true)"):
+        assert sig in src, sig
+    proj = open(os.path.join(ROOT, "bindings", "csharp", "Zstandard.B200.csproj")).read()
+    assert "<TargetFramework>netstandard2.0</TargetFramework>" in proj and "NativeMemory." not in src and "Span<" not in src
