@@ -203,7 +203,9 @@ std::vector<Range> make_subbatches(size_t n, size_t maxIn, size_t maxOut, size_t
 enum class Op { Decompress, Compress };
 
 // Switches a launch to the block-parallel path for multi-block frames (zb_blocks.cuh); ZSTDB200_PAR=0 keeps every frame
-// on the frame-serial kernels (A/B measurements).  slot: the stream slot the launch runs on (its pair of counters).
+// on the frame-serial kernels (A/B measurements).  Also hands every launch its per-stream scratch: slot = the stream slot
+// the launch runs on (its eight counters, its Huffman full-table region); the item lists are indexed by item_base, so
+// slices of one sub-batch that run concurrently use disjoint ranges of them.
 void with_units(Device& d, DecodeArgs& a, u32 slot, size_t ctx_items) {
   static const bool on = env_int("ZSTDB200_PAR", 1, 0, 1) != 0;
   static const u32 seqAMax = (u32)env_int("ZSTDB200_SEQ_A_MAX", 512, 0, 0x7FFFFFFF), seqBMax = (u32)env_int("ZSTDB200_SEQ_B_MAX", 2048, 0, 0x7FFFFFFF);
