@@ -82,8 +82,8 @@ __global__ void __launch_bounds__(32) k_enc_match(EncodeArgs a, EncodeScratch sc
   extern __shared__ __align__(16) u16 tabShared[];
   const u32 lane = threadIdx.x, warp = blockIdx.x, nWarps = gridDim.x;
   const u32 tw = (1u << hlogL) + (DFAST ? (1u << hlogS) : 0);
-  // gtab != nullptr (launches that have the device to themselves): the tables of this warp live in global scratch, kGtabStride bytes per warp, and the launch
-  // asks for no shared memory.  This kernel's throughput is its resident warp count (a serial chain per warp with a far
+  // gtab != nullptr (launches that have the device to themselves): the tables of this warp live in global scratch,
+  // kGtabStride bytes per warp, and the launch asks for no shared memory.  This kernel's throughput is its resident warp count (a serial chain per warp with a far
   // memory round trip per sequence), and shared-memory tables bound that at 24 / 12 / 16 warps per SM (levels 1 / 2 / 3) and
   // 9 for chunks above 128 KiB; 32 one-warp CTAs per SM keep 256-384 KB of tables in L1 / L2 instead.  Measured on 1 GiB of
   // log text in 128 KiB chunks: 37.9 -> 28.8 ms (level 1), 60.1 -> 35.4 (level 2), 69.2 -> 50.5 (level 3); tick 1 MiB chunks
@@ -694,9 +694,10 @@ cudaError_t encode_launch(const EncodeArgs& a, EncodeScratch& s, cudaStream_t st
   u16* gtab = nullptr;
   if (envGtab && exclusive && smem <= kGtabStride) {
     const u32 wps = envPerSm ? (envPerSm < (int)kGtabWarpsPerSm ? (u32)envPerSm : kGtabWarpsPerSm) : kGtabWarpsPerSm;
-    if (!s.gtab && (e = cudaMalloc(&s.gtab, (size_t)s.sms * kGtabWarpsPerSm * kGtabStride)) != cudaSuccess) return e;
-    gtab = (u16*)s.gtab;
-    grid = (u32)s.sms * wps; if (grid > units) grid = (u32)units;
+    if (!s.gtab && cudaMalloc(&s.gtab, (size_t)s.sms * kGtabWarpsPerSm * kGtabStride) != cudaSuccess) {
+      cudaGetLastError(); s.gtab = nullptr;                      // no room for the 113 MB: this launch keeps shared-memory tables
+    }
+    if (s.gtab) { gtab = (u16*)s.gtab; grid = (u32)s.sms * wps; if (grid > units) grid = (u32)units; }
   }
   if (marks) cudaEventRecord(marks[0], st);
   if (dfast) k_enc_match<true><<<grid, 32, gtab ? 0 : smem, st>>>(a, s, hlogL, hlogS, mls, gtab);
